@@ -1,0 +1,164 @@
+"""Generate the golden vectors under tests/golden/ from the REAL reference.
+
+Run in the build container only (needs /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The reference (pure PyTorch, /root/reference/framework/STC_GNN.py) is imported unmodified and
+evaluated in fp64 (and fp32, for the record) on seeded inputs whose values are exactly
+representable in fp32, so the GPU fp32 path and the fp64 oracle see identical inputs.
+The reference has no tests or golden vectors of its own; these files are the pin.
+
+Files written (all ``np.savez_compressed``):
+  cell_<name>.npz   one STC_Cell forward + every gradient (STC_GNN.py:65-79 through autograd)
+  stack_sf.npz      encoder(2 layers x T=9) + decoder(horizon 3) roll-out on real SF data with the
+                    MGP_Gen-produced (denormal-laden) supports, outputs + gradients
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("STC_REF_DIR", "/root/reference/framework")
+DATA = os.path.join(os.path.dirname(REF), "data", "SF-incidents-4h.npz")
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+
+import STC_GNN as ref  # noqa: E402
+
+
+def f32exact(t):
+    return t.float().double()
+
+
+def gz(t):
+    """gradient as numpy, zeros when autograd never touched the tensor (Ks=1 / Kc=1: support unused)."""
+    return (t.grad if t.grad is not None else torch.zeros_like(t)).numpy()
+
+
+def run_cell(name, B, N, C, Din, h, Ks, Kc, use_bias=True, act=None, seed=0, Gs=None, Gc=None, Xt=None,
+             bias_scale=0.1, strided_T=None):
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    torch.set_default_dtype(torch.float64)
+    activation = {None: None, "relu": torch.nn.ReLU}[act]
+    cell = ref.STC_Cell(N, C, Ks, Kc, Din, h, use_bias=use_bias, activation=activation)
+    with torch.no_grad():
+        for p in cell.parameters():
+            p.copy_(f32exact(p))
+        if use_bias:
+            cell.gates.b.copy_(f32exact(torch.randn(2 * h, generator=g) * bias_scale))
+            cell.candi.b.copy_(f32exact(torch.randn(h, generator=g) * bias_scale))
+    if Gs is None:
+        Gs = torch.rand(N, N, generator=g) * (2.0 / N)
+    if Gc is None:
+        Gc = torch.rand(C, C, generator=g) * (2.0 / C)
+    Gs = f32exact(Gs).requires_grad_(True)
+    Gc = f32exact(Gc).requires_grad_(True)
+    if Xt is None:
+        if strided_T is not None:
+            # the encoder hands the cell a [:, t] view whose batch stride is non-standard (STC_GNN.py:111)
+            seq = f32exact(torch.randn(B, strided_T, N, C, Din, generator=g))
+            Xt = seq[:, 1]
+        else:
+            Xt = f32exact(torch.randn(B, N, C, Din, generator=g))
+    Xt = Xt.clone().requires_grad_(True)
+    H = f32exact(torch.randn(B, N, C, h, generator=g) * 0.5).requires_grad_(True)
+    dHn = f32exact(torch.randn(B, N, C, h, generator=g))
+
+    Hn = cell(Gs=Gs, Gc=Gc, Xt=Xt, Ht_1=H)
+    Hn.backward(dHn)
+    out = dict(
+        meta=np.array([B, N, C, Din, h, Ks, Kc, int(use_bias), 1 if act == "relu" else 0], dtype=np.int64),
+        Gs=Gs.detach().float().numpy(), Gc=Gc.detach().float().numpy(),
+        Xt=Xt.detach().float().numpy(), H=H.detach().float().numpy(), dHn=dHn.float().numpy(),
+        Wg=cell.gates.W.detach().float().numpy(), Wc=cell.candi.W.detach().float().numpy(),
+        Hn=Hn.detach().numpy(), dGs=gz(Gs), dGc=gz(Gc), dXt=Xt.grad.numpy(), dH=H.grad.numpy(),
+        dWg=cell.gates.W.grad.numpy(), dWc=cell.candi.W.grad.numpy(),
+    )
+    if use_bias:
+        out.update(bg=cell.gates.b.detach().float().numpy(), bc=cell.candi.b.detach().float().numpy(),
+                   dbg=cell.gates.b.grad.numpy(), dbc=cell.candi.b.grad.numpy())
+    # the reference evaluated in its native fp32, for the record (noise floor of the reference itself)
+    torch.set_default_dtype(torch.float32)
+    cell32 = ref.STC_Cell(N, C, Ks, Kc, Din, h, use_bias=use_bias, activation=activation)
+    cell32.load_state_dict({k: v.float() for k, v in cell.state_dict().items()})
+    Hn32 = cell32(Gs=Gs.detach().float(), Gc=Gc.detach().float(), Xt=Xt.detach().float(), Ht_1=H.detach().float())
+    out["Hn_ref_fp32"] = Hn32.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, f"cell_{name}.npz"), **out)
+    print(f"cell_{name}: |Hn|={Hn.abs().mean():.4f} fp32-vs-fp64 max {np.abs(out['Hn_ref_fp32'] - out['Hn']).max():.2e}")
+
+
+def sf_supports_and_data(B=2):
+    """Real SF data slice and the supports the real MGP_Gen produces from it (denormal-laden Gs)."""
+    d = np.load(DATA)
+    inc = torch.from_numpy(d["incident"].reshape(d["incident"].shape[0], 100, 5).astype(np.float32))
+    As = torch.from_numpy(d["s_adj"]).float()
+    Ac = torch.from_numpy(d["c_cor"]).float()
+    T = 9
+    # supports come from a full training batch of 32 windows (Data_Container.py:107-112), as in a real
+    # forward: the batch/time-summed scores (STC_GNN.py:231-232) are large enough that the softmax
+    # underflows into zeros and fp32 denormals; only B windows are kept as cell inputs.
+    X32 = torch.stack([inc[i:i + T] for i in range(32)], dim=0)             # [32,T,N,C]
+    torch.set_default_dtype(torch.float32)
+    torch.manual_seed(0)
+    mgp = ref.MGP_Gen(100, 5, 16)
+    with torch.no_grad():
+        Gs, Gc = mgp(X32, As, Ac)
+    return X32[:B].clone(), Gs.detach(), Gc.detach()
+
+
+def run_stack(X_seq, Gs, Gc):
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(1)
+    N, C, h, Ks, Kc, layers, horizon = 100, 5, 16, 2, 2, 2, 3
+    enc = ref.STC_Encoder(N, C, Ks, Kc, 1, h, layers)
+    dec = ref.STC_Decoder(N, C, Ks, Kc, h, h, layers, horizon)
+    with torch.no_grad():
+        for p in list(enc.parameters()) + list(dec.parameters()):
+            p.copy_(f32exact(p))
+    Gs = f32exact(Gs).requires_grad_(True)
+    Gc = f32exact(Gc).requires_grad_(True)
+    X = f32exact(X_seq).unsqueeze(-1).requires_grad_(True)
+    _, Ht = enc(Gs=Gs, Gc=Gc, X_seq=X, H0_l=None)
+    inp = Ht[-1]
+    outs = []
+    for _ in range(horizon):
+        Hl, Ht = dec(Gs=Gs, Gc=Gc, Xt=inp, H0_l=Ht)
+        inp = Hl
+        outs.append(Hl)
+    out = torch.stack(outs, dim=1)
+    g = torch.Generator().manual_seed(2)
+    dOut = f32exact(torch.randn(out.shape, generator=g))
+    out.backward(dOut)
+    save = dict(meta=np.array([X.shape[0], 9, N, C, 1, h, Ks, Kc, layers, horizon], dtype=np.int64),
+                X_seq=X.detach().float().numpy(), Gs=Gs.detach().float().numpy(), Gc=Gc.detach().float().numpy(),
+                dOut=dOut.float().numpy(), out=out.detach().numpy(), dGs=Gs.grad.numpy(), dGc=Gc.grad.numpy(),
+                dX_seq=X.grad.numpy())
+    for tag, mod in (("enc", enc), ("dec", dec)):
+        for i, cell in enumerate(mod.cell_list):
+            for conv in ("gates", "candi"):
+                for pn in ("W", "b"):
+                    p = getattr(getattr(cell, conv), pn)
+                    save[f"{tag}{i}_{conv}_{pn}"] = p.detach().float().numpy()
+                    save[f"d_{tag}{i}_{conv}_{pn}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "stack_sf.npz"), **save)
+    den = ((Gs.detach().float().abs() < 1.1754944e-38) & (Gs.detach() != 0)).float().mean().item()
+    print(f"stack_sf: out mean|.|={out.abs().mean():.4f}; Gs denormal fraction {den:.3f}, "
+          f"zero fraction {(Gs.detach() == 0).float().mean():.3f}")
+
+
+if __name__ == "__main__":
+    run_cell("tiny", B=2, N=7, C=3, Din=1, h=4, Ks=2, Kc=2, seed=1)
+    run_cell("k33", B=2, N=9, C=4, Din=3, h=5, Ks=3, Kc=3, seed=2)
+    run_cell("k42_relu", B=1, N=8, C=2, Din=2, h=4, Ks=4, Kc=2, act="relu", seed=3)
+    run_cell("k24_nobias", B=3, N=5, C=6, Din=2, h=3, Ks=2, Kc=4, use_bias=False, seed=4)
+    run_cell("k11", B=2, N=6, C=3, Din=2, h=4, Ks=1, Kc=1, seed=5)
+    run_cell("strided", B=3, N=10, C=5, Din=1, h=8, Ks=2, Kc=2, seed=6, strided_T=4)
+    X_seq, Gs, Gc = sf_supports_and_data(B=2)
+    run_cell("sf_din1", B=2, N=100, C=5, Din=1, h=16, Ks=2, Kc=2, seed=7, Gs=Gs, Gc=Gc,
+             Xt=f32exact(X_seq[:, 3]).unsqueeze(-1))
+    run_cell("sf_din16", B=2, N=100, C=5, Din=16, h=16, Ks=2, Kc=2, seed=8, Gs=Gs, Gc=Gc)
+    run_stack(X_seq, Gs, Gc)

@@ -1,0 +1,61 @@
+"""Shared test helpers: golden loading and seeded case construction."""
+import glob
+import os
+
+import numpy as np
+import torch
+
+from oracle import stc_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CELL_CASES = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN, "cell_*.npz")))
+GRAD_KEYS = ("dXt", "dH", "dWg", "dWc", "dbg", "dbc", "dGs", "dGc")
+
+
+def load_cell(name):
+    z = np.load(os.path.join(GOLDEN, f"cell_{name}.npz"))
+    B, N, C, Din, h, Ks, Kc, use_bias, relu = (int(v) for v in z["meta"])
+    cfg = dict(B=B, N=N, C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, use_bias=bool(use_bias), activation="relu" if relu else None)
+    t = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    return cfg, t
+
+
+def load_stack():
+    z = np.load(os.path.join(GOLDEN, "stack_sf.npz"))
+    B, T, N, C, Din, h, Ks, Kc, layers, horizon = (int(v) for v in z["meta"])
+    cfg = dict(B=B, T=T, N=N, C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, layers=layers, horizon=horizon)
+    t = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    return cfg, t
+
+
+def random_case(B, N, C, Din, h, Ks, Kc, seed=0, use_bias=True, sparse_frac=None, dtype=torch.float64):
+    """Seeded inputs with fp32-exact values. ``sparse_frac`` zeroes that fraction of Gs (for CSR tests)."""
+    g = torch.Generator().manual_seed(seed)
+    f = lambda t: t.float().to(dtype)
+    Gs = torch.rand(N, N, generator=g) * (2.0 / max(N, 1))
+    if sparse_frac is not None:
+        Gs = Gs * (torch.rand(N, N, generator=g) >= sparse_frac) * (1.0 / max(1e-3, 1.0 - sparse_frac))
+    Gc = torch.rand(C, C, generator=g) * (2.0 / C)
+    p = O.xavier_cell_params(Din, h, Ks, Kc, g, dtype=torch.float32, use_bias=use_bias, bias_scale=0.1)
+    case = dict(Gs=f(Gs), Gc=f(Gc), Xt=f(torch.randn(B, N, C, Din, generator=g)),
+                H=f(torch.randn(B, N, C, h, generator=g) * 0.5), dHn=f(torch.randn(B, N, C, h, generator=g)),
+                Wg=f(p.Wg), Wc=f(p.Wc), bg=f(p.bg) if use_bias else None, bc=f(p.bc) if use_bias else None)
+    return case
+
+
+def oracle_cell_with_grads(t, cfg, dtype=torch.float64):
+    """Run the lean oracle through autograd; returns (Hn, grads dict)."""
+    names = ["Gs", "Gc", "Xt", "H", "Wg", "Wc"] + (["bg", "bc"] if t.get("bg") is not None else [])
+    v = {}
+    for k in names:
+        x = t[k]
+        x = x.to_dense() if x.layout != torch.strided else x
+        v[k] = x.to(dtype).clone().requires_grad_(True)
+    Hn = O.stc_cell(v["Gs"], v["Gc"], v["Xt"], v["H"], v["Wg"], v.get("bg"), v["Wc"], v.get("bc"),
+                    cfg["Ks"], cfg["Kc"], cfg.get("activation"))
+    Hn.backward(t["dHn"].to(dtype))
+    z = lambda k: v[k].grad if v[k].grad is not None else torch.zeros_like(v[k])
+    grads = dict(dXt=z("Xt"), dH=z("H"), dWg=z("Wg"), dWc=z("Wc"), dGs=z("Gs"), dGc=z("Gc"))
+    if "bg" in v:
+        grads.update(dbg=z("bg"), dbc=z("bc"))
+    return Hn.detach(), grads

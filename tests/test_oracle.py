@@ -1,0 +1,132 @@
+"""CPU tests: the oracle (oracle/stc_oracle.py) against the golden vectors generated from the real
+reference (tests/golden/make_golden.py), against its own analytic backward, and -- when the reference
+tree is present (build container only) -- against the live reference."""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import stc_oracle as O
+from tests.helpers import CELL_CASES, GRAD_KEYS, load_cell, load_stack, oracle_cell_with_grads, random_case
+
+REF_DIR = os.environ.get("STC_REF_DIR", "/root/reference/framework")
+
+
+def test_golden_files_present():
+    assert len(CELL_CASES) >= 8, CELL_CASES
+
+
+@pytest.mark.parametrize("name", CELL_CASES)
+def test_oracle_matches_golden_cell(name):
+    cfg, t = load_cell(name)
+    Hn, grads = oracle_cell_with_grads(t, cfg)
+    # fp64 vs fp64: only summation order differs -> 1e-9 relative
+    O.assert_close(Hn, t["Hn"], f"{name}:Hn", rtol=1e-9, atol_scale=1e-10)
+    for k in GRAD_KEYS:
+        if k in t:
+            O.assert_close(grads[k], t[k], f"{name}:{k}", rtol=1e-9, atol_scale=1e-9)
+
+
+@pytest.mark.parametrize("name", CELL_CASES)
+def test_analytic_backward_matches_golden(name):
+    cfg, t = load_cell(name)
+    d = lambda k: t[k].double() if k in t else None
+    g = O.stc_cell_backward(d("Gs"), d("Gc"), d("Xt"), d("H"), d("Wg"), d("bg"), d("Wc"), d("bc"),
+                            cfg["Ks"], cfg["Kc"], d("dHn"), cfg["activation"])
+    for k in GRAD_KEYS:
+        if k in t:
+            O.assert_close(g[k], t[k], f"{name}:{k}", rtol=1e-9, atol_scale=1e-9)
+
+
+@pytest.mark.parametrize("name", ["tiny", "k33", "sf_din16"])
+def test_refshape_matches_lean(name):
+    cfg, t = load_cell(name)
+    d = lambda k: t[k].double() if k in t else None
+    a = O.stc_cell_refshape(d("Gs"), d("Gc"), d("Xt"), d("H"), d("Wg"), d("bg"), d("Wc"), d("bc"),
+                            cfg["Ks"], cfg["Kc"], cfg["activation"])
+    O.assert_close(a, t["Hn"], name, rtol=1e-9, atol_scale=1e-10)
+
+
+def test_reference_fp32_noise_floor_is_inside_tolerance():
+    """The tolerance must at least admit the reference's own fp32 evaluation."""
+    for name in CELL_CASES:
+        _, t = load_cell(name)
+        O.assert_close(t["Hn_ref_fp32"], t["Hn"], name)
+
+
+def test_sparse_support_equals_dense():
+    cfg = dict(B=2, N=40, C=3, Din=2, h=4, Ks=4, Kc=2)
+    t = random_case(**cfg, seed=11, sparse_frac=0.8)
+    a = O.stc_cell(t["Gs"], t["Gc"], t["Xt"], t["H"], t["Wg"], t["bg"], t["Wc"], t["bc"], 4, 2)
+    b = O.stc_cell(t["Gs"].to_sparse_csr(), t["Gc"], t["Xt"], t["H"], t["Wg"], t["bg"], t["Wc"], t["bc"], 4, 2)
+    O.assert_close(b, a, "csr", rtol=1e-12, atol_scale=1e-12)
+    g1 = O.stc_cell_backward(t["Gs"], t["Gc"], t["Xt"], t["H"], t["Wg"], t["bg"], t["Wc"], t["bc"], 4, 2, t["dHn"])
+    g2 = O.stc_cell_backward(t["Gs"].to_sparse_csr(), t["Gc"], t["Xt"], t["H"], t["Wg"], t["bg"], t["Wc"],
+                             t["bc"], 4, 2, t["dHn"])
+    for k in ("dXt", "dH", "dWg", "dWc", "dGc"):
+        O.assert_close(g2[k], g1[k], k, rtol=1e-11, atol_scale=1e-11)
+    assert g2["dGs"] is None
+
+
+def test_stack_matches_golden():
+    cfg, t = load_stack()
+    enc, dec, leaves = [], [], {}
+    for tag, lst in (("enc", enc), ("dec", dec)):
+        for i in range(cfg["layers"]):
+            ps = []
+            for conv in ("gates", "candi"):
+                for pn in ("W", "b"):
+                    k = f"{tag}{i}_{conv}_{pn}"
+                    leaves[k] = t[k].double().requires_grad_(True)
+                    ps.append(leaves[k])
+            lst.append(O.CellParams(*ps))
+    Gs = t["Gs"].double().requires_grad_(True)
+    Gc = t["Gc"].double().requires_grad_(True)
+    X = t["X_seq"].double().requires_grad_(True)
+    out = O.stack_forward(Gs, Gc, X, enc, dec, cfg["horizon"], cfg["Ks"], cfg["Kc"])
+    O.assert_close(out, t["out"], "stack out", rtol=1e-9, atol_scale=1e-10)
+    out.backward(t["dOut"].double())
+    O.assert_close(Gs.grad, t["dGs"], "dGs", rtol=1e-8, atol_scale=1e-9)
+    O.assert_close(Gc.grad, t["dGc"], "dGc", rtol=1e-8, atol_scale=1e-9)
+    O.assert_close(X.grad, t["dX_seq"], "dX_seq", rtol=1e-8, atol_scale=1e-9)
+    for k, v in leaves.items():
+        O.assert_close(v.grad, t["d_" + k], k, rtol=1e-8, atol_scale=1e-9)
+
+
+def test_grid_adjacency_matches_shipped_shape():
+    A = O.grid_adjacency(10, 10)
+    assert int(A.sum()) == 684 and bool((A == A.t()).all()) and float(A.diagonal().abs().sum()) == 0.0
+    assert sorted(set(A.sum(1).tolist())) == [3.0, 5.0, 8.0]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DIR), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("Ks,Kc,act", [(2, 2, None), (3, 2, "relu"), (4, 3, None)])
+def test_oracle_matches_live_reference(Ks, Kc, act):
+    sys.dont_write_bytecode = True
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import STC_GNN as ref
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        cfg = dict(B=2, N=11, C=4, Din=3, h=6, Ks=Ks, Kc=Kc)
+        t = random_case(**cfg, seed=Ks * 10 + Kc)
+        cell = ref.STC_Cell(11, 4, Ks, Kc, 3, 6, activation=torch.nn.ReLU if act else None)
+        with torch.no_grad():
+            cell.gates.W.copy_(t["Wg"]); cell.gates.b.copy_(t["bg"])
+            cell.candi.W.copy_(t["Wc"]); cell.candi.b.copy_(t["bc"])
+        leaves = {k: t[k].clone().requires_grad_(True) for k in ("Gs", "Gc", "Xt", "H")}
+        Hn = cell(Gs=leaves["Gs"], Gc=leaves["Gc"], Xt=leaves["Xt"], Ht_1=leaves["H"])
+        Hn.backward(t["dHn"])
+        cfg["activation"] = act
+        Hn_o, g = oracle_cell_with_grads(t, cfg)
+        O.assert_close(Hn_o, Hn.detach(), "Hn", rtol=1e-10, atol_scale=1e-11)
+        O.assert_close(g["dGs"], leaves["Gs"].grad, "dGs", rtol=1e-9, atol_scale=1e-9)
+        O.assert_close(g["dGc"], leaves["Gc"].grad, "dGc", rtol=1e-9, atol_scale=1e-9)
+        O.assert_close(g["dXt"], leaves["Xt"].grad, "dXt", rtol=1e-9, atol_scale=1e-9)
+        O.assert_close(g["dH"], leaves["H"].grad, "dH", rtol=1e-9, atol_scale=1e-9)
+        O.assert_close(g["dWg"], cell.gates.W.grad, "dWg", rtol=1e-9, atol_scale=1e-9)
+        O.assert_close(g["dbc"], cell.candi.b.grad, "dbc", rtol=1e-9, atol_scale=1e-9)
+    finally:
+        torch.set_default_dtype(old)

@@ -1,0 +1,129 @@
+/* stc_b200.h -- C ABI of libstc_b200.so: the B200 (sm_100a) implementation of STC-GNN's
+ * per-timestep spatio-temporal-categorical graph-convolution GRU cell.
+ *
+ * What it replaces (reference = underdoc-wang/STC-GNN, framework/STC_GNN.py):
+ *   STC_Cell.forward                STC_GNN.py:65-79   -> stc_cell_fwd
+ *   BDG_Dif.forward (x2 per cell)   STC_GNN.py:31-47   -> inside stc_cell_fwd
+ *   BDG_Dif.cheby_poly              STC_GNN.py:24-29   -> inside (feature-side recurrence for Gs,
+ *                                                         matrix-space for the small Gc)
+ *   autograd of the above           Model_Trainer.py:81 (loss.backward()) -> stc_cell_bwd
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless it says "host".
+ *   - all tensors are fp32, row-major, feature axis fastest:  X[b][n][c][l].
+ *   - the library never allocates or frees device memory.  The forward pass writes what backward
+ *     needs into `saved` (size from stc_cell_saved_bytes; keep it untouched until stc_cell_bwd has
+ *     run -- it is the autograd node's "saved tensors"); backward additionally takes `scratch`
+ *     (size from stc_cell_bwd_scratch_bytes) which may be reused by any later call.
+ *   - launches go to `stream` (a cudaStream_t passed as void*); no host synchronisation inside.
+ *   - return value: 0 on success, a negative StcStatus otherwise; stc_last_error() gives the text
+ *     (thread-local).  Nothing throws across the boundary.  There is no CPU fallback.
+ */
+#ifndef STC_B200_H_
+#define STC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STC_ABI_VERSION 1
+
+typedef enum {
+  STC_OK = 0,
+  STC_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, bad enum */
+  STC_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels tile (message says which) */
+  STC_ERR_WORKSPACE = -3,    /* saved/scratch buffer smaller than the *_bytes() query says */
+  STC_ERR_CUDA = -4,         /* a CUDA runtime call or launch failed */
+  STC_ERR_ARCH = -5          /* device is not compute capability 10.x */
+} StcStatus;
+
+enum { STC_ACT_NONE = 0, STC_ACT_RELU = 1 };          /* BDG_Dif(activation=...), STC_GNN.py:13,46 */
+enum { STC_SUPPORT_DENSE = 0, STC_SUPPORT_CSR = 1 };
+
+/* Static shape of one cell call.  Mirrors STC_Cell.__init__ (STC_GNN.py:52-58) plus the batch. */
+typedef struct {
+  int32_t B;        /* batch                                  */
+  int32_t N;        /* num_nodes  (regions)                   */
+  int32_t C;        /* num_categories (incident types)        */
+  int32_t Din;      /* input_dim of Xt                        */
+  int32_t h;        /* hidden_dim                             */
+  int32_t Ks;       /* number of spatial Chebyshev terms  (orders 0..Ks-1) */
+  int32_t Kc;       /* number of categorical Chebyshev terms               */
+  int32_t act;      /* STC_ACT_*                              */
+  int32_t has_bias; /* use_bias                               */
+} StcDims;
+
+/* Spatial support Gs [N,N].  The forward pass contracts over Gs's FIRST index
+ * ('bncl,nm->bmcl', STC_GNN.py:37), i.e. applies Gs^T; backward applies Gs.
+ *   dense: vals = Gs row-major [N][N]  (vals[n*N+m] = Gs[n,m]); the other fields are ignored.
+ *   CSR  : (rowptr, col, vals) is Gs in CSR (row n lists the m with Gs[n,m] != 0, used by backward),
+ *          (t_rowptr, t_col, t_vals) is Gs^T in CSR (row m lists the n, used by forward).
+ *          Column indices are int32; nnz < 2^31. */
+typedef struct {
+  int32_t kind;
+  int64_t nnz;
+  const float* vals;
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* t_vals;
+  const int32_t* t_rowptr;
+  const int32_t* t_col;
+} StcSupport;
+
+int stc_abi_version(void);
+const char* stc_last_error(void);
+
+/* Bytes of the `saved` buffer of one cell call (forward intermediates; also the forward's scratch). */
+size_t stc_cell_saved_bytes(const StcDims* d);
+/* Bytes of the `scratch` buffer stc_cell_bwd needs. */
+size_t stc_cell_bwd_scratch_bytes(const StcDims* d);
+
+/* H' = STC_Cell(Gs, Gc, Xt, H)                                             STC_GNN.py:65-79
+ *   gc        [C][C]
+ *   xt        [B][N][C][Din], inner [N][C][Din] slab contiguous, batch stride xt_batch_stride ELEMENTS
+ *             (the encoder hands in a [:,t] view: STC_GNN.py:111)
+ *   h_prev    [B][N][C][h] contiguous
+ *   Wg        [(Din+h)*Ks*Kc][2h]  rows ordered (n, c, l)  (STC_GNN.py:17,35-41);  bg [2h] or NULL
+ *   Wc        [(Din+h)*Ks*Kc][h];                                                   bc [h]  or NULL
+ *   h_out     [B][N][C][h] contiguous, must not alias an input                                   */
+int stc_cell_fwd(const StcDims* d, const StcSupport* gs, const float* gc,
+                 const float* xt, int64_t xt_batch_stride, const float* h_prev,
+                 const float* Wg, const float* bg, const float* Wc, const float* bc,
+                 float* h_out, void* saved, size_t saved_bytes, void* stream);
+
+/* Gradients of stc_cell_fwd given d_h_out.  `saved` is the buffer the matching forward call filled.
+ *   d_xt      [B][N][C][Din] contiguous, or NULL when Xt needs no gradient
+ *   d_h_prev  [B][N][C][h]
+ *   dWg,dbg,dWc,dbc  same shapes as the parameters (dbg/dbc NULL when has_bias == 0)
+ *   dGs       [N][N] dense or NULL (must be NULL for a CSR support: constants by construction)
+ *   dGc       [C][C] or NULL
+ *   accumulate_params != 0: parameter/support gradients are ADDED to the buffers' contents
+ *   (lets a time loop accumulate dW over steps); == 0: they are overwritten.
+ *   d_xt / d_h_prev are always overwritten.                                                     */
+int stc_cell_bwd(const StcDims* d, const StcSupport* gs, const float* gc,
+                 const float* xt, int64_t xt_batch_stride, const float* h_prev,
+                 const float* Wg, const float* Wc, const float* d_h_out,
+                 float* d_xt, float* d_h_prev,
+                 float* dWg, float* dbg, float* dWc, float* dbc, float* dGs, float* dGc,
+                 int32_t accumulate_params, const void* saved, size_t saved_bytes,
+                 void* scratch, size_t scratch_bytes, void* stream);
+
+/* Y[b,m,:] = alpha * sum_n A(m,n) X[b,n,:] + beta * Z[b,m,:]  with A = Gs^T (transpose != 0, the
+ * forward mode product of STC_GNN.py:37) or A = Gs.  X,Z,Y: [B][N][width]; X and Z may carry a batch
+ * stride (elements), Y is contiguous; Z may be NULL when beta == 0; Y may alias Z.  Exposed because it
+ * is the support kernel the roofline is quoted on, and the building block of the halo-partitioned path. */
+int stc_support_apply(const StcSupport* gs, int32_t N, int32_t B, int32_t width, int32_t transpose,
+                      const float* x, int64_t x_batch_stride, const float* z, int64_t z_batch_stride,
+                      float* y, float alpha, float beta, void* stream);
+
+/* Number of kernel launches the last stc_cell_fwd / stc_cell_bwd on this thread issued
+ * (bench.py reports gpu_launches from these). */
+int stc_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STC_B200_H_ */

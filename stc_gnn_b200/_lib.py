@@ -1,0 +1,78 @@
+"""ctypes binding of libstc_b200.so -- the C ABI declared in include/stc_b200.h.
+
+The product path has no CPU fallback: if the library cannot be loaded, or a call returns a negative
+status, a RuntimeError carrying stc_last_error() is raised.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libstc_b200.so")
+
+ABI_VERSION = 1
+ACT_NONE, ACT_RELU = 0, 1
+SUPPORT_DENSE, SUPPORT_CSR = 0, 1
+
+# every symbol include/stc_b200.h declares (tests check the built library exports all of them)
+EXPORTED = (
+    "stc_abi_version", "stc_last_error", "stc_cell_saved_bytes", "stc_cell_bwd_scratch_bytes",
+    "stc_cell_fwd", "stc_cell_bwd", "stc_support_apply", "stc_last_launch_count",
+)
+
+
+class StcDims(Structure):
+    _fields_ = [(n, c_int32) for n in ("B", "N", "C", "Din", "h", "Ks", "Kc", "act", "has_bias")]
+
+
+class StcSupport(Structure):
+    _fields_ = [("kind", c_int32), ("nnz", c_int64), ("vals", c_void_p), ("rowptr", c_void_p), ("col", c_void_p),
+                ("t_vals", c_void_p), ("t_rowptr", c_void_p), ("t_col", c_void_p)]
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if the sources changed and nvcc is present) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from .build import build
+        build()
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m stc_gnn_b200.build` (no CPU fallback exists)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.stc_abi_version.restype = c_int
+    lib.stc_last_error.restype = c_char_p
+    lib.stc_last_launch_count.restype = c_int
+    lib.stc_cell_saved_bytes.restype = c_size_t
+    lib.stc_cell_saved_bytes.argtypes = [POINTER(StcDims)]
+    lib.stc_cell_bwd_scratch_bytes.restype = c_size_t
+    lib.stc_cell_bwd_scratch_bytes.argtypes = [POINTER(StcDims)]
+    lib.stc_cell_fwd.restype = c_int
+    lib.stc_cell_fwd.argtypes = [POINTER(StcDims), POINTER(StcSupport), c_void_p, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.stc_cell_bwd.restype = c_int
+    lib.stc_cell_bwd.argtypes = [POINTER(StcDims), POINTER(StcSupport), c_void_p, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_void_p, c_size_t,
+                                 c_void_p]
+    lib.stc_support_apply.restype = c_int
+    lib.stc_support_apply.argtypes = [POINTER(StcSupport), c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
+                                      c_void_p, c_int64, c_void_p, c_float, c_float, c_void_p]
+    if lib.stc_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libstc_b200.so ABI {lib.stc_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = _lib.stc_last_error().decode("utf-8", "replace") if _lib is not None else ""
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def last_launch_count() -> int:
+    return int(load().stc_last_launch_count())

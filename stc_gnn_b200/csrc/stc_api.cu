@@ -1,0 +1,351 @@
+// C ABI of libstc_b200.so (declared in include/stc_b200.h): argument checking, workspace layout and the
+// launch sequence of one cell forward / backward on the general path.
+#include "stc_common.cuh"
+
+#include <string.h>
+
+namespace stc {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+int device_sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    cached = p.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+int check_arch() {
+  static thread_local int ok_dev = -1;
+  int dev = 0;
+  STC_CUDA_OK(cudaGetDevice(&dev));
+  if (dev == ok_dev) return STC_OK;
+  int major = 0;
+  STC_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("libstc_b200 is built for sm_100a only; device %d has compute capability major %d", dev, major);
+    return STC_ERR_ARCH;
+  }
+  ok_dev = dev;
+  return STC_OK;
+}
+
+WsLayout make_layout(const StcDims& d) {
+  WsLayout w;
+  const size_t A = 64;  // 256-byte alignment of every region
+  w.R = (size_t)d.B * d.N * d.C;
+  const size_t Rh = w.R * d.h, Rx = w.R * d.Din;
+  const size_t km1 = d.Ks > 1 ? (size_t)(d.Ks - 1) : 0;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t at = o; o = round_up(o + n, A); return at; };
+  w.u = take(Rh);
+  w.r = take(Rh);
+  w.c = take(Rh);
+  w.Yr = take((size_t)d.Ks * Rh);   // Yr[0] = r*H, then its spatial terms
+  w.Yx = take(km1 * Rx);
+  w.Yh = take(km1 * Rh);
+  w.Q = take((size_t)d.Kc * d.C * d.C);
+  w.saved_total = o;
+  o = 0;
+  w.dpre = take(w.R * 2 * d.h);
+  w.dYx0 = take(Rx);
+  w.dYx = take(km1 * Rx);
+  w.dYh = take(km1 * Rh);
+  w.dYr = take((size_t)d.Ks * Rh);
+  w.dQ = take((size_t)d.Kc * d.C * d.C);
+  w.scratch_total = o;
+  return w;
+}
+
+static int check_dims(const StcDims* d) {
+  if (!d) {
+    set_error("dims is NULL");
+    return STC_ERR_BAD_ARG;
+  }
+  if (d->B < 0 || d->N <= 0 || d->C <= 0 || d->Din <= 0 || d->h <= 0 || d->Ks <= 0 || d->Kc <= 0) {
+    set_error("bad dims B=%d N=%d C=%d Din=%d h=%d Ks=%d Kc=%d", d->B, d->N, d->C, d->Din, d->h, d->Ks, d->Kc);
+    return STC_ERR_BAD_ARG;
+  }
+  if (d->act != STC_ACT_NONE && d->act != STC_ACT_RELU) {
+    set_error("unsupported activation code %d (none=0, relu=1)", d->act);
+    return STC_ERR_UNSUPPORTED;
+  }
+  if ((long long)d->B * d->N * d->C * (long long)(2 * d->h > d->Din ? 2 * d->h : d->Din) >= (1LL << 40)) {
+    set_error("problem too large");
+    return STC_ERR_UNSUPPORTED;
+  }
+  return STC_OK;
+}
+
+static ConvArgs base_args(const StcDims& d, const float* xt, int64_t xt_bs, const float* W, const float* Q,
+                          float* ws, const WsLayout& w, int phase) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = d.B; a.N = d.N; a.C = d.C; a.Din = d.Din; a.h = d.h; a.Ks = d.Ks; a.Kc = d.Kc;
+  a.act = d.act;
+  a.phase = phase;
+  a.Hout = phase == 0 ? 2 * d.h : d.h;
+  a.x0 = xt;
+  a.x0_bs = xt_bs;
+  a.yx = ws + w.Yx;
+  a.W = W;
+  a.Q = Q;
+  return a;
+}
+
+}  // namespace stc
+
+using namespace stc;
+
+extern "C" {
+
+int stc_abi_version(void) { return STC_ABI_VERSION; }
+const char* stc_last_error(void) { return g_err; }
+int stc_last_launch_count(void) { return g_launches; }
+
+size_t stc_cell_saved_bytes(const StcDims* d) {
+  if (check_dims(d) != STC_OK) return 0;
+  return make_layout(*d).saved_total * sizeof(float);
+}
+size_t stc_cell_bwd_scratch_bytes(const StcDims* d) {
+  if (check_dims(d) != STC_OK) return 0;
+  return make_layout(*d).scratch_total * sizeof(float);
+}
+
+int stc_support_apply(const StcSupport* gs, int32_t N, int32_t B, int32_t width, int32_t transpose,
+                      const float* x, int64_t x_batch_stride, const float* z, int64_t z_batch_stride, float* y,
+                      float alpha, float beta, void* stream) {
+  reset_launch_count();
+  if (!gs || !x || !y) {
+    set_error("stc_support_apply: NULL argument");
+    return STC_ERR_BAD_ARG;
+  }
+  STC_TRY(check_arch());
+  return launch_support_apply(*gs, N, B, width, transpose != 0, x, x_batch_stride, z, z_batch_stride, y, alpha,
+                              beta, nullptr, 0.f, (cudaStream_t)stream);
+}
+
+int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* bg, const float* Wc,
+                 const float* bc, float* h_out, void* wsv, size_t ws_bytes, void* stream) {  // wsv = `saved`
+  reset_launch_count();
+  STC_TRY(check_dims(dp));
+  const StcDims& d = *dp;
+  if (!gs || !gc || !xt || !h_prev || !Wg || !Wc || !h_out || !wsv) {
+    set_error("stc_cell_fwd: NULL argument");
+    return STC_ERR_BAD_ARG;
+  }
+  if (d.has_bias && (!bg || !bc)) {
+    set_error("stc_cell_fwd: has_bias set but bias pointer is NULL");
+    return STC_ERR_BAD_ARG;
+  }
+  const WsLayout w = make_layout(d);
+  if (ws_bytes < w.saved_total * sizeof(float)) {
+    set_error("saved buffer too small: %zu < %zu bytes", ws_bytes, w.saved_total * sizeof(float));
+    return STC_ERR_WORKSPACE;
+  }
+  if (d.B == 0) return STC_OK;
+  STC_TRY(check_arch());
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)wsv;
+  const size_t Rh = w.R * d.h, Rx = w.R * d.Din;
+  const int CD = d.C * d.Din, CH = d.C * d.h;
+  const long long nbs_h = (long long)d.N * CH;
+
+  if (d.Kc > 1) STC_TRY(launch_cheby_small(gc, d.C, d.Kc, ws + w.Q, st));
+
+  // spatial Chebyshev terms of Xt and H:  Y_1 = Gs^T Y_0,  Y_k = 2 Gs^T Y_{k-1} - Y_{k-2}
+  for (int k = 1; k < d.Ks; ++k) {
+    const float alpha = k == 1 ? 1.f : 2.f, beta = k == 1 ? 0.f : -1.f;
+    const float* xin = k == 1 ? xt : ws + w.Yx + (size_t)(k - 2) * Rx;
+    const int64_t xin_bs = k == 1 ? xt_batch_stride : (int64_t)d.N * CD;
+    const float* xz = k == 1 ? nullptr : (k == 2 ? xt : ws + w.Yx + (size_t)(k - 3) * Rx);
+    const int64_t xz_bs = k == 2 ? xt_batch_stride : (int64_t)d.N * CD;
+    STC_TRY(launch_support_apply(*gs, d.N, d.B, CD, true, xin, xin_bs, xz, xz_bs, ws + w.Yx + (size_t)(k - 1) * Rx,
+                                 alpha, beta, nullptr, 0.f, st));
+    const float* hin = k == 1 ? h_prev : ws + w.Yh + (size_t)(k - 2) * Rh;
+    const float* hz = k == 1 ? nullptr : (k == 2 ? h_prev : ws + w.Yh + (size_t)(k - 3) * Rh);
+    STC_TRY(launch_support_apply(*gs, d.N, d.B, CH, true, hin, nbs_h, hz, nbs_h, ws + w.Yh + (size_t)(k - 1) * Rh,
+                                 alpha, beta, nullptr, 0.f, st));
+  }
+
+  // gates:  [u|r] = sigmoid(conv([Xt,H])),  rH = r*H
+  {
+    ConvArgs a = base_args(d, xt, xt_batch_stride, Wg, ws + w.Q, ws, w, 0);
+    a.h0 = h_prev;
+    a.yh = ws + w.Yh;
+    a.bias = d.has_bias ? bg : nullptr;
+    a.Hprev = h_prev;
+    a.u = ws + w.u;
+    a.r = ws + w.r;
+    a.rH = ws + w.Yr;
+    STC_TRY(launch_conv_fwd(a, st));
+  }
+  // spatial terms of r*H
+  for (int k = 1; k < d.Ks; ++k) {
+    const float alpha = k == 1 ? 1.f : 2.f, beta = k == 1 ? 0.f : -1.f;
+    const float* in = ws + w.Yr + (size_t)(k - 1) * Rh;
+    const float* z = k == 1 ? nullptr : ws + w.Yr + (size_t)(k - 2) * Rh;
+    STC_TRY(launch_support_apply(*gs, d.N, d.B, CH, true, in, nbs_h, z, nbs_h, ws + w.Yr + (size_t)k * Rh, alpha, beta,
+                                 nullptr, 0.f, st));
+  }
+  // candidate:  c = tanh(conv([Xt, rH])),  H' = (1-u) H + u c
+  {
+    ConvArgs a = base_args(d, xt, xt_batch_stride, Wc, ws + w.Q, ws, w, 1);
+    a.h0 = ws + w.Yr;
+    a.yh = ws + w.Yr + Rh;
+    a.bias = d.has_bias ? bc : nullptr;
+    a.Hprev = h_prev;
+    a.u = ws + w.u;
+    a.c = ws + w.c;
+    a.Hnew = h_out;
+    STC_TRY(launch_conv_fwd(a, st));
+  }
+  return STC_OK;
+}
+
+// reverse of the feature-side recurrence Y_k = 2 A^T Y_{k-1} - Y_{k-2} (Y_1 = A^T Y_0) for one operand:
+//   ybar[k-1] += (k>=2 ? 2 : 1) * Gs * ybar[k];  ybar[k-2] -= ybar[k];  dGs += coef * Y_{k-1} (x) ybar[k]
+static int adjoint_chain(const StcDims& d, const StcSupport& gs, int width, const float* y0, int64_t y0_bs,
+                         const float* yk /* terms k>=1, contiguous */, float* ybar0, float* ybark /* k>=1 */,
+                         float* dGs, cudaStream_t st) {
+  const size_t Rw = (size_t)d.B * d.N * width;
+  const int64_t nbs = (int64_t)d.N * width;
+  for (int k = d.Ks - 1; k >= 1; --k) {
+    const float coef = k >= 2 ? 2.f : 1.f;
+    float* yb_k = ybark + (size_t)(k - 1) * Rw;
+    float* yb_km1 = k == 1 ? ybar0 : ybark + (size_t)(k - 2) * Rw;
+    if (dGs) {
+      const float* yprev = k == 1 ? y0 : yk + (size_t)(k - 2) * Rw;
+      const int64_t yprev_bs = k == 1 ? y0_bs : nbs;
+      STC_TRY(launch_support_outer(d.N, d.B, width, yprev, yprev_bs, yb_k, coef, dGs, st));
+    }
+    float* axpy = nullptr;
+    if (k >= 2) axpy = k == 2 ? ybar0 : ybark + (size_t)(k - 3) * Rw;
+    STC_TRY(launch_support_apply(gs, d.N, d.B, width, false, yb_k, nbs, yb_km1, nbs, yb_km1, coef, 1.f, axpy, -1.f,
+                                 st));
+  }
+  return STC_OK;
+}
+
+int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* Wc,
+                 const float* d_h_out, float* d_xt, float* d_h_prev, float* dWg, float* dbg, float* dWc, float* dbc,
+                 float* dGs, float* dGc, int32_t accumulate_params, const void* savedv, size_t saved_bytes,
+                 void* scratchv, size_t scratch_bytes, void* stream) {
+  reset_launch_count();
+  STC_TRY(check_dims(dp));
+  const StcDims& d = *dp;
+  if (!gs || !gc || !xt || !h_prev || !Wg || !Wc || !d_h_out || !d_h_prev || !dWg || !dWc || !savedv || !scratchv) {
+    set_error("stc_cell_bwd: NULL argument");
+    return STC_ERR_BAD_ARG;
+  }
+  if (d.has_bias && (!dbg || !dbc)) {
+    set_error("stc_cell_bwd: has_bias set but a bias-gradient pointer is NULL");
+    return STC_ERR_BAD_ARG;
+  }
+  if (dGs && gs->kind != STC_SUPPORT_DENSE) {
+    set_error("stc_cell_bwd: dGs is only defined for a dense support");
+    return STC_ERR_BAD_ARG;
+  }
+  const WsLayout w = make_layout(d);
+  if (saved_bytes < w.saved_total * sizeof(float) || scratch_bytes < w.scratch_total * sizeof(float)) {
+    set_error("buffers too small: saved %zu (need %zu), scratch %zu (need %zu) bytes", saved_bytes,
+              w.saved_total * sizeof(float), scratch_bytes, w.scratch_total * sizeof(float));
+    return STC_ERR_WORKSPACE;
+  }
+  STC_TRY(check_arch());
+  cudaStream_t st = (cudaStream_t)stream;
+  float* sv = const_cast<float*>((const float*)savedv);  // read-only here
+  float* sc = (float*)scratchv;
+  const int L = d.Din + d.h, P = d.Ks * d.Kc;
+  const size_t Rh = w.R * d.h;
+  const int CD = d.C * d.Din, CH = d.C * d.h;
+  const bool want_dGc = dGc != nullptr && d.Kc > 1;
+
+  if (!accumulate_params) {
+    STC_CUDA_OK(cudaMemsetAsync(dWg, 0, sizeof(float) * P * L * 2 * d.h, st));
+    STC_CUDA_OK(cudaMemsetAsync(dWc, 0, sizeof(float) * P * L * d.h, st));
+    if (d.has_bias) {
+      STC_CUDA_OK(cudaMemsetAsync(dbg, 0, sizeof(float) * 2 * d.h, st));
+      STC_CUDA_OK(cudaMemsetAsync(dbc, 0, sizeof(float) * d.h, st));
+    }
+    if (dGs) STC_CUDA_OK(cudaMemsetAsync(dGs, 0, sizeof(float) * d.N * d.N, st));
+    if (dGc) STC_CUDA_OK(cudaMemsetAsync(dGc, 0, sizeof(float) * d.C * d.C, st));
+  }
+  if (d.B == 0) return STC_OK;
+  if (want_dGc) STC_CUDA_OK(cudaMemsetAsync(sc + w.dQ, 0, sizeof(float) * d.Kc * d.C * d.C, st));
+
+  float* dYx0 = d_xt ? d_xt : sc + w.dYx0;
+
+  // ---- candidate conv adjoint ----
+  {
+    ConvArgs a = base_args(d, xt, xt_batch_stride, Wc, sv + w.Q, sv, w, 1);
+    a.h0 = sv + w.Yr;
+    a.yh = sv + w.Yr + Rh;
+    a.Hprev = h_prev;
+    a.u = sv + w.u;
+    a.c = sv + w.c;
+    a.dHn = d_h_out;
+    a.dpre = sc + w.dpre;
+    a.dbias = d.has_bias ? dbc : nullptr;
+    a.dYx0 = dYx0;
+    a.dYx = sc + w.dYx;
+    a.accum_x = 0;
+    a.dYh0 = sc + w.dYr;
+    a.dYh = sc + w.dYr + Rh;
+    a.dQ = want_dGc ? sc + w.dQ : nullptr;
+    a.dW = dWc;
+    STC_TRY(launch_conv_bwd_dx(a, st));
+    STC_TRY(launch_conv_bwd_dw(a, st));
+  }
+  // d(rH) through the spatial recurrence
+  STC_TRY(adjoint_chain(d, *gs, CH, sv + w.Yr, (int64_t)d.N * CH, sv + w.Yr + Rh, sc + w.dYr, sc + w.dYr + Rh, dGs, st));
+
+  // ---- GRU elementwise adjoint + gates conv adjoint ----
+  {
+    ConvArgs a = base_args(d, xt, xt_batch_stride, Wg, sv + w.Q, sv, w, 0);
+    a.h0 = h_prev;
+    a.yh = sv + w.Yh;
+    a.Hprev = h_prev;
+    a.u = sv + w.u;
+    a.r = sv + w.r;
+    a.c = sv + w.c;
+    a.dHn = d_h_out;
+    a.drH = sc + w.dYr;
+    a.dpre = sc + w.dpre;
+    a.dbias = d.has_bias ? dbg : nullptr;
+    a.dYx0 = dYx0;
+    a.dYx = sc + w.dYx;
+    a.accum_x = 1;
+    a.dYh0 = d_h_prev;
+    a.dYh = sc + w.dYh;
+    a.dQ = want_dGc ? sc + w.dQ : nullptr;
+    a.dW = dWg;
+    STC_TRY(launch_conv_bwd_dx(a, st));
+    STC_TRY(launch_conv_bwd_dw(a, st));
+  }
+  STC_TRY(adjoint_chain(d, *gs, CD, xt, xt_batch_stride, sv + w.Yx, dYx0, sc + w.dYx, dGs, st));
+  STC_TRY(adjoint_chain(d, *gs, CH, h_prev, (int64_t)d.N * CH, sv + w.Yh, d_h_prev, sc + w.dYh, dGs, st));
+
+  if (want_dGc) STC_TRY(launch_cheby_small_bwd(gc, sv + w.Q, sc + w.dQ, d.C, d.Kc, dGc, st));
+  return STC_OK;
+}
+
+}  // extern "C"

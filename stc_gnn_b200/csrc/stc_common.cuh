@@ -1,0 +1,105 @@
+// Internal helpers shared by the libstc_b200 translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/stc_b200.h"
+
+namespace stc {
+
+// ---- error plumbing (thread-local message + launch counter) -------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+void reset_launch_count();
+
+#define STC_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      stc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return STC_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define STC_LAUNCH_OK(name)                                                                 \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      stc::set_error("launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return STC_ERR_CUDA;                                                                  \
+    }                                                                                       \
+    stc::count_launch();                                                                    \
+  } while (0)
+
+#define STC_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != STC_OK) return _s; \
+  } while (0)
+
+static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int device_sm_count();   // cached, current device
+int check_arch();        // STC_OK when the current device is compute capability 10.x
+
+// ---- workspace layout of one cell call (offsets in floats) -------------------------------------
+struct WsLayout {
+  size_t R;  // B*N*C rows
+  // `saved` buffer (written by forward, read by backward)
+  size_t u, r, c, Yr, Yx, Yh, Q, saved_total;
+  // backward `scratch` buffer
+  size_t dpre, dYx0, dYx, dYh, dYr, dQ, scratch_total;
+};
+WsLayout make_layout(const StcDims& d);
+
+// ---- launchers implemented in the kernel TUs -----------------------------------------------------
+int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool transpose, const float* x,
+                         int64_t x_bs, const float* z, int64_t z_bs, float* y, float alpha, float beta,
+                         float* axpy_out, float axpy_coef, cudaStream_t st);
+
+int launch_support_outer(int N, int B, int width, const float* a, int64_t a_bs, const float* bmat, float coef,
+                         float* dG, cudaStream_t st);
+
+int launch_cheby_small(const float* G, int C, int K, float* Q, cudaStream_t st);
+int launch_cheby_small_bwd(const float* G, const float* Q, float* dQ, int C, int K, float* dG, cudaStream_t st);
+
+struct ConvArgs {
+  // shape
+  int B, N, C, Din, h, Ks, Kc, Hout, act, phase;  // phase 0 = gates conv, 1 = candidate conv
+  // feature sources: x-part (k = 0 from x0, k >= 1 from yx[k-1]) and h-part (h0 / yh[k-1])
+  const float* x0;
+  long long x0_bs;
+  const float* yx;
+  const float* h0;
+  const float* yh;
+  const float* W;     // [(Ks*Kc*L)][Hout]
+  const float* bias;  // [Hout] or null
+  const float* Q;     // [Kc][C][C]
+  // forward epilogue
+  const float* Hprev;
+  float* u;
+  float* r;
+  float* rH;
+  float* c;
+  float* Hnew;
+  // backward inputs / outputs
+  const float* dHn;
+  const float* drH;    // gates phase: adjoint of r*H
+  float* dpre;         // [R][Hout] scratch written by dx, read by dw
+  float* dbias;        // atomically accumulated, or null
+  float* dYx0;         // k = 0 x-part adjoint destination
+  float* dYx;          // k >= 1
+  int accum_x;         // add into dYx* instead of overwrite (gates phase after candidate phase)
+  float* dYh0;         // k = 0 h-part adjoint destination (d_h_prev for gates, d(rH) for candidate)
+  float* dYh;          // k >= 1
+  float* dQ;           // [Kc][C][C] atomically accumulated, or null
+  float* dW;           // atomically accumulated
+};
+int launch_conv_fwd(const ConvArgs& a, cudaStream_t st);
+int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st);
+int launch_conv_bwd_dw(const ConvArgs& a, cudaStream_t st);
+
+}  // namespace stc

@@ -1,0 +1,210 @@
+"""GPU parity tests (run on a B200 via gpurun): the CUDA path, called through the C ABI, against the
+golden vectors from the real reference and against the fp64 oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star: fp32, rtol 1e-4; SURVEY.md §8c adds the scale-aware atol the
+reference's own fp32 evaluation needs):   |got - ref| <= 1e-4 * |ref| + 1e-5 * mean|ref|
+"""
+import pytest
+import torch
+
+import stc_gnn_b200 as S
+from oracle import stc_oracle as O
+from tests.helpers import CELL_CASES, GRAD_KEYS, load_cell, load_stack, oracle_cell_with_grads, random_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def run_cuda_cell(t, cfg, Gs_override=None, need_dxt=True):
+    """Forward + backward through the product path; returns (Hn, grads) on CPU."""
+    dev = torch.device(DEV)
+    leaf = lambda x, rg=True: x.float().to(dev).requires_grad_(rg)
+    Gs = Gs_override if Gs_override is not None else leaf(t["Gs"])
+    Gc, H = leaf(t["Gc"]), leaf(t["H"])
+    if t["Xt"].is_contiguous():
+        Xt = leaf(t["Xt"], need_dxt)
+    else:  # keep the view's strides on the device
+        base = t["Xt"]._base.float().to(dev)
+        Xt = base.as_strided(t["Xt"].shape, t["Xt"].stride(), t["Xt"].storage_offset()).requires_grad_(need_dxt)
+    Wg, Wc = leaf(t["Wg"]), leaf(t["Wc"])
+    bg = leaf(t["bg"]) if t.get("bg") is not None else None
+    bc = leaf(t["bc"]) if t.get("bc") is not None else None
+    Hn = S.stc_cell_forward(Gs, Gc, Xt, H, Wg, bg, Wc, bc, cfg["Ks"], cfg["Kc"], cfg.get("activation"))
+    Hn.backward(t["dHn"].float().to(dev))
+    torch.cuda.synchronize()
+    g = dict(dH=H.grad, dWg=Wg.grad, dWc=Wc.grad, dGc=Gc.grad)
+    if need_dxt:
+        g["dXt"] = Xt.grad
+    if isinstance(Gs, torch.Tensor):
+        g["dGs"] = Gs.grad
+    if bg is not None:
+        g.update(dbg=bg.grad, dbc=bc.grad)
+    zero = lambda k: torch.zeros_like(t[k.replace("d", "", 1)]) if k in ("dGs", "dGc") else None
+    return Hn.detach().cpu(), {k: (v.cpu() if v is not None else zero(k)) for k, v in g.items()}
+
+
+@pytest.mark.parametrize("name", CELL_CASES)
+def test_cell_matches_reference_golden(name):
+    cfg, t = load_cell(name)
+    if name == "strided":  # rebuild the [:, t] view the encoder would pass (STC_GNN.py:111)
+        seq = torch.zeros(cfg["B"], 4, cfg["N"], cfg["C"], cfg["Din"])
+        seq[:, 1] = t["Xt"]
+        t["Xt"] = seq[:, 1]
+        assert not t["Xt"].is_contiguous()
+    Hn, g = run_cuda_cell(t, cfg)
+    O.assert_close(Hn, t["Hn"], f"{name}:Hn")
+    for k in GRAD_KEYS:
+        if k in t:
+            O.assert_close(g[k], t[k], f"{name}:{k}")
+
+
+SHAPES = [
+    # B, N, C, Din, h, Ks, Kc
+    (3, 33, 5, 1, 16, 2, 2),
+    (2, 70, 4, 16, 16, 3, 2),
+    (2, 130, 3, 5, 7, 2, 3),      # N > one 64-row tile twice, odd widths
+    (1, 20, 64, 8, 16, 2, 2),     # wide category axis (LongC-like)
+    (2, 24, 16, 64, 64, 2, 2),    # F = 64 (G4096-like feature widths)
+    (5, 12, 8, 64, 64, 4, 2),     # Ks = 4 (kNN64K-like)
+    (2, 9, 2, 3, 4, 1, 3),
+    (4, 1, 1, 1, 1, 2, 2),        # degenerate sizes
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("act", [None, "relu"])
+def test_cell_matches_oracle_dense(shape, act):
+    B, N, C, Din, h, Ks, Kc = shape
+    cfg = dict(B=B, N=N, C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, activation=act)
+    t = random_case(B, N, C, Din, h, Ks, Kc, seed=sum(shape))
+    Hn_o, g_o = oracle_cell_with_grads(t, cfg)
+    Hn, g = run_cuda_cell(t, cfg)
+    O.assert_close(Hn, Hn_o, "Hn")
+    for k, v in g.items():
+        O.assert_close(v, g_o[k], k)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 4, 3, 8, 2, 2), (3, 200, 8, 16, 16, 4, 2), (1, 50, 5, 1, 16, 3, 3)])
+def test_cell_matches_oracle_csr(shape):
+    B, N, C, Din, h, Ks, Kc = shape
+    cfg = dict(B=B, N=N, C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, activation=None)
+    t = random_case(B, N, C, Din, h, Ks, Kc, seed=sum(shape), sparse_frac=0.9)
+    Hn_o, g_o = oracle_cell_with_grads(t, cfg)
+    csr = S.CsrSupport.from_dense(t["Gs"].float().to(DEV))
+    Hn, g = run_cuda_cell(t, cfg, Gs_override=csr)
+    O.assert_close(Hn, Hn_o, "Hn")
+    for k in ("dXt", "dH", "dWg", "dWc", "dbg", "dbc", "dGc"):
+        O.assert_close(g[k], g_o[k], k)
+    # torch sparse tensors are accepted by the module form as well
+    cell = S.STC_Cell(N, C, Ks, Kc, Din, h).to(DEV)
+    with torch.no_grad():
+        cell.gates.W.copy_(t["Wg"]); cell.gates.b.copy_(t["bg"]); cell.candi.W.copy_(t["Wc"]); cell.candi.b.copy_(t["bc"])
+    out = cell(Gs=t["Gs"].float().to(DEV).to_sparse_csr(), Gc=t["Gc"].float().to(DEV), Xt=t["Xt"].float().to(DEV),
+               Ht_1=t["H"].float().to(DEV))
+    O.assert_close(out.detach().cpu(), Hn_o, "Hn via torch sparse")
+
+
+def test_no_grad_and_eval_modes():
+    cfg, t = load_cell("tiny")
+    cell = S.STC_Cell(cfg["N"], cfg["C"], cfg["Ks"], cfg["Kc"], cfg["Din"], cfg["h"]).to(DEV).eval()
+    with torch.no_grad():
+        cell.gates.W.copy_(t["Wg"]); cell.gates.b.copy_(t["bg"]); cell.candi.W.copy_(t["Wc"]); cell.candi.b.copy_(t["bc"])
+        out = cell(Gs=t["Gs"].to(DEV), Gc=t["Gc"].to(DEV), Xt=t["Xt"].to(DEV), Ht_1=t["H"].to(DEV))
+    assert not out.requires_grad
+    O.assert_close(out.cpu(), t["Hn"], "no_grad Hn")
+    H_in = t["H"].to(DEV)
+    H_copy = H_in.clone()
+    out2 = cell(Gs=t["Gs"].to(DEV), Gc=t["Gc"].to(DEV), Xt=t["Xt"].to(DEV), Ht_1=H_in)   # grad mode on, eval()
+    assert out2.requires_grad and torch.equal(H_in, H_copy), "inputs must not be modified"
+
+
+def test_stack_matches_reference_golden():
+    cfg, t = load_stack()
+    stack = S.RecurrentStack(cfg["N"], cfg["C"], cfg["Ks"], cfg["Kc"], cfg["Din"], cfg["h"], cfg["layers"],
+                             cfg["horizon"]).to(DEV)
+    with torch.no_grad():
+        for tag, mods in (("enc", stack.encoder), ("dec", stack.decoder)):
+            for i, cell in enumerate(mods):
+                for conv in ("gates", "candi"):
+                    for pn in ("W", "b"):
+                        getattr(getattr(cell, conv), pn).copy_(t[f"{tag}{i}_{conv}_{pn}"])
+    Gs = t["Gs"].to(DEV).requires_grad_(True)
+    Gc = t["Gc"].to(DEV).requires_grad_(True)
+    X = t["X_seq"].to(DEV).requires_grad_(True)
+    out = stack(Gs, Gc, X)
+    O.assert_close(out.detach().cpu(), t["out"], "stack out")
+    out.backward(t["dOut"].to(DEV))
+    O.assert_close(Gs.grad.cpu(), t["dGs"], "dGs")
+    O.assert_close(Gc.grad.cpu(), t["dGc"], "dGc")
+    O.assert_close(X.grad.cpu(), t["dX_seq"], "dX_seq")
+    for tag, mods in (("enc", stack.encoder), ("dec", stack.decoder)):
+        for i, cell in enumerate(mods):
+            for conv in ("gates", "candi"):
+                for pn in ("W", "b"):
+                    O.assert_close(getattr(getattr(cell, conv), pn).grad.cpu(), t[f"d_{tag}{i}_{conv}_{pn}"],
+                                   f"{tag}{i}.{conv}.{pn}")
+
+
+@pytest.mark.parametrize("kind", ["dense", "csr"])
+def test_support_apply_matches_oracle(kind):
+    g = torch.Generator().manual_seed(3)
+    N, B, W = 77, 5, 24
+    G = (torch.rand(N, N, generator=g) * (torch.rand(N, N, generator=g) > 0.7)).float()
+    X = torch.randn(B, N, 4, 6, generator=g).float()
+    Gd = G.to(DEV)
+    sup = Gd if kind == "dense" else S.CsrSupport.from_dense(Gd)
+    Y = S.support_apply(sup, X.to(DEV), transpose=True).cpu()
+    O.assert_close(Y, O.support_T_apply(G.double(), X.double()), "G^T X")
+    Y2 = S.support_apply(sup, X.to(DEV), transpose=False, alpha=2.0, beta=-1.0, Z=X.to(DEV)).cpu()
+    O.assert_close(Y2, 2 * O.support_apply(G.double(), X.double()) - X.double(), "2 G X - X")
+
+
+# ---- size-independent properties at the benchmark's full size (SF shape, B = 1024) -----------------
+def test_full_size_properties():
+    dev = torch.device(DEV)
+    B, N, C, Din, h = 1024, 100, 5, 16, 16
+    g = torch.Generator(device=dev).manual_seed(0)
+    Gs = torch.rand(N, N, device=dev, generator=g) * 0.02
+    Gc = torch.rand(C, C, device=dev, generator=g) * 0.3
+    Xt = torch.randn(B, N, C, Din, device=dev, generator=g)
+    H = torch.randn(B, N, C, h, device=dev, generator=g)
+    cell = S.STC_Cell(N, C, 2, 2, Din, h).to(dev)
+    # (1) zero weights: u = r = 1/2, c = 0  =>  H' = H / 2 exactly
+    with torch.no_grad():
+        W0 = [p.clone() for p in cell.parameters()]
+        for p in cell.parameters():
+            p.zero_()
+        out = cell(Gs=Gs, Gc=Gc, Xt=Xt, Ht_1=H)
+        assert torch.equal(out, 0.5 * H)
+        for p, w in zip(cell.parameters(), W0):
+            p.copy_(w)
+        # (2) batch independence: any sample of the big batch equals that sample run alone
+        full = cell(Gs=Gs, Gc=Gc, Xt=Xt, Ht_1=H)
+        for b in (0, 517, B - 1):
+            one = cell(Gs=Gs, Gc=Gc, Xt=Xt[b:b + 1], Ht_1=H[b:b + 1])
+            assert torch.allclose(one[0], full[b], rtol=0, atol=1e-6)
+        # (3) spot-check three samples against the fp64 oracle
+        idx = [0, 517, B - 1]
+        ref = O.stc_cell(Gs.double().cpu(), Gc.double().cpu(), Xt[idx].double().cpu(), H[idx].double().cpu(),
+                         cell.gates.W.double().cpu(), cell.gates.b.double().cpu(), cell.candi.W.double().cpu(),
+                         cell.candi.b.double().cpu(), 2, 2)
+        O.assert_close(full[idx].cpu(), ref, "full-size spot check")
+    # (4) support linearity: S(aX + bY) = a S(X) + b S(Y)
+    Y = torch.randn_like(H)
+    lhs = S.support_apply(Gs, 2.0 * H - 3.0 * Y)
+    rhs = 2.0 * S.support_apply(Gs, H) - 3.0 * S.support_apply(Gs, Y)
+    assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-5)
+
+
+def test_error_paths():
+    dev = torch.device(DEV)
+    cell = S.STC_Cell(6, 3, 2, 2, 1, 4).to(dev)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    with pytest.raises(RuntimeError):
+        cell(Gs=z(5, 5), Gc=z(3, 3), Xt=z(2, 6, 3, 1), Ht_1=z(2, 6, 3, 4))          # wrong Gs shape
+    with pytest.raises(RuntimeError):
+        cell(Gs=z(6, 6), Gc=z(3, 3), Xt=z(2, 6, 3, 1), Ht_1=z(2, 6, 3, 5))          # wrong hidden width
+    with pytest.raises(RuntimeError):
+        cell(Gs=z(6, 6).double(), Gc=z(3, 3), Xt=z(2, 6, 3, 1), Ht_1=z(2, 6, 3, 4))  # fp64 is not accepted
+    out = cell(Gs=z(6, 6), Gc=z(3, 3), Xt=z(0, 6, 3, 1), Ht_1=z(0, 6, 3, 4))         # empty batch
+    assert out.shape == (0, 6, 3, 4)

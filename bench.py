@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/s (forward+backward) of the STC-GNN recurrent cell stack on B200.
+
+Workload (BASELINE.json configs[1], "synthetic SF-shape tensors ... on 1xB200"): the SF-shape
+recurrent stack -- encoder 2 layers x T=9 + decoder horizon 3 x 2 layers = 24 cell steps per sample
+(N=100 regions, C=5 categories, h=16, Ks=Kc=2, dense learned-like Gs requiring grad), i.e. the
+reference's STCGNN.forward/backward minus MGP_Gen and out_proj -- the hot path this repo replaces.
+One "step" = forward + backward of one batch of B windows per GPU; a sample = one [T,N,C] window.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same through the
+public module API with host (pinned) inputs copied in and the loss read back every step;
+`roofline` = the dominant kernel's algorithmic bytes / its device time (CUDA events around every launch
+of that kernel during a second, instrumented pass over the same K steps) against the measured HBM peak;
+`cpu_baseline` = the oracle's reference-shaped port timed on this box's host cores on a bounded sample.
+`--impl reference` runs only that CPU port (rank 0) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SF = dict(N=100, C=5, h=16, Din=1, Ks=2, Kc=2, layers=2, T=9, horizon=3, grid=(10, 10))
+METRIC = "train samples/s (fwd+bwd), SF-shape STC cell stack"
+UNIT = "samples/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--batch", type=int, default=4096, help="windows per GPU per step (weak scaling)")
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--cpu-batch", type=int, default=32, help="windows per CPU-baseline step (bounded sample)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic SF-shape inputs
+# ------------------------------------------------------------------------------------------------
+def synthetic_inputs(B, seed, device="cpu", pin=False):
+    from stc_gnn_b200.synth import sf_supports
+    g = torch.Generator().manual_seed(seed)
+    X = (torch.rand(B, SF["T"], SF["N"], SF["C"], 1, generator=g) < 0.1635).float()   # Bernoulli(data mean)
+    y = (torch.rand(B, SF["horizon"], SF["N"], SF["C"], generator=g) < 0.1635).float()
+    Gs, Gc = sf_supports(seed=0)
+    if pin:
+        X, y = X.pin_memory(), y.pin_memory()
+    return X, y, Gs, Gc
+
+
+def loss_fn(out, y):
+    """Stand-in for out_proj + loss: mean over the hidden axis, squared error against the target."""
+    return (out.mean(dim=-1) - y).square().mean()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.path = None, f"/tmp/stc_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port of the reference (oracle/) -- the reference arm and the cpu_baseline leg
+# ------------------------------------------------------------------------------------------------
+def cpu_port_throughput(B, steps, warmup, seed=0, budget_s=20.0):
+    """fwd+bwd samples/s of the reference-shaped CPU port (same operator sequence as the reference's
+    BDG_Dif/STC_Cell through autograd, fp32, all host threads) on B windows of the same workload."""
+    from oracle import stc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(seed)
+    X, y, Gs, Gc = synthetic_inputs(B, seed)
+    enc = [O.xavier_cell_params(SF["Din"] if i == 0 else SF["h"], SF["h"], SF["Ks"], SF["Kc"], g, torch.float32)
+           for i in range(SF["layers"])]
+    dec = [O.xavier_cell_params(SF["h"], SF["h"], SF["Ks"], SF["Kc"], g, torch.float32) for _ in range(SF["layers"])]
+    leaves = [Gs.requires_grad_(True), Gc.requires_grad_(True)]
+    for p in enc + dec:
+        for t in p.tensors():
+            leaves.append(t.requires_grad_(True))
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        out = O.stack_forward(Gs, Gc, X, enc, dec, SF["horizon"], SF["Ks"], SF["Kc"], cell_fn=O.stc_cell_refshape)
+        loss = loss_fn(out, y)
+        loss.backward()
+        return float(loss.detach())
+
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    return B / (ms / 1e3), ms, len(times), torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    value, ms, n, cores = cpu_port_throughput(args.cpu_batch, max(2, args.steps), min(args.warmup, 1), budget_s=60.0)
+    sample = (f"{n} timed fwd+bwd steps of B={args.cpu_batch} windows (the reference's own batch size) of the same "
+              f"SF-shape workload, fp32, reference-shaped operator sequence through autograd, denormal-free Gs")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.cpu_batch, args.gpus, reference=True),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(B, n_gpus, reference=False):
+    return {
+        "workload": "sf_cell_stack: encoder 2x9 + decoder 3x2 = 24 STC cell steps/sample, fwd+bwd incl. dGs,dGc "
+                    "(BASELINE.json configs[1], SF shape)",
+        "N": SF["N"], "C": SF["C"], "hidden": SF["h"], "Ks": SF["Ks"], "Kc": SF["Kc"], "layers": SF["layers"],
+        "T": SF["T"], "horizon": SF["horizon"], "batch_per_gpu": B, "global_batch": B * (1 if reference else n_gpus),
+        "parallelism": "cpu" if reference else f"dp{n_gpus}",
+        "l2": "inputs+activations exceed L2 (no flush needed)" if B >= 1024 else "working set may fit L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import stc_gnn_b200 as S
+    from stc_gnn_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a GPU (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B = args.batch
+    torch.manual_seed(0)
+    stack = S.RecurrentStack(SF["N"], SF["C"], SF["Ks"], SF["Kc"], SF["Din"], SF["h"], SF["layers"], SF["horizon"]).to(dev)
+    params = list(stack.parameters())
+    Xh, yh, Gs_h, Gc_h = synthetic_inputs(B, seed=rank, pin=True)
+    Gs = Gs_h.to(dev).requires_grad_(True)
+    Gc = Gc_h.to(dev).requires_grad_(True)
+    X_res, y_res = Xh.to(dev), yh.to(dev)
+    grads_flat = None
+
+    def allreduce_grads():
+        nonlocal grads_flat
+        if world == 1:
+            return
+        gl = [p.grad for p in params] + [Gs.grad, Gc.grad]
+        flat = torch.cat([g.reshape(-1) for g in gl])
+        dist.all_reduce(flat)
+        grads_flat = flat
+
+    def step(X, y):
+        for p in params:
+            p.grad = None
+        Gs.grad = None
+        Gc.grad = None
+        out = stack(Gs, Gc, X)
+        loss = loss_fn(out, y)
+        loss.backward()
+        allreduce_grads()
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput ----
+    for _ in range(max(args.warmup, 3)):
+        step(X_res, y_res)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.LAUNCHES
+    ms_total = timed(lambda: step(X_res, y_res), args.steps)
+    launches = _lib.LAUNCHES - l0
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+
+    # ---- end to end through the module API: pinned host inputs in, loss out, every step ----
+    def e2e_step():
+        X = Xh.to(dev, non_blocking=True)
+        y = yh.to(dev, non_blocking=True)
+        return float(step(X, y).item())
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e = {"value": B * world / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": Xh.numel() * 4 + yh.numel() * 4, "d2h_bytes_per_step": 4}
+
+    # ---- instrumented pass: per-kernel device time + algorithmic bytes over the same K steps ----
+    roofline, breakdown = None, None
+    if rank == 0:
+        _lib.timing_enable(True)
+        _lib.timing_collect()
+        for _ in range(args.steps):
+            step(X_res, y_res)
+        torch.cuda.synchronize()
+        _lib.timing_enable(False)
+        kinds = _lib.timing_collect()
+        peak, peak_src = measured_peaks()
+        tot_ms = sum(v[0] for v in kinds.values())
+        breakdown = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                         "share": v[0] / tot_ms, "achieved_GBs": v[2] / (v[0] * 1e-3) / 1e9}
+                     for k, v in sorted(kinds.items(), key=lambda kv: -kv[1][0])}
+        top = max(kinds.items(), key=lambda kv: kv[1][0])
+        name, (kms, kn, kbytes) = top
+        achieved = kbytes / (kms * 1e-3) / 1e9
+        roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_us": 1e3 * kms / kn, "alg_bytes_per_launch": kbytes / kn,
+                    "share_of_kernel_time": kms / tot_ms,
+                    "note": "FFMA general path: this kernel is FP32-pipe bound, not HBM bound; frac is reported "
+                            "against the HBM roofline the metric names"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, ms, n, cores = cpu_port_throughput(args.cpu_batch, 40, 1, budget_s=15.0)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+                        "sample": f"{n} timed fwd+bwd steps of B={args.cpu_batch} windows of the same workload "
+                                  f"(oracle/stc_oracle.py reference-shaped port, fp32, autograd)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

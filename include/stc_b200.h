@@ -123,6 +123,15 @@ int stc_support_apply(const StcSupport* gs, int32_t N, int32_t B, int32_t width,
  * (bench.py reports gpu_launches from these). */
 int stc_last_launch_count(void);
 
+/* Optional per-kernel instrumentation for bench.py's roofline line (off by default; when on, every kernel
+ * launch is bracketed by CUDA events on its own stream).  stc_timing_collect synchronises the recorded
+ * events, ADDS per-kind device milliseconds / launch counts / algorithmic bytes (the compulsory HBM traffic
+ * of each launch, formulas next to each launcher) into the caller's arrays of length n_kinds (host
+ * pointers), clears the record and returns the number of kinds the library knows. */
+int stc_timing_enable(int32_t on);
+int stc_timing_collect(double* ms_by_kind, int64_t* launches_by_kind, double* alg_bytes_by_kind, int32_t n_kinds);
+const char* stc_kernel_kind_name(int32_t kind);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ SUPPORT_DENSE, SUPPORT_CSR = 0, 1
 EXPORTED = (
     "stc_abi_version", "stc_last_error", "stc_cell_saved_bytes", "stc_cell_bwd_scratch_bytes",
     "stc_cell_fwd", "stc_cell_bwd", "stc_support_apply", "stc_last_launch_count",
+    "stc_timing_enable", "stc_timing_collect", "stc_kernel_kind_name",
 )
 
 
@@ -62,6 +63,12 @@ def load(build_if_missing: bool = True):
     lib.stc_support_apply.restype = c_int
     lib.stc_support_apply.argtypes = [POINTER(StcSupport), c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
                                       c_void_p, c_int64, c_void_p, c_float, c_float, c_void_p]
+    lib.stc_timing_enable.restype = c_int
+    lib.stc_timing_enable.argtypes = [c_int32]
+    lib.stc_timing_collect.restype = c_int
+    lib.stc_timing_collect.argtypes = [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(ctypes.c_double), c_int32]
+    lib.stc_kernel_kind_name.restype = c_char_p
+    lib.stc_kernel_kind_name.argtypes = [c_int32]
     if lib.stc_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libstc_b200.so ABI {lib.stc_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
     _lib = lib
@@ -76,3 +83,27 @@ def check(status: int, what: str) -> None:
 
 def last_launch_count() -> int:
     return int(load().stc_last_launch_count())
+
+
+# running total of kernels launched through the library by this process (bench.py's gpu_launches)
+LAUNCHES = 0
+
+
+def note_launches() -> None:
+    global LAUNCHES
+    LAUNCHES += int(_lib.stc_last_launch_count())
+
+
+def timing_enable(on: bool) -> None:
+    load().stc_timing_enable(1 if on else 0)
+
+
+def timing_collect():
+    """{kernel kind: (device ms, launches, algorithmic bytes)} since the last collect."""
+    lib = load()
+    n = 16
+    ms = (ctypes.c_double * n)()
+    cnt = (c_int64 * n)()
+    by = (ctypes.c_double * n)()
+    kinds = lib.stc_timing_collect(ms, cnt, by, n)
+    return {lib.stc_kernel_kind_name(k).decode(): (ms[k], int(cnt[k]), by[k]) for k in range(kinds) if cnt[k]}

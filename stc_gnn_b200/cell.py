@@ -90,10 +90,11 @@ class _CellFunction(torch.autograd.Function):
         saved = torch.empty(lib.stc_cell_saved_bytes(dims) // 4, dtype=torch.float32, device=Xt.device)
         Hn = torch.empty((B, N, C, h), dtype=torch.float32, device=Xt.device)
         stream = torch.cuda.current_stream().cuda_stream
-        status = lib.stc_cell_fwd(dims, gs_struct, Gc_c.data_ptr(), Xt_c.data_ptr(), xbs, H_c.data_ptr(),
+        status = 0 if B == 0 else lib.stc_cell_fwd(dims, gs_struct, Gc_c.data_ptr(), Xt_c.data_ptr(), xbs, H_c.data_ptr(),
                                   Wg_c.data_ptr(), _ptr(bg_c), Wc_c.data_ptr(), _ptr(bc_c), Hn.data_ptr(),
                                   saved.data_ptr(), saved.numel() * 4, stream)
         _lib.check(status, "stc_cell_fwd")
+        _lib.note_launches()
         ctx.cfg, ctx.dims_tuple, ctx.xbs, ctx.csr = cfg, (B, N, C, Din, h), xbs, csr
         ctx.gs_obj = Gs if csr else None
         ctx.has_bias = bg is not None
@@ -127,12 +128,18 @@ class _CellFunction(torch.autograd.Function):
         dGs = new(N, N) if (need[0] and not ctx.csr) else None
         dGc = new(C, C) if need[1] else None
         scratch = torch.empty(lib.stc_cell_bwd_scratch_bytes(dims) // 4, dtype=torch.float32, device=dev)
+        if B == 0:  # empty batch: every parameter gradient is zero, nothing to launch
+            for g_ in (dWg, dWc, dbg, dbc, dGs, dGc):
+                if g_ is not None:
+                    g_.zero_()
+            return dGs, dGc, dXt, dH, dWg, dbg, dWc, dbc, None
         status = lib.stc_cell_bwd(dims, gs_struct, Gc.data_ptr(), Xt.data_ptr(), ctx.xbs, H.data_ptr(), Wg.data_ptr(),
                                   Wc.data_ptr(), dHn.data_ptr(), _ptr(dXt), dH.data_ptr(), dWg.data_ptr(), _ptr(dbg),
                                   dWc.data_ptr(), _ptr(dbc), _ptr(dGs), _ptr(dGc), 0, saved.data_ptr(),
                                   saved.numel() * 4, scratch.data_ptr(), scratch.numel() * 4,
                                   torch.cuda.current_stream().cuda_stream)
         _lib.check(status, "stc_cell_bwd")
+        _lib.note_launches()
         return dGs, dGc, dXt, dH, dWg, dbg, dWc, dbc, None
 
 

@@ -4,6 +4,9 @@
 
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 namespace stc {
 
 static thread_local char g_err[512] = "";
@@ -17,6 +20,43 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 void reset_launch_count() { g_launches = 0; }
+
+// ---- per-kernel timing record (process-wide, guarded; only touched when enabled) ----
+struct TimedLaunch {
+  int kind;
+  double bytes;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_tmu;
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ScopedKernelTimer::ScopedKernelTimer(int kind, cudaStream_t st_, double alg_bytes) : slot(-1), st(st_) {
+  if (!g_timing) return;
+  std::lock_guard<std::mutex> lk(g_tmu);
+  TimedLaunch t{kind, alg_bytes, take_event(), take_event()};
+  if (!t.e0 || !t.e1) return;
+  cudaEventRecord(t.e0, st);
+  g_timed.push_back(t);
+  slot = (int)g_timed.size() - 1;
+}
+ScopedKernelTimer::~ScopedKernelTimer() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_tmu);
+  if (slot < (int)g_timed.size()) cudaEventRecord(g_timed[slot].e1, st);
+}
 
 int device_sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -114,6 +154,35 @@ static ConvArgs base_args(const StcDims& d, const float* xt, int64_t xt_bs, cons
 using namespace stc;
 
 extern "C" {
+
+int stc_timing_enable(int32_t on) {
+  std::lock_guard<std::mutex> lk(g_tmu);
+  g_timing = on != 0;
+  return STC_OK;
+}
+
+int stc_timing_collect(double* ms, int64_t* launches, double* bytes, int32_t n_kinds) {
+  std::lock_guard<std::mutex> lk(g_tmu);
+  for (auto& t : g_timed) {
+    float m = 0.f;
+    if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&m, t.e0, t.e1) == cudaSuccess &&
+        t.kind < n_kinds) {
+      if (ms) ms[t.kind] += m;
+      if (launches) launches[t.kind] += 1;
+      if (bytes) bytes[t.kind] += t.bytes;
+    }
+    g_event_pool.push_back(t.e0);
+    g_event_pool.push_back(t.e1);
+  }
+  g_timed.clear();
+  return KK_COUNT;
+}
+
+const char* stc_kernel_kind_name(int32_t kind) {
+  static const char* names[KK_COUNT] = {"support_dense", "support_csr", "support_outer", "cheby_small",
+                                        "conv_fwd",      "conv_bwd_dx", "conv_bwd_dw"};
+  return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "?";
+}
 
 int stc_abi_version(void) { return STC_ABI_VERSION; }
 const char* stc_last_error(void) { return g_err; }

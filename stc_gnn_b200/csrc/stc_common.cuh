@@ -39,6 +39,18 @@ void reset_launch_count();
     if (_s != STC_OK) return _s; \
   } while (0)
 
+// ---- optional per-kernel timing (stc_timing_* in the ABI) ---------------------------------------
+enum KernelKind {
+  KK_SUPPORT_DENSE = 0, KK_SUPPORT_CSR, KK_SUPPORT_OUTER, KK_CHEBY_SMALL, KK_CONV_FWD, KK_CONV_BWD_DX,
+  KK_CONV_BWD_DW, KK_COUNT
+};
+struct ScopedKernelTimer {  // declare right before a launch; the destructor records the stop event
+  ScopedKernelTimer(int kind, cudaStream_t st, double alg_bytes);
+  ~ScopedKernelTimer();
+  int slot;
+  cudaStream_t st;
+};
+
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

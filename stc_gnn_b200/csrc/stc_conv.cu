@@ -287,6 +287,11 @@ int launch_conv_fwd(const ConvArgs& a, cudaStream_t st) {
   STC_TRY(pick_rows_fwd(a, &t, &smem, &ni));
   long long total_nodes = (long long)a.B * a.N;
   int grid = ceil_div(total_nodes, t.npt);
+  // compulsory traffic per row: the Ks spatial terms of [x|h] once, then gates: write u, r, r*H;
+  // candidate: read u, H, write c, H'.  Plus the weights.
+  const double R = (double)total_nodes * a.C;
+  ScopedKernelTimer _t(KK_CONV_FWD, st,
+                       4.0 * R * (a.Ks * t.L + (a.phase == 0 ? 3 * a.h : 4 * a.h)) + 4.0 * a.Ks * a.Kc * t.L * a.Hout);
   switch (ni) {
     case 1: STC_TRY(set_smem(conv_fwd_kernel<1>, smem)); conv_fwd_kernel<1><<<grid, CV_THREADS, smem, st>>>(a, t); break;
     case 2: STC_TRY(set_smem(conv_fwd_kernel<2>, smem)); conv_fwd_kernel<2><<<grid, CV_THREADS, smem, st>>>(a, t); break;
@@ -477,6 +482,13 @@ int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st) {
   }
   long long total_nodes = (long long)a.B * a.N;
   int grid = ceil_div(total_nodes, t.npt);
+  // compulsory traffic per row: candidate reads dH',u,c (3h), gates reads dH',u,c,H,r,d(rH) (6h) and writes
+  // the direct dH terms (h); both write dpre (Hout) and the Ks adjoint terms (Ks*L; the gates pass re-reads
+  // the x-part it accumulates into); the spatial terms are re-read only when dGc is wanted.
+  const double R = (double)total_nodes * a.C;
+  ScopedKernelTimer _t(KK_CONV_BWD_DX, st,
+                       4.0 * R * ((a.phase == 0 ? 7 * a.h + a.Ks * a.Din : 3 * a.h) + a.Hout + a.Ks * L +
+                                  ((a.dQ && a.Kc > 1) ? a.Ks * L : 0)) + 4.0 * a.Ks * a.Kc * L * a.Hout);
   switch (ni) {
     case 1: STC_TRY(set_smem(conv_bwd_dx_kernel<1>, smem)); conv_bwd_dx_kernel<1><<<grid, CV_THREADS, smem, st>>>(a, t, DP); break;
     case 2: STC_TRY(set_smem(conv_bwd_dx_kernel<2>, smem)); conv_bwd_dx_kernel<2><<<grid, CV_THREADS, smem, st>>>(a, t, DP); break;
@@ -629,6 +641,9 @@ int launch_conv_bwd_dw(const ConvArgs& a, cudaStream_t st) {
   int tiles_per_cta = ceil_div(ntiles, want_chunks);
   int chunks = ceil_div(ntiles, tiles_per_cta);
   dim3 grid(chunks, P, slabs);
+  // compulsory traffic per row: the Ks spatial terms once and dpre once; plus the dW block written
+  ScopedKernelTimer _t(KK_CONV_BWD_DW, st,
+                       4.0 * (double)total_nodes * a.C * (a.Ks * L + a.Hout) + 4.0 * P * L * a.Hout);
   switch (ni) {
     case 1: STC_TRY(set_smem(conv_bwd_dw_kernel<1>, smem)); conv_bwd_dw_kernel<1><<<grid, CV_THREADS, smem, st>>>(a, t, tiles_per_cta); break;
     case 2: STC_TRY(set_smem(conv_bwd_dw_kernel<2>, smem)); conv_bwd_dw_kernel<2><<<grid, CV_THREADS, smem, st>>>(a, t, tiles_per_cta); break;

@@ -189,6 +189,9 @@ int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool tra
     }
     long long total_q = (long long)B * width;
     dim3 grid(ceil_div(total_q, SD_BQ), ceil_div(N, SD_BM));
+    // compulsory traffic: read X, write Y, (+ read Z) (+ read/modify/write of the axpy target), + the support
+    ScopedKernelTimer _t(KK_SUPPORT_DENSE, st,
+                         4.0 * B * N * width * (2 + (beta != 0.f ? 1 : 0) + (axpy_out ? 2 : 0)) + 4.0 * N * N);
     if (grid.y > 65535) {
       set_error("dense support with N=%d is not tiled (use CSR)", N);
       return STC_ERR_UNSUPPORTED;
@@ -220,6 +223,8 @@ int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool tra
   long long want = (rows_total + warps_per_block - 1) / warps_per_block;
   int grid = (int)(want < (long long)device_sm_count() * 16 ? want : (long long)device_sm_count() * 16);
   if (grid < 1) grid = 1;
+  ScopedKernelTimer _t(KK_SUPPORT_CSR, st,
+                       4.0 * B * N * width * (2 + (beta != 0.f ? 1 : 0) + (axpy_out ? 2 : 0)) + 8.0 * gs.nnz + 4.0 * (N + 1));
   if (vec)
     support_csr_kernel<4><<<grid, warps_per_block * 32, 0, st>>>(rp, ci, va, N, rows_total, x, x_bs, z, z_bs, y,
                                                                   width, alpha, beta, axpy_out, axpy_coef);
@@ -302,6 +307,7 @@ int launch_support_outer(int N, int B, int width, const float* a, int64_t a_bs, 
   int b_per = ceil_div(B, zsplit);
   zsplit = ceil_div(B, b_per);
   dim3 grid(tiles, tiles, zsplit);
+  ScopedKernelTimer _t(KK_SUPPORT_OUTER, st, 4.0 * B * N * width * 2 + 4.0 * N * N);
   support_outer_kernel<<<grid, SO_THREADS, 0, st>>>(N, B, width, a, a_bs, bmat, coef, dG, b_per);
   STC_LAUNCH_OK("support_outer_kernel");
   return STC_OK;
@@ -358,12 +364,14 @@ __global__ void cheby_small_bwd_kernel(const float* __restrict__ G, const float*
 }
 
 int launch_cheby_small(const float* G, int C, int K, float* Q, cudaStream_t st) {
+  ScopedKernelTimer _t(KK_CHEBY_SMALL, st, 4.0 * C * C * (K + 1));
   cheby_small_kernel<<<1, 256, 0, st>>>(G, C, K, Q);
   STC_LAUNCH_OK("cheby_small_kernel");
   return STC_OK;
 }
 
 int launch_cheby_small_bwd(const float* G, const float* Q, float* dQ, int C, int K, float* dG, cudaStream_t st) {
+  ScopedKernelTimer _t(KK_CHEBY_SMALL, st, 4.0 * C * C * (2 * K + 2));
   cheby_small_bwd_kernel<<<1, 256, 0, st>>>(G, Q, dQ, C, K, dG);
   STC_LAUNCH_OK("cheby_small_bwd_kernel");
   return STC_OK;

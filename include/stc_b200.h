@@ -119,6 +119,10 @@ int stc_support_apply(const StcSupport* gs, int32_t N, int32_t B, int32_t width,
                       const float* x, int64_t x_batch_stride, const float* z, int64_t z_batch_stride,
                       float* y, float alpha, float beta, void* stream);
 
+/* Building block self-test / microbenchmark: D[M][N] = A[M][K] * B[K][N], row-major fp32, evaluated as a
+ * 3xTF32 tcgen05 product with TMEM accumulation (the same code path as the gate contraction).  N <= 256. */
+int stc_tf32x3_gemm(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K, void* stream);
+
 /* Number of kernel launches the last stc_cell_fwd / stc_cell_bwd on this thread issued
  * (bench.py reports gpu_launches from these). */
 int stc_last_launch_count(void);

@@ -18,7 +18,7 @@ SUPPORT_DENSE, SUPPORT_CSR = 0, 1
 EXPORTED = (
     "stc_abi_version", "stc_last_error", "stc_cell_saved_bytes", "stc_cell_bwd_scratch_bytes",
     "stc_cell_fwd", "stc_cell_bwd", "stc_support_apply", "stc_last_launch_count",
-    "stc_timing_enable", "stc_timing_collect", "stc_kernel_kind_name",
+    "stc_timing_enable", "stc_timing_collect", "stc_kernel_kind_name", "stc_tf32x3_gemm",
 )
 
 
@@ -63,6 +63,8 @@ def load(build_if_missing: bool = True):
     lib.stc_support_apply.restype = c_int
     lib.stc_support_apply.argtypes = [POINTER(StcSupport), c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
                                       c_void_p, c_int64, c_void_p, c_float, c_float, c_void_p]
+    lib.stc_tf32x3_gemm.restype = c_int
+    lib.stc_tf32x3_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     lib.stc_timing_enable.restype = c_int
     lib.stc_timing_enable.argtypes = [c_int32]
     lib.stc_timing_collect.restype = c_int

@@ -180,7 +180,8 @@ int stc_timing_collect(double* ms, int64_t* launches, double* bytes, int32_t n_k
 
 const char* stc_kernel_kind_name(int32_t kind) {
   static const char* names[KK_COUNT] = {"support_dense", "support_csr", "support_outer", "cheby_small",
-                                        "conv_fwd",      "conv_bwd_dx", "conv_bwd_dw"};
+                                        "conv_fwd",      "conv_bwd_dx", "conv_bwd_dw", "tc_conv_fwd", "tc_conv_bwd_dx", "tc_conv_bwd_dw",
+                                        "tc_support", "tc_gemm_test"};
   return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "?";
 }
 
@@ -208,6 +209,16 @@ int stc_support_apply(const StcSupport* gs, int32_t N, int32_t B, int32_t width,
   STC_TRY(check_arch());
   return launch_support_apply(*gs, N, B, width, transpose != 0, x, x_batch_stride, z, z_batch_stride, y, alpha,
                               beta, nullptr, 0.f, (cudaStream_t)stream);
+}
+
+int stc_tf32x3_gemm(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K, void* stream) {
+  reset_launch_count();
+  if (!a || !b || !d) {
+    set_error("stc_tf32x3_gemm: NULL argument");
+    return STC_ERR_BAD_ARG;
+  }
+  STC_TRY(check_arch());
+  return launch_tf32x3_gemm(a, b, d, M, N, K, (cudaStream_t)stream);
 }
 
 int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,

@@ -42,7 +42,7 @@ void reset_launch_count();
 // ---- optional per-kernel timing (stc_timing_* in the ABI) ---------------------------------------
 enum KernelKind {
   KK_SUPPORT_DENSE = 0, KK_SUPPORT_CSR, KK_SUPPORT_OUTER, KK_CHEBY_SMALL, KK_CONV_FWD, KK_CONV_BWD_DX,
-  KK_CONV_BWD_DW, KK_COUNT
+  KK_CONV_BWD_DW, KK_TC_CONV_FWD, KK_TC_CONV_BWD_DX, KK_TC_CONV_BWD_DW, KK_TC_SUPPORT, KK_TC_GEMM_TEST, KK_COUNT
 };
 struct ScopedKernelTimer {  // declare right before a launch; the destructor records the stop event
   ScopedKernelTimer(int kind, cudaStream_t st, double alg_bytes);
@@ -110,6 +110,7 @@ struct ConvArgs {
   float* dQ;           // [Kc][C][C] atomically accumulated, or null
   float* dW;           // atomically accumulated
 };
+int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, cudaStream_t st);
 int launch_conv_fwd(const ConvArgs& a, cudaStream_t st);
 int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st);
 int launch_conv_bwd_dw(const ConvArgs& a, cudaStream_t st);

@@ -1,0 +1,518 @@
+// tcgen05 / TMEM version of the gate / candidate weight contraction with the categorical mix and the GRU
+// epilogue fused (forward).  Replaces conv_fwd_kernel (stc_conv.cu) whenever the shape is eligible; the
+// arithmetic is the reference's 'bmdk,kh->bmdh' (/root/reference/framework/STC_GNN.py:42) evaluated as a
+// 3xTF32 tensor-core product (see stc_tc.cuh), bias/activation (:44-46) and sigmoid / tanh / blend
+// (STC_GNN.py:71-78) applied on the accumulator as it is read back from TMEM.
+//
+// One persistent CTA per SM slot.  Per 128-row tile (whole nodes x all categories):
+//   for each spatial Chebyshev term k:  stage [rows][L] fp32 <- HBM (x-part | h-part)
+//     for each categorical term c and each 32-wide K atom j:
+//        CUDA cores build the A atom (mix with T_c(Gc) on the fly, split hi/lo, 128B-swizzled K-major)
+//        into one of two buffers; one thread issues 3 x ksteps tcgen05.mma against the resident W atoms;
+//        tcgen05.commit -> mbarrier releases the buffer two atoms later.
+//   epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias, activation, sigmoid/tanh, GRU blend, stores.
+#include "stc_conv_common.cuh"
+#include "stc_tc.cuh"
+
+#include <stdlib.h>
+
+namespace stc {
+
+using namespace tc;
+
+// Formulation.  With P_c = sum_k Y_k W_{k,c}  (Y_k the k-th spatial term of [Xt | H], rows = (node, category)),
+//     out[(node,d)] = P_0[(node,d)] + sum_{c>=1} sum_{c'} T_c(Gc)[c',d] * P_c[(node,c')]
+// i.e. the categorical mode product is applied to the GEMM *output* (Hout wide) instead of to the features
+// (K wide): the A operand is the raw staged tile, the GEMM is [rows x Ks*KBL] x [Ks*KBL x Kc*Hout], and the
+// C x C mix runs in the epilogue on values read back from TMEM.  Same arithmetic as STC_GNN.py:35-45 with the
+// two linear maps commuted.
+//
+// K layout of one spatial term: [ h-part (h floats) | x-part (Din floats, zero-padded to Dp) ] so that 16-byte
+// chunks never straddle the two source tensors; the rows of W are permuted to match in the resident B atoms.
+struct TcFwdPlan {
+  int npt;        // nodes per tile (rows = npt*C <= 128)
+  int Dp;         // Din rounded up to 8
+  int KBL;        // h + Dp
+  int KB;         // 32-wide atoms per spatial term
+  int Ntot;       // Kc * Hout (GEMM N)
+  int Npad;       // Ntot rounded up to 16
+  int nacc;       // main accumulators = Ks*KB (one per atom); the cross-term accumulator follows them
+  int tmem_cols;  // power of two
+  int ntiles;
+  int x_bulk;     // x-part can be staged with bulk copies (16-byte aligned rows)
+  int PS;         // row stride (floats) of the epilogue exchange buffer
+  uint32_t off_a, off_b, off_sh, off_sx, off_q, off_bar, smem_bytes;
+};
+
+// thread 0: stage every spatial term of tile `tile` with bulk copies that complete on `bar`
+__device__ __forceinline__ void tc_issue_tile_loads(const ConvArgs& a, const TcFwdPlan& p, int tile, float* stage_h,
+                                                    float* stage_x, uint64_t* bar) {
+  const long long total_nodes = (long long)a.B * a.N;
+  const long long g0 = (long long)tile * p.npt;
+  const int nv = (int)min((long long)p.npt, total_nodes - g0);
+  const long long R = total_nodes * a.C;
+  const int CH = a.C * a.h, CD = a.C * a.Din;
+  uint32_t bytes = (uint32_t)(a.Ks * nv * CH * 4);
+  if (p.x_bulk) bytes += (uint32_t)(a.Ks * nv * CD * 4);
+  mbar_arrive_expect_tx(bar, bytes);
+  for (int k = 0; k < a.Ks; ++k) {
+    const float* hsrc = (k == 0 ? a.h0 : a.yh + (long long)(k - 1) * R * a.h) + g0 * CH;
+    bulk_g2s(stage_h + (size_t)k * 128 * a.h, hsrc, (uint32_t)(nv * CH * 4), bar);
+    if (!p.x_bulk) continue;
+    float* dst = stage_x + (size_t)k * 128 * a.Din;
+    if (k > 0) {
+      bulk_g2s(dst, a.yx + (long long)(k - 1) * R * a.Din + g0 * CD, (uint32_t)(nv * CD * 4), bar);
+    } else {  // Xt carries a batch stride: one copy per sample segment
+      long long g = g0;
+      int left = nv;
+      while (left > 0) {
+        const long long b = g / a.N;
+        const int m = (int)(g - b * a.N);
+        const int seg = min(left, a.N - m);
+        bulk_g2s(dst, a.x0 + b * a.x0_bs + (long long)m * CD, (uint32_t)(seg * CD * 4), bar);
+        dst += seg * CD;
+        g += seg;
+        left -= seg;
+      }
+    }
+  }
+}
+
+// sum of the per-atom partials of 8 accumulator columns starting at column c0 (cross terms first, fp32 RN adds)
+__device__ __forceinline__ void tc_read_acc8(uint32_t tl, const TcFwdPlan& p, int c0, float (&v)[8]) {
+  float t[8];
+  tmem_ld8(tl + (uint32_t)(p.nacc * p.Npad + c0), v);
+  for (int m = 0; m < p.nacc; ++m) {
+    tmem_ld8(tl + (uint32_t)(m * p.Npad + c0), t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += t[i];
+  }
+}
+
+__global__ void __launch_bounds__(CV_THREADS, 2)
+tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();  // swizzled atoms need a 1024-byte aligned base
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, L = a.Din + a.h, h = a.h, Din = a.Din, Hout = a.Hout;
+  const uint32_t atomA = 128 * ATOM_ROW_BYTES;            // 16 KB
+  const uint32_t atomB = (uint32_t)p.Npad * ATOM_ROW_BYTES;
+  uint8_t* A_hi = smem + p.off_a;
+  uint8_t* A_lo = A_hi + atomA;
+  float* Pm = reinterpret_cast<float*>(A_hi);             // epilogue exchange buffer aliases the A atoms
+  uint8_t* B_hi = smem + p.off_b;                          // [Ks*KB][atomB]
+  uint8_t* B_lo = B_hi + (size_t)p.nacc * atomB;
+  float* stage_h = reinterpret_cast<float*>(smem + p.off_sh);   // [Ks][128][h]
+  float* stage_x = reinterpret_cast<float*>(smem + p.off_sx);   // [Ks][128][Din]
+  float* Qs = reinterpret_cast<float*>(smem + p.off_q);         // [(Kc-1)][C][C]
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* load_bar = mma_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 2);
+
+  // ---- one-time setup ----
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    mbar_init(load_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  for (int i = tid; i < (a.Kc - 1) * C * C; i += CV_THREADS) Qs[i] = a.Q[C * C + i];
+  for (int i = tid; i < a.Ks * 128 * h; i += CV_THREADS) stage_h[i] = 0.f;
+  for (int i = tid; i < a.Ks * 128 * Din; i += CV_THREADS) stage_x[i] = 0.f;
+  // resident B atoms: Bt[(c,o)][kb] = W[((k*Kc + c)*L + l(kb))*Hout + o]
+  for (int k = 0; k < a.Ks; ++k)
+    for (int j = 0; j < p.KB; ++j) {
+      uint8_t* bh = B_hi + (size_t)(k * p.KB + j) * atomB;
+      uint8_t* bl = B_lo + (size_t)(k * p.KB + j) * atomB;
+      for (int it = tid; it < p.Npad * 8; it += CV_THREADS) {
+        const int n = it >> 3, qq = it & 7;
+        const int c = n / Hout, o = n - c * Hout;
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kb = j * ATOM_K + qq * 4 + i;
+          const int l = kb < h ? Din + kb : (kb - h < Din ? kb - h : -1);
+          v[i] = (n < p.Ntot && l >= 0) ? a.W[((size_t)(k * a.Kc + c) * L + l) * Hout + o] : 0.f;
+        }
+        store_split4(bh, bl, atom_chunk_offset(n, qq), make_float4(v[0], v[1], v[2], v[3]));
+      }
+    }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, p.Npad);
+  const uint32_t d_small = tmem_base + (uint32_t)(p.nacc * p.Npad);
+  const long long total_nodes = (long long)a.B * a.N;
+  const long long R = total_nodes * C;
+
+  // build mapping: this thread always writes chunk column q of rows r0 + 32 i
+  const int q = tid & 7, r0 = tid >> 3;
+  uint32_t aoff[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) aoff[i] = atom_chunk_offset(r0 + 32 * i, q);
+  // epilogue mapping: this thread owns accumulator row erow and every second 8-column chunk
+  const int lane_base = (warp & 3) * 32, half = warp >> 2;
+  const int erow = lane_base + lane;
+  const int enode = erow / C, ecat = erow - enode * C;
+  const uint32_t tl = tmem_base + ((uint32_t)lane_base << 16);
+
+  uint32_t mma_phase = 0, load_phase = 0;
+  bool mma_pending = false;
+  if (tid == 0 && (int)blockIdx.x < p.ntiles) tc_issue_tile_loads(a, p, blockIdx.x, stage_h, stage_x, load_bar);
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long g0 = (long long)tile * p.npt;
+    const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
+    const int rows_valid = nodes_valid * C;
+    mbar_wait(load_bar, load_phase);
+    load_phase ^= 1u;
+    if (!p.x_bulk) {  // unaligned x-part (e.g. Din = 1): plain loads, it is tiny
+      for (int k = 0; k < a.Ks; ++k) {
+        float* dst = stage_x + (size_t)k * 128 * Din;
+        const int per_node = C * Din;
+        for (int idx = tid; idx < nodes_valid * per_node; idx += CV_THREADS) {
+          const int node = idx / per_node, rem = idx - node * per_node;
+          const long long g = g0 + node;
+          const float* src;
+          if (k == 0) {
+            const long long b = g / a.N;
+            src = a.x0 + b * a.x0_bs + (g - b * a.N) * per_node;
+          } else {
+            src = a.yx + (long long)(k - 1) * R * Din + g * per_node;
+          }
+          dst[idx] = src[rem];
+        }
+      }
+      __syncthreads();
+    }
+    bool acc_small = false;
+    int ai = 0;
+    for (int k = 0; k < a.Ks; ++k) {
+      const float* sh = stage_h + (size_t)k * 128 * h;
+      const float* sx = stage_x + (size_t)k * 128 * Din;
+      for (int j = 0; j < p.KB; ++j, ++ai) {
+        if (mma_pending) {  // single A buffer: the previous atom's MMAs must have read it
+          mbar_wait(mma_bar, mma_phase);
+          mma_phase ^= 1u;
+          mma_pending = false;
+        }
+        const int kb = j * ATOM_K + q * 4;
+        if (kb < h) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            store_split4(A_hi, A_lo, aoff[i], *reinterpret_cast<const float4*>(sh + (r0 + 32 * i) * h + kb));
+        } else if (p.x_bulk && kb - h < Din) {  // Din % 4 == 0: whole chunks
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            store_split4(A_hi, A_lo, aoff[i], *reinterpret_cast<const float4*>(sx + (r0 + 32 * i) * Din + (kb - h)));
+        } else {
+          const int xi = kb - h;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* sp = sx + (r0 + 32 * i) * Din + xi;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (xi + t < Din) e[t] = sp[t];
+            store_split4(A_hi, A_lo, aoff[i], make_float4(e[0], e[1], e[2], e[3]));
+          }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          // the stage is dead after the last build of this tile: prefetch the next tile under the MMAs + epilogue
+          if (ai == p.nacc - 1 && tile + (int)gridDim.x < p.ntiles)
+            tc_issue_tile_loads(a, p, tile + gridDim.x, stage_h, stage_x, load_bar);
+          fence_after_sync();
+          const int kleft = p.KBL - j * ATOM_K;
+          const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
+          const size_t bofs = (size_t)ai * atomB;
+          bool acc_main = false;
+          mma_atom_3x_split(tmem_base + (uint32_t)(ai * p.Npad), d_small, smem_u32(A_hi), smem_u32(A_lo),
+                            smem_u32(B_hi + bofs), smem_u32(B_lo + bofs), ksteps, idesc, acc_main, acc_small);
+          mma_commit(mma_bar);
+        }
+        acc_small = true;
+        mma_pending = true;
+      }
+    }
+    // ---- epilogue ----
+    mbar_wait(mma_bar, mma_phase);   // a commit covers every MMA issued before it; the A atoms are free too
+    mma_phase ^= 1u;
+    mma_pending = false;
+    fence_after_sync();
+    const bool valid = erow < rows_valid;
+    const long long gr = g0 * C + erow;
+    for (int c0 = half * 8; c0 < Hout; c0 += 16) {
+      float v[8];
+      tc_read_acc8(tl, p, c0, v);                                   // P_0
+      for (int c = 1; c < a.Kc; ++c) {                              // + T_c(Gc)^T-mix of P_c over the node's categories
+        float t[8];
+        tc_read_acc8(tl, p, c * Hout + c0, t);
+        __syncthreads();                                            // previous users of Pm are done
+        *reinterpret_cast<float4*>(Pm + erow * p.PS + c0) = make_float4(t[0], t[1], t[2], t[3]);
+        *reinterpret_cast<float4*>(Pm + erow * p.PS + c0 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+        __syncthreads();
+        const float* Qc = Qs + (size_t)(c - 1) * C * C;
+        const float* pp = Pm + (enode * C) * p.PS + c0;
+        for (int cp = 0; cp < C; ++cp) {
+          const float w = Qc[cp * C + ecat];
+          const float4 x0 = *reinterpret_cast<const float4*>(pp + cp * p.PS);
+          const float4 x1 = *reinterpret_cast<const float4*>(pp + cp * p.PS + 4);
+          v[0] = fmaf(w, x0.x, v[0]); v[1] = fmaf(w, x0.y, v[1]); v[2] = fmaf(w, x0.z, v[2]); v[3] = fmaf(w, x0.w, v[3]);
+          v[4] = fmaf(w, x1.x, v[4]); v[5] = fmaf(w, x1.y, v[5]); v[6] = fmaf(w, x1.z, v[6]); v[7] = fmaf(w, x1.w, v[7]);
+        }
+      }
+      if (!valid) continue;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float pre = v[i] + (a.bias ? a.bias[c0 + i] : 0.f);
+        if (a.act == STC_ACT_RELU) pre = fmaxf(pre, 0.f);
+        v[i] = pre;
+      }
+      if (a.phase == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = sigmoidf_acc(v[i]);
+        if (c0 < h) {
+          float4* dst = reinterpret_cast<float4*>(a.u + gr * h + c0);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          const long long o = gr * h + (c0 - h);
+          const float4 h0 = *reinterpret_cast<const float4*>(a.Hprev + o);
+          const float4 h1 = *reinterpret_cast<const float4*>(a.Hprev + o + 4);
+          float4* dr = reinterpret_cast<float4*>(a.r + o);
+          dr[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dr[1] = make_float4(v[4], v[5], v[6], v[7]);
+          float4* drh = reinterpret_cast<float4*>(a.rH + o);
+          drh[0] = make_float4(v[0] * h0.x, v[1] * h0.y, v[2] * h0.z, v[3] * h0.w);
+          drh[1] = make_float4(v[4] * h1.x, v[5] * h1.y, v[6] * h1.z, v[7] * h1.w);
+        }
+      } else {
+        const long long o = gr * h + c0;
+        float uu[8], hp[8], cc[8], hn[8];
+        *reinterpret_cast<float4*>(uu) = *reinterpret_cast<const float4*>(a.u + o);
+        *reinterpret_cast<float4*>(uu + 4) = *reinterpret_cast<const float4*>(a.u + o + 4);
+        *reinterpret_cast<float4*>(hp) = *reinterpret_cast<const float4*>(a.Hprev + o);
+        *reinterpret_cast<float4*>(hp + 4) = *reinterpret_cast<const float4*>(a.Hprev + o + 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          cc[i] = tanhf(v[i]);
+          hn[i] = fmaf(uu[i], cc[i] - hp[i], hp[i]);
+        }
+        float4* dc = reinterpret_cast<float4*>(a.c + o);
+        dc[0] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+        dc[1] = make_float4(cc[4], cc[5], cc[6], cc[7]);
+        float4* dh = reinterpret_cast<float4*>(a.Hnew + o);
+        dh[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        dh[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+      }
+    }
+    fence_before_sync();  // TMEM reads are ordered before the next tile's first (overwriting) MMA,
+    __syncthreads();      // and the exchange buffer is free before the next tile's A build
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+static bool tc_disabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("STC_DISABLE_TC");
+    cached = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (tc_disabled()) return STC_OK;
+  const int L = a.Din + a.h, P = a.Ks * a.Kc;
+  if (a.h % 8 != 0 || a.Hout % 16 != 0 || a.C > 128) return STC_OK;
+  if (!aligned16p(a.u) || !aligned16p(a.Hprev) || !aligned16p(a.r) || !aligned16p(a.rH) || !aligned16p(a.c) ||
+      !aligned16p(a.Hnew) || !aligned16p(a.h0) || !aligned16p(a.yh))
+    return STC_OK;
+  TcFwdPlan p;
+  p.npt = 128 / a.C;
+  p.Dp = (a.Din + 7) & ~7;
+  p.KBL = a.h + p.Dp;
+  p.KB = (p.KBL + ATOM_K - 1) / ATOM_K;
+  p.Ntot = a.Kc * a.Hout;
+  p.Npad = (p.Ntot + 15) & ~15;
+  if (p.Npad > 256) return STC_OK;
+  p.nacc = a.Ks * p.KB;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < (p.nacc + 1) * p.Npad) p.tmem_cols *= 2;
+  if (p.tmem_cols > 512) return STC_OK;
+  p.PS = a.Hout + 4;
+  if ((size_t)128 * p.PS * sizeof(float) > 2 * 128 * ATOM_ROW_BYTES) return STC_OK;  // exchange buffer aliases A
+  p.x_bulk = (a.Din % 4 == 0) && (a.x0_bs % 4 == 0) && aligned16p(a.x0) && aligned16p(a.yx);
+  const long long total_nodes = (long long)a.B * a.N;
+  p.ntiles = ceil_div(total_nodes, p.npt);
+  const size_t atomB = (size_t)p.Npad * ATOM_ROW_BYTES;
+  size_t o = 0;
+  p.off_a = (uint32_t)o; o += 2 * 128 * ATOM_ROW_BYTES;                 // A hi + lo (one atom)
+  p.off_b = (uint32_t)o; o += 2 * (size_t)p.nacc * atomB;               // resident W atoms hi/lo
+  p.off_sh = (uint32_t)o; o += (size_t)a.Ks * 128 * a.h * sizeof(float);
+  p.off_sx = (uint32_t)o; o += round_up((size_t)a.Ks * 128 * a.Din * sizeof(float), 16);
+  p.off_q = (uint32_t)o; o += (size_t)(a.Kc > 1 ? a.Kc - 1 : 0) * a.C * a.C * sizeof(float);
+  o = round_up(o, 16);
+  p.off_bar = (uint32_t)o; o += 32;
+  p.smem_bytes = (uint32_t)o;
+  if (p.smem_bytes > 200 * 1024) return STC_OK;  // not an SF-class shape: the FFMA path handles it
+  STC_TRY(set_smem(tc_conv_fwd_kernel, p.smem_bytes));
+  int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 2) ctas_per_sm = 2;
+  if (ctas_per_sm * p.tmem_cols > 512) ctas_per_sm = 512 / p.tmem_cols;
+  int grid = device_sm_count() * ctas_per_sm;
+  if (grid > p.ntiles) grid = p.ntiles;
+  const double R = (double)total_nodes * a.C;
+  ScopedKernelTimer _t(KK_TC_CONV_FWD, st,
+                       4.0 * R * (a.Ks * L + (a.phase == 0 ? 3 * a.h : 4 * a.h)) + 4.0 * P * L * a.Hout);
+  tc_conv_fwd_kernel<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
+  STC_LAUNCH_OK("tc_conv_fwd_kernel");
+  *handled = true;
+  return STC_OK;
+}
+
+// =================================================================================================
+// self-test / microbenchmark of the building block:  D[M][N] = A[M][K] * Bm[K][N]  (3xTF32)
+//   mode bit 0: truncating split instead of round-to-nearest (experiment)
+//   nmain: number of main (hi*hi) accumulators used round-robin over K atoms; small != 0: the cross terms
+//   get their own accumulator.  All accumulators are summed in fp32 round-to-nearest in the epilogue.
+// =================================================================================================
+__global__ void __launch_bounds__(CV_THREADS, 1)
+tf32x3_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ D, int M, int N,
+                   int K, int Npad, int tmem_cols, int mode, int nmain, int small) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t atomA = 128 * ATOM_ROW_BYTES, atomB = (uint32_t)Npad * ATOM_ROW_BYTES;
+  uint8_t* A_hi = smem;
+  uint8_t* A_lo = A_hi + atomA;
+  uint8_t* B_hi = A_lo + atomA;
+  uint8_t* B_lo = B_hi + atomB;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(B_lo + atomB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, Npad);
+  const int m0 = blockIdx.x * 128;
+  uint32_t phase = 0;
+  bool acc_main[16], acc_small = false;
+  for (int i = 0; i < 16; ++i) acc_main[i] = false;
+  const int natoms = (K + ATOM_K - 1) / ATOM_K;
+  for (int j = 0; j < natoms; ++j) {
+    if (j > 0) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    }
+    for (int it = tid; it < 128 * 8; it += CV_THREADS) {
+      const int row = it >> 3, q = it & 7;
+      float v[4], hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = j * ATOM_K + q * 4 + i;
+        v[i] = (m0 + row < M && k < K) ? A[(size_t)(m0 + row) * K + k] : 0.f;
+        if (mode & 1) split_tf32_trunc(v[i], hi[i], lo[i]); else split_tf32(v[i], hi[i], lo[i]);
+      }
+      const uint32_t off = atom_chunk_offset(row, q);
+      *reinterpret_cast<float4*>(A_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(A_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    for (int it = tid; it < Npad * 8; it += CV_THREADS) {
+      const int n = it >> 3, q = it & 7;
+      float v[4], hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = j * ATOM_K + q * 4 + i;
+        v[i] = (n < N && k < K) ? Bm[(size_t)k * N + n] : 0.f;
+        if (mode & 1) split_tf32_trunc(v[i], hi[i], lo[i]); else split_tf32(v[i], hi[i], lo[i]);
+      }
+      const uint32_t off = atom_chunk_offset(n, q);
+      *reinterpret_cast<float4*>(B_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(B_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const int kleft = K - j * ATOM_K;
+      const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
+      const int mi = j % nmain;
+      const uint32_t d_main = tmem_base + (uint32_t)(mi * Npad);
+      if (small) {
+        const uint32_t d_small = tmem_base + (uint32_t)(nmain * Npad);
+        mma_atom_3x_split(d_main, d_small, smem_u32(A_hi), smem_u32(A_lo), smem_u32(B_hi), smem_u32(B_lo), ksteps, idesc,
+                          acc_main[mi], acc_small);
+      } else {
+        mma_atom_3x(d_main, smem_u32(A_hi), smem_u32(A_lo), smem_u32(B_hi), smem_u32(B_lo), ksteps, idesc, acc_main[mi]);
+      }
+      mma_commit(bar);
+    }
+  }
+  mbar_wait(bar, phase);
+  fence_after_sync();
+  {
+    const int lane_base = (warp & 3) * 32, half = warp >> 2;
+    const int row = m0 + lane_base + lane;
+    const int nchunks = Npad / 8;
+    const int nbuf = (natoms < nmain ? natoms : nmain);
+    for (int ch = half; ch < nchunks; ch += 2) {
+      float acc[8], v[8];
+      if (small) {
+        tmem_ld8(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(nmain * Npad + ch * 8), acc);
+      } else {
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      }
+      for (int b = 0; b < nbuf; ++b) {
+        tmem_ld8(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(b * Npad + ch * 8), v);
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+      if (row < M)
+        for (int i = 0; i < 8; ++i)
+          if (ch * 8 + i < N) D[(size_t)row * N + ch * 8 + i] = acc[i];
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0 || N > 256) {
+    set_error("tf32x3 gemm self-test: need M,K > 0 and 0 < N <= 256");
+    return STC_ERR_BAD_ARG;
+  }
+  // experiment knobs (defaults = what the production kernels use)
+  int mode = 0, nmain = 1, small = 0;
+  if (const char* e = getenv("STC_TC_TEST_MODE")) mode = atoi(e);
+  if (const char* e = getenv("STC_TC_TEST_NMAIN")) nmain = atoi(e);
+  if (const char* e = getenv("STC_TC_TEST_SMALL")) small = atoi(e);
+  const int Npad = (N + 15) & ~15;
+  if (nmain < 1) nmain = 1;
+  if (nmain > 15) nmain = 15;
+  while ((nmain + (small ? 1 : 0)) * Npad > 512 && nmain > 1) --nmain;
+  int tmem_cols = 32;
+  while (tmem_cols < (nmain + (small ? 1 : 0)) * Npad) tmem_cols *= 2;
+  const size_t smem = 2 * 128 * ATOM_ROW_BYTES + 2 * (size_t)Npad * ATOM_ROW_BYTES + 64;
+  STC_TRY(set_smem(tf32x3_gemm_kernel, smem));
+  ScopedKernelTimer _t(KK_TC_GEMM_TEST, st, 4.0 * ((double)M * K + (double)K * N + (double)M * N));
+  tf32x3_gemm_kernel<<<ceil_div(M, 128), CV_THREADS, smem, st>>>(A, Bm, D, M, N, K, Npad, tmem_cols, mode, nmain, small);
+  STC_LAUNCH_OK("tf32x3_gemm_kernel");
+  return STC_OK;
+}
+
+}  // namespace stc

@@ -1,0 +1,181 @@
+// tcgen05 / TMEM helpers for the tensor-core kernels (sm_100a only).
+//
+// Precision scheme ("3xTF32"): every fp32 operand a is split as a = hi + lo with hi = a with the low 13
+// mantissa bits cleared (exactly a TF32 value) and lo = a - hi (exact in fp32), again cleared to TF32.
+// A product is evaluated as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM; the dropped lo*lo term
+// is ~2^-20 relative, which keeps the reference's rtol 1e-4 with margin (single-pass TF32 does not).
+//
+// Operand layout in shared memory: K-major, 128-byte swizzle.  One "atom" is 32 fp32 along K (128 bytes)
+// by R rows; rows are grouped by 8 (1024 contiguous bytes per group), the 16-byte chunk index inside a
+// 128-byte row is XOR-ed with (row % 8).  Atoms must be 1024-byte aligned.  One tcgen05.mma of
+// kind::tf32 consumes K = 8 (32 bytes): K-steps inside an atom advance the descriptor start address by
+// 32 bytes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stc {
+namespace tc {
+
+constexpr int ATOM_K = 32;            // fp32 elements along K per 128-byte swizzle row
+constexpr int ATOM_ROW_BYTES = 128;
+constexpr int GROUP_BYTES = 1024;     // 8 rows x 128 B
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of (row, 16-byte chunk q in [0,8)) inside a K-major SW128 atom
+__device__ __forceinline__ uint32_t atom_chunk_offset(int row, int q) {
+  return (uint32_t)((row >> 3) * GROUP_BYTES + (row & 7) * ATOM_ROW_BYTES + ((q ^ (row & 7)) << 4));
+}
+
+// round-to-nearest TF32 (cvt.rna): the result has its low 13 mantissa bits clear
+__device__ __forceinline__ float to_tf32_rn(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+// hi = RN_tf32(v), lo = v - hi (exact).  The tensor core ignores lo's 13 low mantissa bits; because hi is
+// rounded to nearest, lo has no preferred sign and that truncation is unbiased: |v - hi - tf32(lo)| <= 2^-21 |v|
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = to_tf32_rn(v);
+  lo = v - hi;
+}
+__device__ __forceinline__ void split_tf32_trunc(float v, float& hi, float& lo) {  // experiment only
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = __uint_as_float(__float_as_uint(v - hi) & 0xFFFFE000u);
+}
+
+__device__ __forceinline__ void store_split4(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, float4 v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x);
+  split_tf32(v.y, h.y, l.y);
+  split_tf32(v.z, h.z, l.z);
+  split_tf32(v.w, h.w, l.w);
+  *reinterpret_cast<float4*>(a_hi + off) = h;
+  *reinterpret_cast<float4*>(a_lo + off) = l;
+}
+
+// ---- descriptors ---------------------------------------------------------------------------------
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, SBO = 1024 B (8-row group pitch), LBO unused (=1)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(GROUP_BYTES >> 4) << 32;           // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: kind::tf32, fp32 accumulate, A and B K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- TMEM ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 lanes x 8 consecutive fp32 columns -> 8 registers per thread (thread t of warp w <-> lane 32*(w%4)+t)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+  v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+
+// ---- MMA issue (one thread) ------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when complete
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// same product with the two small cross terms going to their own accumulator (d_small) so that the main
+// accumulator only ever adds hi*hi products (fewer, larger, equally scaled additions)
+__device__ __forceinline__ void mma_atom_3x_split(uint32_t d_main, uint32_t d_small, uint32_t a_hi, uint32_t a_lo,
+                                                  uint32_t b_hi, uint32_t b_lo, int ksteps, uint32_t idesc,
+                                                  bool& acc_main, bool& acc_small) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t o = ks * 32;
+    const uint64_t ah = make_smem_desc_sw128(a_hi + o), al = make_smem_desc_sw128(a_lo + o);
+    const uint64_t bh = make_smem_desc_sw128(b_hi + o), bl = make_smem_desc_sw128(b_lo + o);
+    mma_tf32(d_small, al, bh, idesc, acc_small ? 1u : 0u);
+    mma_tf32(d_small, ah, bl, idesc, 1u);
+    mma_tf32(d_main, ah, bh, idesc, acc_main ? 1u : 0u);
+    acc_main = true;
+    acc_small = true;
+  }
+}
+
+// 3xTF32 product of one atom pair over `ksteps` K-steps of 8: D (+)= A_hi B_hi + A_hi B_lo + A_lo B_hi
+__device__ __forceinline__ void mma_atom_3x(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                            uint32_t b_lo, int ksteps, uint32_t idesc, bool& accumulate) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t o = ks * 32;
+    const uint64_t ah = make_smem_desc_sw128(a_hi + o), al = make_smem_desc_sw128(a_lo + o);
+    const uint64_t bh = make_smem_desc_sw128(b_hi + o), bl = make_smem_desc_sw128(b_lo + o);
+    mma_tf32(d_tmem, al, bh, idesc, accumulate ? 1u : 0u);  // small terms first
+    mma_tf32(d_tmem, ah, bl, idesc, 1u);
+    mma_tf32(d_tmem, ah, bh, idesc, 1u);
+    accumulate = true;
+  }
+}
+
+// ---- bulk async copy global -> shared (TMA 1-D), completion counted in bytes on an mbarrier --------
+// dst, src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// ---- mbarrier --------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+}  // namespace tc
+}  // namespace stc

@@ -134,15 +134,23 @@ def test_stack_matches_reference_golden():
     out = stack(Gs, Gc, X)
     O.assert_close(out.detach().cpu(), t["out"], "stack out")
     out.backward(t["dOut"].to(DEV))
-    O.assert_close(Gs.grad.cpu(), t["dGs"], "dGs")
-    O.assert_close(Gc.grad.cpu(), t["dGc"], "dGc")
-    O.assert_close(X.grad.cpu(), t["dX_seq"], "dX_seq")
+    # Gradients through 24 chained cells: the reference's own fp32 evaluation deviates from fp64 by up to
+    # 1.7e-5 x mean|ref| here (dec0.candi.W; tests/golden/make_golden.py prints it), i.e. it sits right at the
+    # per-cell atol of 1e-5.  The stack-level gradient check therefore uses rtol 1e-4 + 5e-5 x mean|ref|.
+    bad = []
+    def chk(got, ref, name):
+        n, w = O.violations(got, ref, atol_scale=5e-5)
+        if n:
+            bad.append(f"{name}: {n}/{ref.numel()} worst {w:.2e} x mean|ref|")
+    chk(Gs.grad.cpu(), t["dGs"], "dGs")
+    chk(Gc.grad.cpu(), t["dGc"], "dGc")
+    chk(X.grad.cpu(), t["dX_seq"], "dX_seq")
     for tag, mods in (("enc", stack.encoder), ("dec", stack.decoder)):
         for i, cell in enumerate(mods):
             for conv in ("gates", "candi"):
                 for pn in ("W", "b"):
-                    O.assert_close(getattr(getattr(cell, conv), pn).grad.cpu(), t[f"d_{tag}{i}_{conv}_{pn}"],
-                                   f"{tag}{i}.{conv}.{pn}")
+                    chk(getattr(getattr(cell, conv), pn).grad.cpu(), t[f"d_{tag}{i}_{conv}_{pn}"], f"{tag}{i}.{conv}.{pn}")
+    assert not bad, "; ".join(bad)
 
 
 @pytest.mark.parametrize("kind", ["dense", "csr"])
@@ -208,3 +216,23 @@ def test_error_paths():
         cell(Gs=z(6, 6).double(), Gc=z(3, 3), Xt=z(2, 6, 3, 1), Ht_1=z(2, 6, 3, 4))  # fp64 is not accepted
     out = cell(Gs=z(6, 6), Gc=z(3, 3), Xt=z(0, 6, 3, 1), Ht_1=z(0, 6, 3, 4))         # empty batch
     assert out.shape == (0, 6, 3, 4)
+
+
+@pytest.mark.parametrize("mnk", [(128, 32, 32), (300, 48, 100), (256, 16, 17), (1000, 256, 72), (128, 32, 128)])
+def test_tf32x3_tensor_core_gemm_block(mnk):
+    """The tcgen05 building block (3xTF32, TMEM accumulate) against fp64 on the same inputs."""
+    import ctypes
+    from stc_gnn_b200 import _lib
+    lib = _lib.load()
+    M, N, K = mnk
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    Bm = torch.randn(K, N, generator=g).to(DEV)
+    D = torch.empty(M, N, device=DEV)
+    _lib.check(lib.stc_tf32x3_gemm(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), M, N, K,
+                                   torch.cuda.current_stream().cuda_stream), "stc_tf32x3_gemm")
+    torch.cuda.synchronize()
+    ref = A.double().cpu() @ Bm.double().cpu()
+    err = (D.double().cpu() - ref).abs().max().item() / ref.abs().mean().item()
+    assert err < 2e-5, f"3xTF32 error {err:.3e} x mean|ref| is not fp32-class"
+    O.assert_close(D.cpu(), ref, "tf32x3 gemm")

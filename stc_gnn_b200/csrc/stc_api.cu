@@ -101,6 +101,9 @@ WsLayout make_layout(const StcDims& d) {
   w.Yx = take(km1 * Rx);
   w.Yh = take(km1 * Rh);
   w.Q = take((size_t)d.Kc * d.C * d.C);
+  const size_t kcm1 = d.Kc > 1 ? (size_t)(d.Kc - 1) : 0;
+  w.Pg = take(w.R * kcm1 * 2 * d.h);
+  w.Pc = take(w.R * kcm1 * d.h);
   w.saved_total = o;
   o = 0;
   w.dpre = take(w.R * 2 * d.h);
@@ -275,6 +278,7 @@ int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
     a.u = ws + w.u;
     a.r = ws + w.r;
     a.rH = ws + w.Yr;
+    a.Psave = ws + w.Pg;
     STC_TRY(launch_conv_fwd(a, st));
   }
   // spatial terms of r*H
@@ -295,6 +299,7 @@ int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
     a.u = ws + w.u;
     a.c = ws + w.c;
     a.Hnew = h_out;
+    a.Psave = ws + w.Pc;
     STC_TRY(launch_conv_fwd(a, st));
   }
   return STC_OK;
@@ -392,6 +397,7 @@ int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
     a.dYh = sc + w.dYr + Rh;
     a.dQ = want_dGc ? sc + w.dQ : nullptr;
     a.dW = dWc;
+    a.Psave = sv + w.Pc;
     STC_TRY(launch_conv_bwd_dx(a, st));
     STC_TRY(launch_conv_bwd_dw(a, st));
   }
@@ -418,6 +424,7 @@ int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
     a.dYh = sc + w.dYh;
     a.dQ = want_dGc ? sc + w.dQ : nullptr;
     a.dW = dWg;
+    a.Psave = sv + w.Pg;
     STC_TRY(launch_conv_bwd_dx(a, st));
     STC_TRY(launch_conv_bwd_dw(a, st));
   }

@@ -61,7 +61,7 @@ int check_arch();        // STC_OK when the current device is compute capability
 struct WsLayout {
   size_t R;  // B*N*C rows
   // `saved` buffer (written by forward, read by backward)
-  size_t u, r, c, Yr, Yx, Yh, Q, saved_total;
+  size_t u, r, c, Yr, Yx, Yh, Q, Pg, Pc, saved_total;
   // backward `scratch` buffer
   size_t dpre, dYx0, dYx, dYh, dYr, dQ, scratch_total;
 };
@@ -97,6 +97,7 @@ struct ConvArgs {
   float* rH;
   float* c;
   float* Hnew;
+  float* Psave;        // [R][(Kc-1)*Hout]: pre-mix partial outputs P_c, c >= 1 (tcgen05 path, for dGc)
   // backward inputs / outputs
   const float* dHn;
   const float* drH;    // gates phase: adjoint of r*H
@@ -112,6 +113,7 @@ struct ConvArgs {
 };
 int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, cudaStream_t st);
 int launch_conv_fwd(const ConvArgs& a, cudaStream_t st);
+bool conv_tc_eligible(const ConvArgs& a);  // shape-only test shared by forward and backward
 int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st);
 int launch_conv_bwd_dw(const ConvArgs& a, cudaStream_t st);
 

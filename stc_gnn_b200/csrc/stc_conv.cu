@@ -340,6 +340,11 @@ static size_t conv_dx_smem(const ConvArgs& a, const ConvTile& t, int DP) {
 }
 
 int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st) {
+  {
+    bool handled = false;
+    STC_TRY(try_launch_conv_bwd_dx_tc(a, st, &handled));
+    if (handled) return STC_OK;
+  }
   const int L = a.Din + a.h;
   const int CGL = ((L + 3) & ~3) / 4;
   const int HoutP = (a.Hout + 3) & ~3;
@@ -490,6 +495,11 @@ conv_bwd_dw_kernel(const ConvArgs a, const ConvTile t, const int tiles_per_cta) 
 }
 
 int launch_conv_bwd_dw(const ConvArgs& a, cudaStream_t st) {
+  {
+    bool handled = false;
+    STC_TRY(try_launch_conv_bwd_dw_tc(a, st, &handled));
+    if (handled) return STC_OK;
+  }
   const int L = a.Din + a.h;
   const int LP4 = (L + 3) & ~3;
   int slabs = ceil_div(a.Hout, DW_SLAB);

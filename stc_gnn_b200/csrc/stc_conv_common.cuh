@@ -130,5 +130,7 @@ static inline int set_smem(K kernel, size_t smem) {
 
 // tcgen05 path (stc_conv_tc.cu): returns STC_OK and sets *handled when it took the launch
 int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled);
+int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled);
+int try_launch_conv_bwd_dw_tc(const ConvArgs& a, cudaStream_t st, bool* handled);
 
 }  // namespace stc

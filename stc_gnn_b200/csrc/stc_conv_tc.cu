@@ -254,6 +254,11 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
         __syncthreads();                                            // previous users of Pm are done
         *reinterpret_cast<float4*>(Pm + erow * p.PS + c0) = make_float4(t[0], t[1], t[2], t[3]);
         *reinterpret_cast<float4*>(Pm + erow * p.PS + c0 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+        if (a.Psave && valid) {  // backward forms dGc from these partials (no recomputation of the GEMM)
+          float4* ps = reinterpret_cast<float4*>(a.Psave + gr * (long long)((a.Kc - 1) * Hout) + (c - 1) * Hout + c0);
+          ps[0] = make_float4(t[0], t[1], t[2], t[3]);
+          ps[1] = make_float4(t[4], t[5], t[6], t[7]);
+        }
         __syncthreads();
         const float* Qc = Qs + (size_t)(c - 1) * C * C;
         const float* pp = Pm + (enode * C) * p.PS + c0;
@@ -328,14 +333,37 @@ static bool tc_disabled() {
 
 static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Shape-only eligibility of the tcgen05 path; forward and backward must agree (backward reads what forward saved).
+bool conv_tc_eligible(const ConvArgs& a) {
+  if (tc_disabled()) return false;
+  if (a.h % 8 != 0 || a.Hout % 16 != 0 || a.C > 128) return false;
+  const int Dp = (a.Din + 7) & ~7, KBL = a.h + Dp, KB = (KBL + ATOM_K - 1) / ATOM_K;
+  // forward: N = Kc*Hout, accumulators = Ks*KB mains + 1
+  const int Nf = (a.Kc * a.Hout + 15) & ~15;
+  if (Nf > 256 || (a.Ks * KB + 1) * Nf > 512) return false;
+  if ((size_t)128 * (a.Hout + 4) * sizeof(float) > 2 * 128 * ATOM_ROW_BYTES) return false;
+  const size_t fwd_smem = 2 * 128 * ATOM_ROW_BYTES + 2 * (size_t)a.Ks * KB * Nf * ATOM_ROW_BYTES +
+                          (size_t)a.Ks * 128 * (a.h + a.Din) * sizeof(float) + (size_t)a.Kc * a.C * a.C * sizeof(float) + 64;
+  if (fwd_smem > 200 * 1024) return false;
+  // backward dx: N = Ks*KBL, K = Kc*Hout
+  const int Nb = (a.Ks * KBL + 15) & ~15, KA = (a.Kc * a.Hout + ATOM_K - 1) / ATOM_K;
+  if (Nb > 256 || (KA + 1) * Nb > 512) return false;
+  const size_t dx_smem = 2 * 128 * ATOM_ROW_BYTES + 2 * (size_t)KA * Nb * ATOM_ROW_BYTES +
+                         (size_t)128 * (a.Hout + 4 + a.h + (a.Kc - 1) * a.Hout) * sizeof(float) +
+                         (size_t)2 * a.Kc * a.C * a.C * sizeof(float) + 256;
+  if (dx_smem > 200 * 1024) return false;
+  return true;
+}
+
 int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
   *handled = false;
-  if (tc_disabled()) return STC_OK;
+  if (!conv_tc_eligible(a)) return STC_OK;
   const int L = a.Din + a.h, P = a.Ks * a.Kc;
-  if (a.h % 8 != 0 || a.Hout % 16 != 0 || a.C > 128) return STC_OK;
   if (!aligned16p(a.u) || !aligned16p(a.Hprev) || !aligned16p(a.r) || !aligned16p(a.rH) || !aligned16p(a.c) ||
-      !aligned16p(a.Hnew) || !aligned16p(a.h0) || !aligned16p(a.yh))
-    return STC_OK;
+      !aligned16p(a.Hnew) || !aligned16p(a.h0) || !aligned16p(a.yh) || !aligned16p(a.Psave)) {
+    set_error("tcgen05 path needs 16-byte aligned state / workspace tensors");
+    return STC_ERR_BAD_ARG;
+  }
   TcFwdPlan p;
   p.npt = 128 / a.C;
   p.Dp = (a.Din + 7) & ~7;
@@ -491,6 +519,103 @@ tf32x3_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, fl
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// MN-major variant of the self-test (STC_TC_TEST_MODE bit 1): the same product with both operand tiles stored
+// [K rows][M or N contiguous] -- the layout the dW kernel uses to contract over tile rows without transposing.
+__global__ void __launch_bounds__(CV_THREADS, 1)
+tf32x3_gemm_mn_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ D, int M, int N,
+                      int K, int Npad, int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncolB = (Npad + 31) / 32;                  // 32-wide column blocks of B
+  const uint32_t colblk = 32 * ATOM_ROW_BYTES;         // [32 K-rows][128 B] = 4 KB
+  uint8_t* A_hi = smem;                                // 4 column blocks (M = 128)
+  uint8_t* A_lo = A_hi + 4 * colblk;
+  uint8_t* B_hi = A_lo + 4 * colblk;
+  uint8_t* B_lo = B_hi + ncolB * colblk;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(B_lo + ncolB * colblk);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc_tf32_mn(128, Npad);
+  const int m0 = blockIdx.x * 128;
+  uint32_t phase = 0;
+  const int nchunksK = (K + 31) / 32;
+  bool acc_main = false, acc_small = false;
+  for (int j = 0; j < nchunksK; ++j) {
+    if (j > 0) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    }
+    // A tile: element (m, k) -> column block m/32, row k, 16-byte chunk (m%32)/4
+    for (int it = tid; it < 32 * 32; it += CV_THREADS) {    // 32 k-rows x 32 chunks (128 m / 4)
+      const int k = it >> 5, ch = it & 31;
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = ch * 4 + i, kk = j * 32 + k;
+        v[i] = (m0 + m < M && kk < K) ? A[(size_t)(m0 + m) * K + kk] : 0.f;
+      }
+      const uint32_t off = (uint32_t)(ch >> 3) * colblk + atom_chunk_offset(k, ch & 7);
+      store_split4(A_hi, A_lo, off, make_float4(v[0], v[1], v[2], v[3]));
+    }
+    for (int it = tid; it < 32 * ncolB * 8; it += CV_THREADS) {
+      const int k = it / (ncolB * 8), ch = it - k * (ncolB * 8);
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = ch * 4 + i, kk = j * 32 + k;
+        v[i] = (n < N && kk < K) ? Bm[(size_t)kk * N + n] : 0.f;
+      }
+      const uint32_t off = (uint32_t)(ch >> 3) * colblk + atom_chunk_offset(k, ch & 7);
+      store_split4(B_hi, B_lo, off, make_float4(v[0], v[1], v[2], v[3]));
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const int kleft = K - j * 32;
+      const int ksteps = kleft >= 32 ? 4 : (kleft + 7) / 8;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t o = ks * GROUP_BYTES;  // next 8-row group along K
+        const uint64_t ah = make_smem_desc_sw128_mn(smem_u32(A_hi) + o, colblk, GROUP_BYTES);
+        const uint64_t al = make_smem_desc_sw128_mn(smem_u32(A_lo) + o, colblk, GROUP_BYTES);
+        const uint64_t bh = make_smem_desc_sw128_mn(smem_u32(B_hi) + o, colblk, GROUP_BYTES);
+        const uint64_t bl = make_smem_desc_sw128_mn(smem_u32(B_lo) + o, colblk, GROUP_BYTES);
+        mma_tf32(tmem_base + (uint32_t)Npad, al, bh, idesc, acc_small ? 1u : 0u);
+        mma_tf32(tmem_base + (uint32_t)Npad, ah, bl, idesc, 1u);
+        mma_tf32(tmem_base, ah, bh, idesc, acc_main ? 1u : 0u);
+        acc_main = acc_small = true;
+      }
+      mma_commit(bar);
+    }
+  }
+  mbar_wait(bar, phase);
+  fence_after_sync();
+  {
+    const int lane_base = (warp & 3) * 32, half = warp >> 2;
+    const int row = m0 + lane_base + lane;
+    for (int ch = half; ch < Npad / 8; ch += 2) {
+      float v[8], t[8];
+      tmem_ld8(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(Npad + ch * 8), v);
+      tmem_ld8(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(ch * 8), t);
+      if (row < M)
+        for (int i = 0; i < 8; ++i)
+          if (ch * 8 + i < N) D[(size_t)row * N + ch * 8 + i] = v[i] + t[i];
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
 int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0 || N > 256) {
     set_error("tf32x3 gemm self-test: need M,K > 0 and 0 < N <= 256");
@@ -502,6 +627,16 @@ int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, 
   if (const char* e = getenv("STC_TC_TEST_NMAIN")) nmain = atoi(e);
   if (const char* e = getenv("STC_TC_TEST_SMALL")) small = atoi(e);
   const int Npad = (N + 15) & ~15;
+  if (mode & 2) {
+    int cols = 32;
+    while (cols < 2 * Npad) cols *= 2;
+    const size_t smem_mn = (size_t)(8 + 2 * ((Npad + 31) / 32)) * 32 * ATOM_ROW_BYTES + 64;
+    STC_TRY(set_smem(tf32x3_gemm_mn_kernel, smem_mn));
+    ScopedKernelTimer _t(KK_TC_GEMM_TEST, st, 4.0 * ((double)M * K + (double)K * N + (double)M * N));
+    tf32x3_gemm_mn_kernel<<<ceil_div(M, 128), CV_THREADS, smem_mn, st>>>(A, Bm, D, M, N, K, Npad, cols);
+    STC_LAUNCH_OK("tf32x3_gemm_mn_kernel");
+    return STC_OK;
+  }
   if (nmain < 1) nmain = 1;
   if (nmain > 15) nmain = 15;
   while ((nmain + (small ? 1 : 0)) * Npad > 512 && nmain > 1) --nmain;

@@ -1,0 +1,364 @@
+// tcgen05 / TMEM backward kernels of the gate / candidate convolution (the adjoint of stc_conv_tc.cu).
+//
+// tc_conv_bwd_dx_kernel, per 128-row tile (whole nodes x all categories):
+//   1. CUDA cores: GRU / activation adjoint -> pre-activation gradient Ds [rows][Hout] (also written to HBM for
+//      the dW kernel), bias-gradient column sums, the direct dH terms;
+//   2. the categorical mix is pulled onto the K side:  dY_k = [Ds | Dm_1 | ...] x [W_{k,0}^T ; W_{k,1}^T ; ...]
+//      with Dm_c[(node,c')] = sum_d T_c(Gc)[c',d] Ds[(node,d)]  (adjoint of 'bmcl,cd->bmdl', STC_GNN.py:38),
+//      so one 3xTF32 tensor-core GEMM [rows x Kc*Hout] x [Kc*Hout x Ks*KBL] yields every spatial-term adjoint;
+//   3. epilogue: TMEM -> registers -> dY_k tiles in HBM (x-part accumulated across the two convolutions);
+//   4. dT_c(Gc) from the partial outputs P_c the forward kernel saved:  dQ_c[c',d] = sum P_c[(n,c')][o] Ds[(n,d)][o].
+#include "stc_conv_common.cuh"
+#include "stc_tc.cuh"
+
+namespace stc {
+
+using namespace tc;
+
+struct TcDxPlan {
+  int npt, Dp, KBL;
+  int N1;         // Ks * KBL  (GEMM N: every spatial term's [h | x] block)
+  int Npad;       // N1 rounded up to 16
+  int Kdd;        // Kc * Hout (GEMM K)
+  int KA;         // 32-wide atoms along K
+  int tmem_cols, ntiles;
+  int DP;         // row stride of the plain Ds tile (floats)
+  int PW;         // (Kc-1) * Hout: width of the saved partial-output tile
+  uint32_t off_a, off_b, off_ds, off_dh, off_ps, off_q, off_acc, off_bar, smem_bytes;
+};
+
+__global__ void __launch_bounds__(CV_THREADS, 2)
+tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, L = a.Din + a.h, h = a.h, Din = a.Din, Hout = a.Hout, DP = p.DP;
+  const bool want_dQ = a.dQ != nullptr && a.Kc > 1;
+  const uint32_t atomA = 128 * ATOM_ROW_BYTES;
+  const uint32_t atomB = (uint32_t)p.Npad * ATOM_ROW_BYTES;
+  uint8_t* A_hi = smem + p.off_a;
+  uint8_t* A_lo = A_hi + atomA;
+  uint8_t* B_hi = smem + p.off_b;                               // [KA][atomB]
+  uint8_t* B_lo = B_hi + (size_t)p.KA * atomB;
+  float* Dsm = reinterpret_cast<float*>(smem + p.off_ds);       // [128][DP]  plain Ds
+  float* Dh = reinterpret_cast<float*>(smem + p.off_dh);        // [128][h]   direct dH terms (gates)
+  float* Psm = reinterpret_cast<float*>(smem + p.off_ps);       // [128][PW]  saved P_c tile (bulk copied)
+  float* Qs = reinterpret_cast<float*>(smem + p.off_q);         // [(Kc-1)][C][C]
+  float* dQacc = reinterpret_cast<float*>(smem + p.off_acc);    // [(Kc-1)][C][C] per-CTA accumulators
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* load_bar = mma_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 2);
+
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    mbar_init(load_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  for (int i = tid; i < (a.Kc - 1) * C * C; i += CV_THREADS) {
+    Qs[i] = a.Q[C * C + i];
+    dQacc[i] = 0.f;
+  }
+  // resident B atoms:  Bt[(k,kb)][(c,o)] = W[((k*Kc + c)*L + l(kb))*Hout + o]
+  for (int ja = 0; ja < p.KA; ++ja) {
+    uint8_t* bh = B_hi + (size_t)ja * atomB;
+    uint8_t* bl = B_lo + (size_t)ja * atomB;
+    for (int it = tid; it < p.Npad * 8; it += CV_THREADS) {
+      const int n = it >> 3, qq = it & 7;
+      const int k = n / p.KBL, kb = n - k * p.KBL;
+      const int l = kb < h ? Din + kb : (kb - h < Din ? kb - h : -1);
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = ja * ATOM_K + qq * 4 + i;
+        const int c = kk / Hout, o = kk - c * Hout;
+        v[i] = (n < p.N1 && l >= 0 && kk < p.Kdd) ? a.W[((size_t)(k * a.Kc + c) * L + l) * Hout + o] : 0.f;
+      }
+      store_split4(bh, bl, atom_chunk_offset(n, qq), make_float4(v[0], v[1], v[2], v[3]));
+    }
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, p.Npad);
+  const uint32_t d_small = tmem_base + (uint32_t)(p.KA * p.Npad);
+  const long long total_nodes = (long long)a.B * a.N;
+  const long long R = total_nodes * C;
+
+  const int q = tid & 7, r0 = tid >> 3;
+  uint32_t aoff[4];
+  int rnode[4], rcat[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    aoff[i] = atom_chunk_offset(r0 + 32 * i, q);
+    rnode[i] = (r0 + 32 * i) / C;
+    rcat[i] = (r0 + 32 * i) - rnode[i] * C;
+  }
+  const int lane_base = (warp & 3) * 32, half = warp >> 2;
+  const int erow = lane_base + lane;
+  const uint32_t tl = tmem_base + ((uint32_t)lane_base << 16);
+  float db_acc = 0.f;  // thread j < Hout owns bias-gradient column j
+  uint32_t mma_phase = 0, load_phase = 0;
+  bool mma_pending = false;
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long g0 = (long long)tile * p.npt;
+    const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
+    const int rows_valid = nodes_valid * C;
+    const long long row0 = g0 * C;
+    if (want_dQ && tid == 0) {  // stage the saved partial outputs of this tile while the prologue runs
+      const uint32_t bytes = (uint32_t)(rows_valid * p.PW * 4);
+      mbar_arrive_expect_tx(load_bar, bytes);
+      bulk_g2s(Psm, a.Psave + row0 * p.PW, bytes, load_bar);
+    }
+    // ---- 1. elementwise adjoint: one float4 of hidden channels per item ----
+    const int cpr = h >> 2;
+    for (int it = tid; it < 128 * cpr; it += CV_THREADS) {
+      const int row = it / cpr, j = (it - row * cpr) << 2;
+      float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
+      if (row < rows_valid) {
+        const long long o = (row0 + row) * h + j;
+        const float4 dhn = *reinterpret_cast<const float4*>(a.dHn + o);
+        const float4 uu = *reinterpret_cast<const float4*>(a.u + o);
+        const float4 cc = *reinterpret_cast<const float4*>(a.c + o);
+        if (a.phase == 1) {
+          g0v = make_float4(dhn.x * uu.x * (1.f - cc.x * cc.x), dhn.y * uu.y * (1.f - cc.y * cc.y),
+                            dhn.z * uu.z * (1.f - cc.z * cc.z), dhn.w * uu.w * (1.f - cc.w * cc.w));
+          if (a.act == STC_ACT_RELU) {
+            if (!(cc.x > 0.f)) g0v.x = 0.f;
+            if (!(cc.y > 0.f)) g0v.y = 0.f;
+            if (!(cc.z > 0.f)) g0v.z = 0.f;
+            if (!(cc.w > 0.f)) g0v.w = 0.f;
+          }
+          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * Hout + j) = g0v;
+        } else {
+          const float4 hp = *reinterpret_cast<const float4*>(a.Hprev + o);
+          const float4 rr = *reinterpret_cast<const float4*>(a.r + o);
+          const float4 drh = *reinterpret_cast<const float4*>(a.drH + o);
+          g0v = make_float4(dhn.x * (cc.x - hp.x) * uu.x * (1.f - uu.x), dhn.y * (cc.y - hp.y) * uu.y * (1.f - uu.y),
+                            dhn.z * (cc.z - hp.z) * uu.z * (1.f - uu.z), dhn.w * (cc.w - hp.w) * uu.w * (1.f - uu.w));
+          g1v = make_float4(drh.x * hp.x * rr.x * (1.f - rr.x), drh.y * hp.y * rr.y * (1.f - rr.y),
+                            drh.z * hp.z * rr.z * (1.f - rr.z), drh.w * hp.w * rr.w * (1.f - rr.w));
+          if (a.act == STC_ACT_RELU) {
+            if (!(uu.x > 0.5f)) g0v.x = 0.f;
+            if (!(uu.y > 0.5f)) g0v.y = 0.f;
+            if (!(uu.z > 0.5f)) g0v.z = 0.f;
+            if (!(uu.w > 0.5f)) g0v.w = 0.f;
+            if (!(rr.x > 0.5f)) g1v.x = 0.f;
+            if (!(rr.y > 0.5f)) g1v.y = 0.f;
+            if (!(rr.z > 0.5f)) g1v.z = 0.f;
+            if (!(rr.w > 0.5f)) g1v.w = 0.f;
+          }
+          dir = make_float4(dhn.x * (1.f - uu.x) + drh.x * rr.x, dhn.y * (1.f - uu.y) + drh.y * rr.y,
+                            dhn.z * (1.f - uu.z) + drh.z * rr.z, dhn.w * (1.f - uu.w) + drh.w * rr.w);
+          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * Hout + j) = g0v;
+          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * Hout + h + j) = g1v;
+        }
+      }
+      *reinterpret_cast<float4*>(Dsm + row * DP + j) = g0v;
+      if (a.phase == 0) {
+        *reinterpret_cast<float4*>(Dsm + row * DP + h + j) = g1v;
+        *reinterpret_cast<float4*>(Dh + row * h + j) = dir;
+      }
+    }
+    __syncthreads();
+    if (a.dbias && tid < Hout) {
+      float s = 0.f;
+      for (int row = 0; row < rows_valid; ++row) s += Dsm[row * DP + tid];
+      db_acc += s;
+    }
+    // ---- 2. DD atoms + MMAs ----
+    bool acc_small = false;
+    for (int ja = 0; ja < p.KA; ++ja) {
+      if (mma_pending) {
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1u;
+        mma_pending = false;
+      }
+      const int kk = ja * ATOM_K + q * 4;
+      const int c = kk / Hout, o0 = kk - c * Hout;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kk < p.Kdd) {
+          if (c == 0) {
+            v = *reinterpret_cast<const float4*>(Dsm + (r0 + 32 * i) * DP + o0);
+          } else {  // Dm_c[(node,c')][o] = sum_d Q_c[c'][d] Ds[(node,d)][o]
+            const float* Qc = Qs + (size_t)(c - 1) * C * C + rcat[i] * C;
+            const float* sp = Dsm + rnode[i] * C * DP + o0;
+            for (int d = 0; d < C; ++d) {
+              const float w = Qc[d];
+              const float4 x = *reinterpret_cast<const float4*>(sp + d * DP);
+              v.x = fmaf(w, x.x, v.x); v.y = fmaf(w, x.y, v.y); v.z = fmaf(w, x.z, v.z); v.w = fmaf(w, x.w, v.w);
+            }
+          }
+        }
+        store_split4(A_hi, A_lo, aoff[i], v);
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        const int kleft = p.Kdd - ja * ATOM_K;
+        const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
+        bool acc_main = false;
+        mma_atom_3x_split(tmem_base + (uint32_t)(ja * p.Npad), d_small, smem_u32(A_hi), smem_u32(A_lo),
+                          smem_u32(B_hi + (size_t)ja * atomB), smem_u32(B_lo + (size_t)ja * atomB), ksteps, idesc,
+                          acc_main, acc_small);
+        mma_commit(mma_bar);
+      }
+      acc_small = true;
+      mma_pending = true;
+    }
+    // ---- 4 (overlaps the MMAs). dQ_c[c'][d] += sum_{node,o} P_c[(node,c')][o] * Ds[(node,d)][o] ----
+    if (want_dQ) {
+      mbar_wait(load_bar, load_phase);
+      load_phase ^= 1u;
+      const int npairs = (a.Kc - 1) * C * C;
+      const int groups = CV_THREADS / npairs;      // node groups working on the same pair
+      if (groups >= 1) {
+        const int pr = tid % npairs, grp = tid / npairs;
+        if (grp < groups) {
+          const int c = pr / (C * C), rem = pr - c * C * C, cp = rem / C, d = rem - cp * C;
+          float s = 0.f;
+          for (int node = grp; node < nodes_valid; node += groups) {
+            const float* pp = Psm + (node * C + cp) * p.PW + c * Hout;
+            const float* dd = Dsm + (node * C + d) * DP;
+            for (int o = 0; o < Hout; o += 4) {
+              const float4 x = *reinterpret_cast<const float4*>(pp + o);
+              const float4 y = *reinterpret_cast<const float4*>(dd + o);
+              s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+            }
+          }
+          atomicAdd(&dQacc[pr], s);
+        }
+      } else {  // more pairs than threads (large C): each thread walks several pairs
+        for (int pr = tid; pr < npairs; pr += CV_THREADS) {
+          const int c = pr / (C * C), rem = pr - c * C * C, cp = rem / C, d = rem - cp * C;
+          float s = 0.f;
+          for (int node = 0; node < nodes_valid; ++node) {
+            const float* pp = Psm + (node * C + cp) * p.PW + c * Hout;
+            const float* dd = Dsm + (node * C + d) * DP;
+            for (int o = 0; o < Hout; ++o) s = fmaf(pp[o], dd[o], s);
+          }
+          dQacc[pr] += s;
+        }
+      }
+    }
+    // ---- 3. epilogue: dY_k tiles ----
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1u;
+    mma_pending = false;
+    fence_after_sync();
+    {
+      const bool valid = erow < rows_valid;
+      const long long gr = row0 + erow;
+      for (int n0 = half * 8; n0 < p.Npad; n0 += 16) {
+        float v[8], t[8];
+        tmem_ld8(tl + (uint32_t)(p.KA * p.Npad + n0), v);
+        for (int m = 0; m < p.KA; ++m) {
+          tmem_ld8(tl + (uint32_t)(m * p.Npad + n0), t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += t[i];
+        }
+        if (!valid || n0 >= p.N1) continue;
+        const int k = n0 / p.KBL, kb = n0 - k * p.KBL;   // KBL % 8 == 0: a chunk never straddles terms or parts
+        if (kb < h) {
+          float* dst = (k == 0 ? a.dYh0 : a.dYh + (size_t)(k - 1) * R * h) + gr * h + kb;
+          if (k == 0 && a.phase == 0) {
+            const float* dp = Dh + erow * h + kb;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += dp[i];
+          }
+          reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+          reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          const int xi = kb - h;
+          float* dbase = (k == 0 ? a.dYx0 : a.dYx + (size_t)(k - 1) * R * Din);
+          if (dbase == nullptr) continue;
+          float* dst = dbase + gr * Din + xi;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (xi + i < Din) dst[i] = a.accum_x ? dst[i] + v[i] : v[i];
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();  // Dsm / Dh / Psm are rewritten by the next tile's prologue
+  }
+  if (a.dbias && tid < Hout) atomicAdd(&a.dbias[tid], db_acc);
+  __syncthreads();
+  if (want_dQ)
+    for (int i = tid; i < (a.Kc - 1) * C * C; i += CV_THREADS) atomicAdd(&a.dQ[C * C + i], dQacc[i]);
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+static bool aligned16b(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (!conv_tc_eligible(a)) return STC_OK;
+  if (!aligned16b(a.dHn) || !aligned16b(a.u) || !aligned16b(a.c) || !aligned16b(a.Hprev) || !aligned16b(a.dpre) ||
+      !aligned16b(a.dYh0) || !aligned16b(a.dYh) || !aligned16b(a.Psave) || (a.phase == 0 && (!aligned16b(a.r) || !aligned16b(a.drH)))) {
+    set_error("tcgen05 backward needs 16-byte aligned gradient / workspace tensors");
+    return STC_ERR_BAD_ARG;
+  }
+  const int L = a.Din + a.h;
+  TcDxPlan p;
+  p.npt = 128 / a.C;
+  p.Dp = (a.Din + 7) & ~7;
+  p.KBL = a.h + p.Dp;
+  p.N1 = a.Ks * p.KBL;
+  p.Npad = (p.N1 + 15) & ~15;
+  p.Kdd = a.Kc * a.Hout;
+  p.KA = (p.Kdd + ATOM_K - 1) / ATOM_K;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < (p.KA + 1) * p.Npad) p.tmem_cols *= 2;
+  p.DP = a.Hout + 4;
+  p.PW = (a.Kc - 1) * a.Hout;
+  const long long total_nodes = (long long)a.B * a.N;
+  p.ntiles = ceil_div(total_nodes, p.npt);
+  const size_t atomB = (size_t)p.Npad * ATOM_ROW_BYTES;
+  size_t o = 0;
+  p.off_a = (uint32_t)o; o += 2 * 128 * ATOM_ROW_BYTES;
+  p.off_b = (uint32_t)o; o += 2 * (size_t)p.KA * atomB;
+  p.off_ds = (uint32_t)o; o += (size_t)128 * p.DP * sizeof(float);
+  p.off_dh = (uint32_t)o; o += (size_t)128 * a.h * sizeof(float);
+  p.off_ps = (uint32_t)o; o += round_up((size_t)128 * p.PW * sizeof(float), 16);
+  p.off_q = (uint32_t)o; o += round_up((size_t)(a.Kc > 1 ? a.Kc - 1 : 0) * a.C * a.C * sizeof(float), 16);
+  p.off_acc = (uint32_t)o; o += round_up((size_t)(a.Kc > 1 ? a.Kc - 1 : 0) * a.C * a.C * sizeof(float), 16);
+  p.off_bar = (uint32_t)o; o += 32;
+  p.smem_bytes = (uint32_t)o;
+  if (p.smem_bytes > 200 * 1024) {
+    set_error("tcgen05 backward tile does not fit (%u B) although the forward ran on the tensor-core path", p.smem_bytes);
+    return STC_ERR_UNSUPPORTED;
+  }
+  STC_TRY(set_smem(tc_conv_bwd_dx_kernel, p.smem_bytes));
+  int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 2) ctas_per_sm = 2;
+  if (ctas_per_sm * p.tmem_cols > 512) ctas_per_sm = 512 / p.tmem_cols;
+  int grid = device_sm_count() * ctas_per_sm;
+  if (grid > p.ntiles) grid = p.ntiles;
+  // compulsory traffic per row: candidate reads dH',u,c (3h), gates reads dH',u,c,H,r,d(rH) (6h); both write dpre
+  // (Hout) and the Ks adjoint terms (Ks*L; the gates pass re-reads the x-part it accumulates into) and, for dGc,
+  // read the saved partial outputs ((Kc-1)*Hout).
+  const double R = (double)total_nodes * a.C;
+  ScopedKernelTimer _t(KK_TC_CONV_BWD_DX, st,
+                       4.0 * R * ((a.phase == 0 ? 6 * a.h + a.Ks * a.Din : 3 * a.h) + a.Hout + a.Ks * L +
+                                  ((a.dQ && a.Kc > 1) ? p.PW : 0)) + 4.0 * a.Ks * a.Kc * L * a.Hout);
+  tc_conv_bwd_dx_kernel<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
+  STC_LAUNCH_OK("tc_conv_bwd_dx_kernel");
+  *handled = true;
+  return STC_OK;
+}
+
+int try_launch_conv_bwd_dw_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
+  *handled = false;   // tensor-core dW lands next; the FFMA kernel is still the one that runs
+  (void)a; (void)st;
+  return STC_OK;
+}
+
+}  // namespace stc

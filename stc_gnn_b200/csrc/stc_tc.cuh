@@ -67,6 +67,23 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (the K index is the slow one: tile rows = K, 128-byte rows hold 32 consecutive M/N elements).
+// Physically the same swizzled [rows][128 B] blocks as the K-major atoms; LBO = pitch between 32-element column
+// blocks along M/N, SBO = pitch between 8-row groups along K.  One MMA (K = 8) consumes one 8-row group.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {  // both operands MN-major
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
 // instruction descriptor: kind::tf32, fp32 accumulate, A and B K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

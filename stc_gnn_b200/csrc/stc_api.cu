@@ -106,7 +106,7 @@ WsLayout make_layout(const StcDims& d) {
   w.Pc = take(w.R * kcm1 * d.h);
   w.saved_total = o;
   o = 0;
-  w.dpre = take(w.R * 2 * d.h);
+  w.dpre = take(w.R * 2 * d.h * d.Kc);   // tcgen05 path keeps the Kc unmixed copies side by side
   w.dYx0 = take(Rx);
   w.dYx = take(km1 * Rx);
   w.dYh = take(km1 * Rh);
@@ -149,6 +149,7 @@ static ConvArgs base_args(const StcDims& d, const float* xt, int64_t xt_bs, cons
   a.yx = ws + w.Yx;
   a.W = W;
   a.Q = Q;
+  a.dpre_ld = conv_tc_eligible(a) ? a.Kc * a.Hout : a.Hout;
   return a;
 }
 

@@ -101,7 +101,9 @@ struct ConvArgs {
   // backward inputs / outputs
   const float* dHn;
   const float* drH;    // gates phase: adjoint of r*H
-  float* dpre;         // [R][Hout] scratch written by dx, read by dw
+  float* dpre;         // [R][dpre_ld] scratch written by dx, read by dw: columns [0,Hout) = pre-activation gradient;
+                       // on the tcgen05 path dpre_ld = Kc*Hout and block c >= 1 holds its T_c(Gc)-unmixed copy
+  int dpre_ld;
   float* dbias;        // atomically accumulated, or null
   float* dYx0;         // k = 0 x-part adjoint destination
   float* dYx;          // k >= 1
@@ -114,6 +116,7 @@ struct ConvArgs {
 int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, cudaStream_t st);
 int launch_conv_fwd(const ConvArgs& a, cudaStream_t st);
 bool conv_tc_eligible(const ConvArgs& a);  // shape-only test shared by forward and backward
+bool conv_tc_dw_shape_ok(const ConvArgs& a);  // additionally: the tensor-core dW kernel tiles this shape
 int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st);
 int launch_conv_bwd_dw(const ConvArgs& a, cudaStream_t st);
 

@@ -220,7 +220,7 @@ conv_bwd_dx_kernel(const ConvArgs a, const ConvTile t, const int DP) {
         float g = dhn * uu * (1.f - cc * cc);
         if (a.act == STC_ACT_RELU && !(cc > 0.f)) g = 0.f;
         Ds[row * DP + j] = g;
-        a.dpre[(row0 + row) * Hout + j] = g;
+        a.dpre[(row0 + row) * a.dpre_ld + j] = g;
       } else {
         const float hp = a.Hprev[o], rr = a.r[o], drh = a.drH[o];
         float gu = dhn * (cc - hp) * uu * (1.f - uu);
@@ -231,8 +231,8 @@ conv_bwd_dx_kernel(const ConvArgs a, const ConvTile t, const int DP) {
         }
         Ds[row * DP + j] = gu;
         Ds[row * DP + h + j] = gr;
-        a.dpre[(row0 + row) * Hout + j] = gu;
-        a.dpre[(row0 + row) * Hout + h + j] = gr;
+        a.dpre[(row0 + row) * a.dpre_ld + j] = gu;
+        a.dpre[(row0 + row) * a.dpre_ld + h + j] = gr;
         a.dYh0[o] = dhn * (1.f - uu) + drh * rr;   // direct terms of dH; the conv adjoint is added below
       }
     } else {
@@ -443,7 +443,7 @@ conv_bwd_dw_kernel(const ConvArgs a, const ConvTile t, const int tiles_per_cta) 
     load_feat_tile(fs, k, g0, nodes_valid, rows_valid, Fin, LP4);
     for (int idx = threadIdx.x; idx < rows_valid * SP; idx += blockDim.x) {
       int row = idx / SP, j = idx - row * SP;
-      Dsm[row * SP + j] = (j < ncol) ? a.dpre[(row0 + row) * Hout + col0 + j] : 0.f;
+      Dsm[row * SP + j] = (j < ncol) ? a.dpre[(row0 + row) * a.dpre_ld + col0 + j] : 0.f;
     }
     __syncthreads();
     const float* F = Fin;

@@ -521,14 +521,42 @@ tf32x3_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, fl
 
 // MN-major variant of the self-test (STC_TC_TEST_MODE bit 1): the same product with both operand tiles stored
 // [K rows][M or N contiguous] -- the layout the dW kernel uses to contract over tile rows without transposing.
+//   variant 0: SWIZZLE_128B_BASE32B, LBO = column-block pitch, SBO = 4-row group pitch (production layout)
+//   variant 1: the same with LBO / SBO exchanged (diagnostic)
+//   variant 2: no swizzle ("interleave"): 8 x 16-byte core matrices, SBO = pitch between 4-element M/N blocks,
+//              LBO = pitch between 8-row K groups (diagnostic fallback)
+struct MnLayout {
+  int variant;
+  uint32_t colblk;   // bytes of one 32-wide column block (variants 0/1)
+  uint32_t kgroup;   // bytes between 8-row K groups (variant 2)
+  __device__ __forceinline__ uint32_t off(int k, int ch) const {  // ch = 16-byte chunk index along M/N
+    if (variant == 2) return (uint32_t)(k >> 3) * kgroup + (uint32_t)ch * 128u + (uint32_t)(k & 7) * 16u;
+    return (uint32_t)(ch >> 3) * colblk + mn32_chunk_offset(k, ch & 7);
+  }
+  __device__ __forceinline__ uint64_t desc(uint32_t base, int ks) const {  // K-step ks (8 rows)
+    if (variant == 2) {
+      uint64_t d = 0;
+      d |= (uint64_t)(((base + ks * kgroup) >> 4) & 0x3FFF);
+      d |= (uint64_t)((kgroup >> 4) & 0x3FFF) << 16;   // LBO
+      d |= (uint64_t)((128u >> 4) & 0x3FFF) << 32;     // SBO
+      d |= (uint64_t)1 << 46;
+      return d;
+    }
+    const uint32_t a = base + ks * 2 * MN32_GROUP_BYTES;
+    return variant == 0 ? make_smem_desc_mn32(a, colblk, MN32_GROUP_BYTES) : make_smem_desc_mn32(a, MN32_GROUP_BYTES, colblk);
+  }
+};
+
 __global__ void __launch_bounds__(CV_THREADS, 1)
 tf32x3_gemm_mn_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ D, int M, int N,
-                      int K, int Npad, int tmem_cols) {
+                      int K, int Npad, int tmem_cols, int variant) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ncolB = (Npad + 31) / 32;                  // 32-wide column blocks of B
   const uint32_t colblk = 32 * ATOM_ROW_BYTES;         // [32 K-rows][128 B] = 4 KB
+  const MnLayout la{variant, colblk, 32u * 128u};      // A: 128 M = 32 chunks per K row
+  const MnLayout lb{variant, colblk, (uint32_t)(ncolB * 8) * 128u};
   uint8_t* A_hi = smem;                                // 4 column blocks (M = 128)
   uint8_t* A_lo = A_hi + 4 * colblk;
   uint8_t* B_hi = A_lo + 4 * colblk;
@@ -554,7 +582,6 @@ tf32x3_gemm_mn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
       mbar_wait(bar, phase);
       phase ^= 1u;
     }
-    // A tile: element (m, k) -> column block m/32, row k, 16-byte chunk (m%32)/4
     for (int it = tid; it < 32 * 32; it += CV_THREADS) {    // 32 k-rows x 32 chunks (128 m / 4)
       const int k = it >> 5, ch = it & 31;
       float v[4];
@@ -563,8 +590,7 @@ tf32x3_gemm_mn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
         const int m = ch * 4 + i, kk = j * 32 + k;
         v[i] = (m0 + m < M && kk < K) ? A[(size_t)(m0 + m) * K + kk] : 0.f;
       }
-      const uint32_t off = (uint32_t)(ch >> 3) * colblk + atom_chunk_offset(k, ch & 7);
-      store_split4(A_hi, A_lo, off, make_float4(v[0], v[1], v[2], v[3]));
+      store_split4(A_hi, A_lo, la.off(k, ch), make_float4(v[0], v[1], v[2], v[3]));
     }
     for (int it = tid; it < 32 * ncolB * 8; it += CV_THREADS) {
       const int k = it / (ncolB * 8), ch = it - k * (ncolB * 8);
@@ -574,8 +600,7 @@ tf32x3_gemm_mn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
         const int n = ch * 4 + i, kk = j * 32 + k;
         v[i] = (n < N && kk < K) ? Bm[(size_t)kk * N + n] : 0.f;
       }
-      const uint32_t off = (uint32_t)(ch >> 3) * colblk + atom_chunk_offset(k, ch & 7);
-      store_split4(B_hi, B_lo, off, make_float4(v[0], v[1], v[2], v[3]));
+      store_split4(B_hi, B_lo, lb.off(k, ch), make_float4(v[0], v[1], v[2], v[3]));
     }
     fence_async_smem();
     __syncthreads();
@@ -584,11 +609,8 @@ tf32x3_gemm_mn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
       const int kleft = K - j * 32;
       const int ksteps = kleft >= 32 ? 4 : (kleft + 7) / 8;
       for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t o = ks * GROUP_BYTES;  // next 8-row group along K
-        const uint64_t ah = make_smem_desc_sw128_mn(smem_u32(A_hi) + o, colblk, GROUP_BYTES);
-        const uint64_t al = make_smem_desc_sw128_mn(smem_u32(A_lo) + o, colblk, GROUP_BYTES);
-        const uint64_t bh = make_smem_desc_sw128_mn(smem_u32(B_hi) + o, colblk, GROUP_BYTES);
-        const uint64_t bl = make_smem_desc_sw128_mn(smem_u32(B_lo) + o, colblk, GROUP_BYTES);
+        const uint64_t ah = la.desc(smem_u32(A_hi), ks), al = la.desc(smem_u32(A_lo), ks);
+        const uint64_t bh = lb.desc(smem_u32(B_hi), ks), bl = lb.desc(smem_u32(B_lo), ks);
         mma_tf32(tmem_base + (uint32_t)Npad, al, bh, idesc, acc_small ? 1u : 0u);
         mma_tf32(tmem_base + (uint32_t)Npad, ah, bl, idesc, 1u);
         mma_tf32(tmem_base, ah, bh, idesc, acc_main ? 1u : 0u);
@@ -633,7 +655,9 @@ int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, 
     const size_t smem_mn = (size_t)(8 + 2 * ((Npad + 31) / 32)) * 32 * ATOM_ROW_BYTES + 64;
     STC_TRY(set_smem(tf32x3_gemm_mn_kernel, smem_mn));
     ScopedKernelTimer _t(KK_TC_GEMM_TEST, st, 4.0 * ((double)M * K + (double)K * N + (double)M * N));
-    tf32x3_gemm_mn_kernel<<<ceil_div(M, 128), CV_THREADS, smem_mn, st>>>(A, Bm, D, M, N, K, Npad, cols);
+    int variant = 0;
+    if (const char* e = getenv("STC_TC_MN_VARIANT")) variant = atoi(e);
+    tf32x3_gemm_mn_kernel<<<ceil_div(M, 128), CV_THREADS, smem_mn, st>>>(A, Bm, D, M, N, K, Npad, cols, variant);
     STC_LAUNCH_OK("tf32x3_gemm_mn_kernel");
     return STC_OK;
   }

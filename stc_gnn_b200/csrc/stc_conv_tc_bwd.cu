@@ -3,6 +3,7 @@
 // tc_conv_bwd_dx_kernel, per 128-row tile (whole nodes x all categories):
 //   1. CUDA cores: GRU / activation adjoint -> pre-activation gradient Ds [rows][Hout] (also written to HBM for
 //      the dW kernel), bias-gradient column sums, the direct dH terms;
+//      (Ds and its unmixed copies Dm_c are also written to HBM for the dW kernel, stc_conv_tc_dw.cu)
 //   2. the categorical mix is pulled onto the K side:  dY_k = [Ds | Dm_1 | ...] x [W_{k,0}^T ; W_{k,1}^T ; ...]
 //      with Dm_c[(node,c')] = sum_d T_c(Gc)[c',d] Ds[(node,d)]  (adjoint of 'bmcl,cd->bmdl', STC_GNN.py:38),
 //      so one 3xTF32 tensor-core GEMM [rows x Kc*Hout] x [Kc*Hout x Ks*KBL] yields every spatial-term adjoint;
@@ -132,7 +133,7 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
             if (!(cc.z > 0.f)) g0v.z = 0.f;
             if (!(cc.w > 0.f)) g0v.w = 0.f;
           }
-          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * Hout + j) = g0v;
+          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * p.Kdd + j) = g0v;
         } else {
           const float4 hp = *reinterpret_cast<const float4*>(a.Hprev + o);
           const float4 rr = *reinterpret_cast<const float4*>(a.r + o);
@@ -153,8 +154,8 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
           }
           dir = make_float4(dhn.x * (1.f - uu.x) + drh.x * rr.x, dhn.y * (1.f - uu.y) + drh.y * rr.y,
                             dhn.z * (1.f - uu.z) + drh.z * rr.z, dhn.w * (1.f - uu.w) + drh.w * rr.w);
-          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * Hout + j) = g0v;
-          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * Hout + h + j) = g1v;
+          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * p.Kdd + j) = g0v;
+          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * p.Kdd + h + j) = g1v;
         }
       }
       *reinterpret_cast<float4*>(Dsm + row * DP + j) = g0v;
@@ -193,6 +194,8 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
               const float4 x = *reinterpret_cast<const float4*>(sp + d * DP);
               v.x = fmaf(w, x.x, v.x); v.y = fmaf(w, x.y, v.y); v.z = fmaf(w, x.z, v.z); v.w = fmaf(w, x.w, v.w);
             }
+            if (r0 + 32 * i < rows_valid)   // the dW kernel contracts Y_k^T with [Ds | Dm_1 | ...] straight from HBM
+              *reinterpret_cast<float4*>(a.dpre + (row0 + r0 + 32 * i) * p.Kdd + kk) = v;
           }
         }
         store_split4(A_hi, A_lo, aoff[i], v);
@@ -352,12 +355,6 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
   tc_conv_bwd_dx_kernel<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
   STC_LAUNCH_OK("tc_conv_bwd_dx_kernel");
   *handled = true;
-  return STC_OK;
-}
-
-int try_launch_conv_bwd_dw_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
-  *handled = false;   // tensor-core dW lands next; the FFMA kernel is still the one that runs
-  (void)a; (void)st;
   return STC_OK;
 }
 

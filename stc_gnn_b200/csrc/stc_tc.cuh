@@ -68,15 +68,22 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 }
 
 // MN-major operand (the K index is the slow one: tile rows = K, 128-byte rows hold 32 consecutive M/N elements).
-// Physically the same swizzled [rows][128 B] blocks as the K-major atoms; LBO = pitch between 32-element column
-// blocks along M/N, SBO = pitch between 8-row groups along K.  One MMA (K = 8) consumes one 8-row group.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// For 32-bit (tf32) operands the only MN-major swizzle the tensor core accepts is SWIZZLE_128B_BASE32B
+// (layout type 1): rows of 128 bytes in groups of FOUR K-rows (512 bytes, 512-byte aligned); inside a group the
+// 32-byte chunk index (address bits [5,7)) is XOR-ed with the row index (address bits [7,9)).  LBO = pitch between
+// 32-element column blocks along M/N, SBO = pitch between 4-row groups along K.  One MMA (K = 8) consumes two groups.
+constexpr int MN32_GROUP_BYTES = 512;
+// byte offset of the 16-byte chunk q in [0,8) (elements 4q..4q+3 of the 32-wide block) of K-row k
+__device__ __forceinline__ uint32_t mn32_chunk_offset(int k, int q) {
+  return (uint32_t)(k * ATOM_ROW_BYTES + ((((q >> 1) ^ (k & 3)) << 5) | ((q & 1) << 4)));
+}
+__device__ __forceinline__ uint64_t make_smem_desc_mn32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)1 << 61;                            // layout type: SWIZZLE_128B_BASE32B
   return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {  // both operands MN-major

@@ -236,3 +236,22 @@ def test_tf32x3_tensor_core_gemm_block(mnk):
     err = (D.double().cpu() - ref).abs().max().item() / ref.abs().mean().item()
     assert err < 2e-5, f"3xTF32 error {err:.3e} x mean|ref| is not fp32-class"
     O.assert_close(D.cpu(), ref, "tf32x3 gemm")
+
+
+@pytest.mark.parametrize("mnk", [(128, 32, 32), (300, 48, 100), (256, 16, 17), (1000, 256, 72), (128, 64, 64)])
+def test_tf32x3_mn_major_block(mnk, monkeypatch):
+    """Same building block with both operands MN-major (SWIZZLE_128B_BASE32B), the layout of the dW kernel."""
+    from stc_gnn_b200 import _lib
+    lib = _lib.load()
+    monkeypatch.setenv("STC_TC_TEST_MODE", "2")
+    monkeypatch.setenv("STC_TC_MN_VARIANT", "0")
+    M, N, K = mnk
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    Bm = torch.randn(K, N, generator=g).to(DEV)
+    D = torch.empty(M, N, device=DEV)
+    _lib.check(lib.stc_tf32x3_gemm(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), M, N, K,
+                                   torch.cuda.current_stream().cuda_stream), "stc_tf32x3_gemm")
+    torch.cuda.synchronize()
+    ref = A.double().cpu() @ Bm.double().cpu()
+    O.assert_close(D.cpu(), ref, "tf32x3 gemm, MN-major operands")

@@ -8,7 +8,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     torch.backends.cuda.matmul.allow_tf32 = False
     res = {}
     for dist in ("pos", "randn"):
-        for K in (32, 128, 512):
+        for K in (32, 128, 512, 2048):
             g = torch.Generator().manual_seed(K)
             M, N = 4096, 32
             A = (torch.rand(M, K, generator=g) if dist == "pos" else torch.randn(M, K, generator=g)).cuda()

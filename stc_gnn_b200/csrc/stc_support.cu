@@ -187,6 +187,11 @@ int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool tra
       set_error("dense support without vals");
       return STC_ERR_BAD_ARG;
     }
+    if (axpy_out == nullptr) {
+      bool handled = false;
+      STC_TRY(try_launch_support_tc(gs.vals, N, B, width, transpose, x, x_bs, z, z_bs, y, alpha, beta, st, &handled));
+      if (handled) return STC_OK;
+    }
     long long total_q = (long long)B * width;
     dim3 grid(ceil_div(total_q, SD_BQ), ceil_div(N, SD_BM));
     // compulsory traffic: read X, write Y, (+ read Z) (+ read/modify/write of the axpy target), + the support
@@ -295,6 +300,11 @@ support_outer_kernel(int N, int B, int W, const float* __restrict__ A, long long
 int launch_support_outer(int N, int B, int width, const float* a, int64_t a_bs, const float* bmat, float coef,
                          float* dG, cudaStream_t st) {
   if (B <= 0 || N <= 0 || width <= 0) return STC_OK;
+  {
+    bool handled = false;
+    STC_TRY(try_launch_outer_tc(N, B, width, a, a_bs, bmat, coef, dG, st, &handled));
+    if (handled) return STC_OK;
+  }
   int tiles = ceil_div(N, SO_T);
   if (tiles > 65535) {
     set_error("dGs for N=%d is not tiled", N);

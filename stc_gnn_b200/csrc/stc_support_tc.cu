@@ -1,0 +1,463 @@
+// tcgen05 / TMEM spatial-support kernels for a dense learned support that fits one tile (N <= ~104: the shipped
+// SF grid has N = 100).
+//
+//  tc_support_kernel   Y[b,m,:] = alpha * sum_n A(m,n) X[b,n,:] + beta * Z[b,m,:],  A = Gs^T (forward mode product
+//                      'bncl,nm->bmcl', /root/reference/framework/STC_GNN.py:37) or A = Gs (its adjoint).
+//      GEMM orientation: D[m][(b,j)] = sum_n A(m,n) * X[b][n][j] -- the output node is the M axis (128 lanes),
+//      the flattened (sample, feature) index the N axis (64 per tile), the input node the K axis.  Both operands
+//      are MN-major (SWIZZLE_128B_BASE32B): the support image [n][m] is built once per CTA, X rows are contiguous
+//      in j.  3xTF32, one short TMEM chain per tile.
+//      Warp-specialised, mbarrier-pipelined:  warp 0 issues the MMAs, warps 1-8 stream X (16-byte loads two tiles
+//      ahead, hi/lo split, swizzled stores into a 2-deep ring), warps 9-12 drain the 2-deep TMEM accumulator ring:
+//      each epilogue thread owns one output node and writes 256 contiguous bytes per tile with 16-byte stores.
+#include "stc_conv_common.cuh"
+#include "stc_tc.cuh"
+
+#include <stdlib.h>
+
+namespace stc {
+
+using namespace tc;
+
+constexpr int TS_NT = 64;                    // (b,j) columns per tile = GEMM N
+constexpr int TS_PROD_WARPS = 8, TS_EPI_WARPS = 4;
+constexpr int TS_THREADS = 32 * (1 + TS_PROD_WARPS + TS_EPI_WARPS);
+constexpr int TS_SLOTS = 8;                  // 16-byte chunks per producer thread per tile (Kp <= 128)
+
+struct TcSupPlan {
+  int N, Kp, Mimg, W, transpose;
+  long long total_cols, ntiles;
+  int tmem_cols;
+  uint32_t off_g, off_x, off_bar, smem_bytes, imgG, imgX;
+};
+
+__global__ void __launch_bounds__(TS_THREADS, 1)
+tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long long x_bs, const float* Z,
+                  long long z_bs, float* Y, float alpha, float beta, const TcSupPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, Kp = p.Kp, W = p.W;
+  uint8_t* G_hi = smem + p.off_g;               // [4 column blocks of 32 m][Kp rows][128 B]
+  uint8_t* G_lo = G_hi + p.imgG;
+  uint8_t* Xbuf = smem + p.off_x;               // [2 buffers][hi | lo][2 column blocks][Kp][128 B]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [2] producers -> MMA
+  uint64_t* empty = full + 2;                                       // [2] MMA -> producers
+  uint64_t* accfull = full + 4;                                     // [2] MMA -> epilogue
+  uint64_t* accempty = full + 6;                                    // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 8);
+  const uint32_t colblk = (uint32_t)Kp * ATOM_ROW_BYTES;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], TS_PROD_WARPS);
+      mbar_init(&empty[i], 1);
+      mbar_init(&accfull[i], 1);
+      mbar_init(&accempty[i], TS_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // support image: element (k = input node, m = output node) = A(m, k):  Gs[k][m] (transpose) or Gs[m][k]
+  for (int it = tid; it < Kp * 32; it += TS_THREADS) {
+    const int k = it >> 5, ch = it & 31;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = ch * 4 + i;
+      v[i] = (k < N && m < N) ? (p.transpose ? G[(size_t)k * N + m] : G[(size_t)m * N + k]) : 0.f;
+    }
+    store_split4(G_hi, G_lo, (uint32_t)(ch >> 3) * colblk + mn32_chunk_offset(k, ch & 7), make_float4(v[0], v[1], v[2], v[3]));
+  }
+  // rows N..Kp-1 of the X images are never written by the producers: zero them once
+  for (uint32_t i = tid * 16u; i < 4 * p.imgX; i += TS_THREADS * 16u)
+    *reinterpret_cast<float4*>(Xbuf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long stride = gridDim.x;
+
+  if (warp == 0) {
+    // =========================== MMA issuer (one thread) ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_mn(128, TS_NT);
+      const uint64_t gh0 = make_smem_desc_mn32(smem_u32(G_hi), colblk, MN32_GROUP_BYTES);
+      const uint64_t gl0 = make_smem_desc_mn32(smem_u32(G_lo), colblk, MN32_GROUP_BYTES);
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
+        const int buf = it & 1;
+        const uint32_t par = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&accempty[buf], par ^ 1u);     // the epilogue drained this accumulator pair (first use: passes)
+        mbar_wait(&full[buf], par);              // the producers staged this X tile
+        fence_after_sync();
+        const uint32_t xhi = smem_u32(Xbuf + (size_t)buf * 2 * p.imgX);
+        const uint64_t xh0 = make_smem_desc_mn32(xhi, colblk, MN32_GROUP_BYTES);
+        const uint64_t xl0 = make_smem_desc_mn32(xhi + p.imgX, colblk, MN32_GROUP_BYTES);
+        const uint32_t d_main = tmem_base + (uint32_t)(buf * 2 * TS_NT), d_small = d_main + TS_NT;
+#pragma unroll 1
+        for (int ks = 0; ks < Kp / 8; ++ks) {
+          const uint64_t o = (uint64_t)(ks * ((2 * MN32_GROUP_BYTES) >> 4));   // K = 8 rows further down
+          mma_tf32(d_small, gl0 + o, xh0 + o, idesc, ks > 0 ? 1u : 0u);
+          mma_tf32(d_small, gh0 + o, xl0 + o, idesc, 1u);
+          mma_tf32(d_main, gh0 + o, xh0 + o, idesc, ks > 0 ? 1u : 0u);
+        }
+        mma_commit(&empty[buf]);      // X buffer may be refilled once these MMAs have read it
+        mma_commit(&accfull[buf]);    // ... and the accumulators are complete
+      }
+    }
+  } else if (warp <= TS_PROD_WARPS) {
+    // =========================== producers ===========================
+    const int pt = tid - 32;
+    const int c0 = (pt & 15) << 2, r0 = pt >> 4;       // chunk column of the 64-wide tile, rows r0 + 16 i
+    const uint32_t soff0 = (uint32_t)(c0 >> 5) * colblk + mn32_chunk_offset(r0, (c0 & 31) >> 2);
+    float4 ra[2][TS_SLOTS];
+    auto fetch = [&](long long tile, float4 (&r)[TS_SLOTS]) {
+      const long long cg = tile * TS_NT + c0;
+      const bool ok = tile < p.ntiles && cg < p.total_cols;     // W % 4 == 0: a chunk never straddles samples
+      const long long b = ok ? cg / W : 0;
+      const float* src = X + b * x_bs + (cg - b * W);
+#pragma unroll
+      for (int i = 0; i < TS_SLOTS; ++i) {
+        const int n = r0 + 16 * i;
+        r[i] = (ok && n < N) ? __ldg(reinterpret_cast<const float4*>(src + (long long)n * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto stage = [&](int it, const float4 (&r)[TS_SLOTS]) {
+      const int buf = it & 1;
+      mbar_wait(&empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // MMAs of the tile two back have read this buffer
+      uint8_t* hi = Xbuf + (size_t)buf * 2 * p.imgX;
+      uint8_t* lo = hi + p.imgX;
+#pragma unroll
+      for (int i = 0; i < TS_SLOTS; ++i)
+        if (r0 + 16 * i < N) store_split4(hi, lo, soff0 + (uint32_t)(16 * i) * ATOM_ROW_BYTES, r[i]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[buf]);
+    };
+    long long tile = blockIdx.x;
+    fetch(tile, ra[0]);
+    fetch(tile + stride, ra[1]);
+    for (int it = 0; tile < p.ntiles; it += 2) {
+      stage(it, ra[0]);
+      fetch(tile + 2 * stride, ra[0]);
+      tile += stride;
+      if (tile >= p.ntiles) break;
+      stage(it + 1, ra[1]);
+      fetch(tile + 2 * stride, ra[1]);
+      tile += stride;
+    }
+  } else {
+    // =========================== epilogue: one output node per thread ===========================
+    const int sp = warp & 3;                       // TMEM sub-partition this warp may read
+    const int m = sp * 32 + lane;
+    const bool live = m < N;
+    const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
+      const int buf = it & 1;
+      long long cg = tile * TS_NT;
+      long long b = cg / W;
+      int j = (int)(cg - b * W);
+      mbar_wait(&accfull[buf], (uint32_t)(it >> 1) & 1u);
+      fence_after_sync();
+#pragma unroll
+      for (int hh = 0; hh < TS_NT / 16; ++hh) {    // 16 columns at a time
+        uint32_t vm[16], vs[16];
+        float4 zz[4];
+        // Z first: its latency hides behind the TMEM loads
+        {
+          long long cb = b;
+          int cj = j;
+          long long cgg = cg;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            zz[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (beta != 0.f && live && cgg < p.total_cols)
+              zz[g] = *reinterpret_cast<const float4*>(Z + cb * z_bs + (long long)m * W + cj);
+            cj += 4; cgg += 4;
+            if (cj >= W) { cj = 0; ++cb; }
+          }
+        }
+        const uint32_t a0 = tl + (uint32_t)(buf * 2 * TS_NT + hh * 16);
+        tmem_ld16_async(a0, vm);
+        tmem_ld16_async(a0 + TS_NT, vs);
+        tmem_ld_wait();
+        tmem_ld_pin16(vm);
+        tmem_ld_pin16(vs);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (live && cg < p.total_cols) {
+            float4 o;
+            o.x = fmaf(beta, zz[g].x, alpha * (__uint_as_float(vm[4 * g + 0]) + __uint_as_float(vs[4 * g + 0])));
+            o.y = fmaf(beta, zz[g].y, alpha * (__uint_as_float(vm[4 * g + 1]) + __uint_as_float(vs[4 * g + 1])));
+            o.z = fmaf(beta, zz[g].z, alpha * (__uint_as_float(vm[4 * g + 2]) + __uint_as_float(vs[4 * g + 2])));
+            o.w = fmaf(beta, zz[g].w, alpha * (__uint_as_float(vm[4 * g + 3]) + __uint_as_float(vs[4 * g + 3])));
+            *reinterpret_cast<float4*>(Y + (b * N + m) * (long long)W + j) = o;
+          }
+          j += 4; cg += 4;
+          if (j >= W) { j = 0; ++b; }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&accempty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+static bool aligned16s(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static bool tc_support_disabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("STC_DISABLE_TC");
+    cached = (e && e[0] && e[0] != '0') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+// Dense support on the tensor cores when the whole support fits one resident image; *handled tells the caller.
+int try_launch_support_tc(const float* G, int N, int B, int width, bool transpose, const float* x, int64_t x_bs,
+                          const float* z, int64_t z_bs, float* y, float alpha, float beta, cudaStream_t st,
+                          bool* handled) {
+  *handled = false;
+  if (tc_support_disabled()) return STC_OK;
+  if (width % 4 != 0 || x_bs % 4 != 0 || !aligned16s(x) || !aligned16s(y) || N < 8 || N > 128) return STC_OK;
+  if (beta != 0.f && (z == nullptr || z_bs % 4 != 0 || !aligned16s(z))) return STC_OK;
+  TcSupPlan p;
+  p.N = N;
+  p.Kp = (N + 7) & ~7;
+  p.Mimg = 128;
+  if (p.Kp > 16 * TS_SLOTS) return STC_OK;
+  p.W = width;
+  p.transpose = transpose ? 1 : 0;
+  p.total_cols = (long long)B * width;
+  p.ntiles = (p.total_cols + TS_NT - 1) / TS_NT;
+  p.imgG = (uint32_t)4 * p.Kp * ATOM_ROW_BYTES;
+  p.imgX = (uint32_t)(TS_NT / 32) * p.Kp * ATOM_ROW_BYTES;
+  p.tmem_cols = 256;   // 2 x (main + cross-term) x 64 columns
+  size_t o = 0;
+  p.off_g = (uint32_t)o; o += 2 * (size_t)p.imgG;
+  o = round_up(o, 1024);
+  p.off_x = (uint32_t)o; o += 4 * (size_t)p.imgX;
+  o = round_up(o, 16);
+  p.off_bar = (uint32_t)o; o += 96;
+  p.smem_bytes = (uint32_t)o;
+  if (p.smem_bytes > 227 * 1024) return STC_OK;   // larger N: the FFMA kernel tiles it
+  STC_TRY(set_smem(tc_support_kernel, p.smem_bytes));
+  long long grid = device_sm_count();
+  if (grid > p.ntiles) grid = p.ntiles;
+  ScopedKernelTimer _t(KK_TC_SUPPORT, st, 4.0 * B * N * width * (2 + (beta != 0.f ? 1 : 0)) + 4.0 * N * N);
+  tc_support_kernel<<<(int)grid, TS_THREADS, p.smem_bytes, st>>>(G, x, x_bs, z, z_bs, y, alpha, beta, p);
+  STC_LAUNCH_OK("tc_support_kernel");
+  *handled = true;
+  return STC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+//  tc_outer_kernel     dGs[n][m] += coef * sum_{b,j} A[b][n][j] * Bm[b][m][j]
+//      (gradient of the mode product of STC_GNN.py:37 w.r.t. the support; the reference gets it from autograd).
+//      GEMM: M = n, N = m, K = (b, j).  Both operands are K-major as stored (a node's feature slab is contiguous),
+//      one SW128 atom = 32 features of one sample.  Three main TMEM accumulators are used round-robin plus one for
+//      the 3xTF32 cross terms; every TO_DRAIN atoms they are drained into fp32 registers (bounded chains, see
+//      profiles/r1_tc_precision.txt); one atomicAdd per element per CTA at the end.
+// ------------------------------------------------------------------------------------------------
+constexpr int TO_DRAIN = 48;
+
+struct TcOuterPlan {
+  int N, Npad, W, B, atoms_per_sample;
+  int tmem_cols;
+  uint32_t imgA, imgB, off_bar, smem_bytes;
+};
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __restrict__ Bm, float coef, float* dG,
+                const TcOuterPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, W = p.W;
+  const uint32_t bufsz = 2 * p.imgA + 2 * p.imgB;    // [A hi | A lo | B hi | B lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  for (uint32_t i = tid * 16u; i < 2 * bufsz; i += CV_THREADS * 16u)   // rows >= N stay zero for good
+    *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, p.Npad);
+  const uint32_t d_small = tmem_base + (uint32_t)(3 * p.Npad);
+
+  // staging map: chunk q of rows r0 + 32 i of either operand
+  const int q = tid & 7, r0 = tid >> 3;
+  uint32_t soff[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) soff[i] = atom_chunk_offset(r0 + 32 * i, q);
+  float4 ra[4], rb[4];
+  auto fetch = [&](long long seq) {   // seq = local atom index -> (sample, atom within sample)
+    const long long s = seq / p.atoms_per_sample;
+    const int at = (int)(seq - s * p.atoms_per_sample);
+    const long long b = blockIdx.x + s * (long long)gridDim.x;
+    const int j = at * ATOM_K + q * 4;
+    const bool ok = j < W;               // W % 4 == 0
+    const float* pa = A + b * a_bs + j;
+    const float* pb = Bm + b * (long long)N * W + j;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 32 * i;
+      const bool live = ok && r < N;
+      ra[i] = live ? __ldg(reinterpret_cast<const float4*>(pa + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[i] = live ? __ldg(reinterpret_cast<const float4*>(pb + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stage = [&](int buf) {
+    uint8_t* base = smem + (size_t)buf * bufsz;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (r0 + 32 * i < N) {
+        store_split4(base, base + p.imgA, soff[i], ra[i]);
+        store_split4(base + 2 * p.imgA, base + 2 * p.imgA + p.imgB, soff[i], rb[i]);
+      }
+    }
+  };
+
+  const int nsamples = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long long natoms = (long long)nsamples * p.atoms_per_sample;
+
+  // accumulators: thread (sub-partition sp, half) owns row 32 sp + lane and Npad/2 columns
+  const int sp = warp & 3, half = warp >> 2;
+  const int nrow = sp * 32 + lane;
+  const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
+  const int ncols_half = p.Npad >> 1, col0 = half * ncols_half;
+  float acc[8][8];   // Npad <= 128 -> at most 64 columns per thread
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  bool pend[2] = {false, false};
+  uint32_t ph[2] = {0u, 0u};
+  bool acc_main[3] = {false, false, false}, acc_small = false;
+  int since_drain = 0;
+  auto drain = [&]() {
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+      if (pend[b]) {
+        mbar_wait(&bars[b], ph[b]);
+        ph[b] ^= 1u;
+        pend[b] = false;
+      }
+    fence_after_sync();
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      if (ch * 8 < ncols_half) {
+        float v[8], t[8];
+        const uint32_t cc = (uint32_t)(col0 + ch * 8);
+        tmem_ld8(tl + (uint32_t)(3 * p.Npad) + cc, v);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          if (acc_main[m]) {
+            tmem_ld8(tl + (uint32_t)(m * p.Npad) + cc, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += t[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[ch][i] += v[i];
+      }
+    }
+    fence_before_sync();
+    acc_main[0] = acc_main[1] = acc_main[2] = false;
+    acc_small = false;
+    since_drain = 0;
+  };
+
+  if (natoms > 0) fetch(0);
+  for (long long seq = 0; seq < natoms; ++seq) {
+    const int buf = (int)(seq & 1);
+    if (pend[buf]) {   // the MMAs that read this buffer two atoms ago
+      mbar_wait(&bars[buf], ph[buf]);
+      ph[buf] ^= 1u;
+      pend[buf] = false;
+    }
+    stage(buf);
+    fence_async_smem();
+    __syncthreads();
+    const int at = (int)(seq % p.atoms_per_sample);
+    const int kleft = W - at * ATOM_K;
+    const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
+    const int mi = since_drain % 3;
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t base = smem_u32(smem + (size_t)buf * bufsz);
+      bool am = acc_main[mi], as = acc_small;
+      mma_atom_3x_split(tmem_base + (uint32_t)(mi * p.Npad), d_small, base, base + p.imgA, base + 2 * p.imgA,
+                        base + 2 * p.imgA + p.imgB, ksteps, idesc, am, as);
+      mma_commit(&bars[buf]);
+    }
+    acc_main[mi] = true;
+    acc_small = true;
+    pend[buf] = true;
+    ++since_drain;
+    if (seq + 1 < natoms) fetch(seq + 1);
+    if (since_drain >= TO_DRAIN) drain();
+  }
+  if (since_drain > 0) drain();
+
+  if (nrow < N) {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      if (ch * 8 < ncols_half) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = col0 + ch * 8 + i;
+          if (m < N) atomicAdd(&dG[(size_t)nrow * N + m], coef * acc[ch][i]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+int try_launch_outer_tc(int N, int B, int width, const float* a, int64_t a_bs, const float* bmat, float coef, float* dG,
+                        cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (tc_support_disabled()) return STC_OK;
+  if (width % 4 != 0 || a_bs % 4 != 0 || !aligned16s(a) || !aligned16s(bmat) || N < 8 || N > 128) return STC_OK;
+  TcOuterPlan p;
+  p.N = N;
+  p.Npad = (N + 15) & ~15;
+  p.W = width;
+  p.B = B;
+  p.atoms_per_sample = (width + ATOM_K - 1) / ATOM_K;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 4 * p.Npad) p.tmem_cols *= 2;
+  p.imgA = 128 * ATOM_ROW_BYTES;
+  p.imgB = (uint32_t)round_up((size_t)p.Npad * ATOM_ROW_BYTES, 1024);
+  const uint32_t bufsz = 2 * p.imgA + 2 * p.imgB;
+  p.off_bar = 2 * bufsz;
+  p.smem_bytes = p.off_bar + 32;
+  STC_TRY(set_smem(tc_outer_kernel, p.smem_bytes));
+  int grid = device_sm_count();
+  if (grid > B) grid = B;
+  ScopedKernelTimer _t(KK_TC_OUTER, st, 4.0 * B * N * width * 2 + 4.0 * N * N);
+  tc_outer_kernel<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, a_bs, bmat, coef, dG, p);
+  STC_LAUNCH_OK("tc_outer_kernel");
+  *handled = true;
+  return STC_OK;
+}
+
+}  // namespace stc

@@ -94,6 +94,25 @@ int stc_cell_fwd(const StcDims* d, const StcSupport* gs, const float* gc,
                  const float* Wg, const float* bg, const float* Wc, const float* bc,
                  float* h_out, void* saved, size_t saved_bytes, void* stream);
 
+/* ---- the cell split at its spatial-support stages (row-partitioned graphs, stc_gnn_b200/halo.py) ----
+ * A rank that owns a block of nodes cannot run the spatial hops inside stc_cell_fwd: each hop needs the
+ * boundary-node features of its neighbours (an NCCL halo exchange).  The caller therefore
+ *   1. fills the spatial terms of Xt and H (regions STC_SAVED_YX, STC_SAVED_YH of `saved`, Ks-1 terms each,
+ *      [B][N][C][Din or h] contiguous) with stc_support_apply + its exchange,
+ *   2. calls stage STC_STAGE_GATES  (node-local: Gc terms, gates conv, writes u, r and r*H = term 0 of STC_SAVED_YR),
+ *   3. fills terms 1..Ks-1 of STC_SAVED_YR the same way,
+ *   4. calls stage STC_STAGE_CANDI  (node-local: candidate conv, tanh, GRU blend -> h_out).
+ * d->N is the number of LOCAL nodes.  stc_cell_saved_layout writes the offset (in floats) of every region of
+ * `saved` into offsets[STC_SAVED_REGIONS]. */
+enum { STC_STAGE_GATES = 0, STC_STAGE_CANDI = 1 };
+enum { STC_SAVED_U = 0, STC_SAVED_R, STC_SAVED_C, STC_SAVED_YR, STC_SAVED_YX, STC_SAVED_YH, STC_SAVED_Q,
+       STC_SAVED_PG, STC_SAVED_PC, STC_SAVED_REGIONS };
+int stc_cell_saved_layout(const StcDims* d, int64_t* offsets_floats, int32_t n_offsets);
+int stc_cell_fwd_stage(const StcDims* d, int32_t stage, const float* gc,
+                       const float* xt, int64_t xt_batch_stride, const float* h_prev,
+                       const float* Wg, const float* bg, const float* Wc, const float* bc,
+                       float* h_out, void* saved, size_t saved_bytes, void* stream);
+
 /* Gradients of stc_cell_fwd given d_h_out.  `saved` is the buffer the matching forward call filled.
  *   d_xt      [B][N][C][Din] contiguous, or NULL when Xt needs no gradient
  *   d_h_prev  [B][N][C][h]

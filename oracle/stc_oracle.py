@@ -136,17 +136,19 @@ def _activate(x: Tensor, activation: Optional[str]) -> Tensor:
 # lean restatement
 # --------------------------------------------------------------------------- #
 def bdg_dif(X: Tensor, Gs, Gc: Tensor, W: Tensor, b: Optional[Tensor], Ks: int, Kc: int,
-            activation: Optional[str] = None) -> Tensor:
+            activation: Optional[str] = None, spatial_terms_fn=None) -> Tensor:
     """out[b,m,d,:] = sum_{n<Ks, c<Kc}  (T_c(Gc)^T (x) T_n(Gs)^T X)[b,m,d,:] @ W[(n*Kc+c)*L:(n*Kc+c+1)*L]  + b
     (STC_GNN.py:31-47; W row order is (n, c, l) because feat_coll is appended n-outer/c-inner and
-    concatenated on the last axis, :35-41)."""
+    concatenated on the last axis, :35-41).  ``spatial_terms_fn(X) -> [Y_0..Y_{Ks-1}]`` replaces the spatial
+    recurrence (the row-partitioned tests inject halo-exchanging hops; Gs is then unused)."""
     B, N, C, L = X.shape
     Hout = W.shape[1]
     assert W.shape[0] == Ks * Kc * L, (W.shape, Ks, Kc, L)
     Wv = W.reshape(Ks, Kc, L, Hout)
     Q = cheby_matrix_terms(Gc, Kc)
     out = None
-    for n, Yn in enumerate(spatial_terms(X, Gs, Ks)):
+    terms = spatial_terms_fn(X) if spatial_terms_fn is not None else spatial_terms(X, Gs, Ks)
+    for n, Yn in enumerate(terms):
         for c in range(Kc):
             F = Yn if c == 0 else categorical_T_apply(Q[c], Yn)
             term = F @ Wv[n, c]
@@ -158,15 +160,15 @@ def bdg_dif(X: Tensor, Gs, Gc: Tensor, W: Tensor, b: Optional[Tensor], Ks: int, 
 
 def stc_cell(Gs, Gc: Tensor, Xt: Tensor, H: Tensor, Wg: Tensor, bg: Optional[Tensor], Wc: Tensor,
              bc: Optional[Tensor], Ks: int, Kc: int, activation: Optional[str] = None,
-             return_gates: bool = False):
+             return_gates: bool = False, spatial_terms_fn=None):
     """GRU cell of STC_GNN.py:65-79: [u|r] = sigmoid(conv_g([Xt,H])), c = tanh(conv_c([Xt, r*H])),
     H' = (1-u)*H + u*c.  u is the FIRST h output channels, r the last h (torch.split, :71)."""
     assert Xt.dim() == 4 and H.dim() == 4
     h = H.shape[-1]
-    g = bdg_dif(torch.cat([Xt, H], dim=-1), Gs, Gc, Wg, bg, Ks, Kc, activation)
+    g = bdg_dif(torch.cat([Xt, H], dim=-1), Gs, Gc, Wg, bg, Ks, Kc, activation, spatial_terms_fn)
     u = torch.sigmoid(g[..., :h])
     r = torch.sigmoid(g[..., h:])
-    c = torch.tanh(bdg_dif(torch.cat([Xt, r * H], dim=-1), Gs, Gc, Wc, bc, Ks, Kc, activation))
+    c = torch.tanh(bdg_dif(torch.cat([Xt, r * H], dim=-1), Gs, Gc, Wc, bc, Ks, Kc, activation, spatial_terms_fn))
     Hn = (1.0 - u) * H + u * c
     if return_gates:
         return Hn, u, r, c

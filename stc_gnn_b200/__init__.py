@@ -6,8 +6,11 @@ Public surface:
   CsrSupport          constant sparse spatial support
   support_apply       the spatial mode product on its own
   install / run_main  rebind STC_GNN.STC_Cell so Model_Trainer.py / Main.py run unchanged
+  dp                  batch data-parallel gradient bucket (one flat all-reduce per step)
+  halo                row-partitioned CSR support with per-hop halo exchange
 """
 from .cell import STC_Cell, GraphConvParams, stc_cell_forward  # noqa: F401
 from .support import CsrSupport, support_apply  # noqa: F401
 from .install import install, run_main  # noqa: F401
 from .stack import RecurrentStack  # noqa: F401
+from . import dp, halo  # noqa: F401

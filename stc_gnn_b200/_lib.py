@@ -19,7 +19,10 @@ EXPORTED = (
     "stc_abi_version", "stc_last_error", "stc_cell_saved_bytes", "stc_cell_bwd_scratch_bytes",
     "stc_cell_fwd", "stc_cell_bwd", "stc_support_apply", "stc_last_launch_count",
     "stc_timing_enable", "stc_timing_collect", "stc_kernel_kind_name", "stc_tf32x3_gemm",
+    "stc_cell_saved_layout", "stc_cell_fwd_stage",
 )
+STAGE_GATES, STAGE_CANDI = 0, 1
+SAVED_REGIONS = ("u", "r", "c", "Yr", "Yx", "Yh", "Q", "Pg", "Pc")
 
 
 class StcDims(Structure):
@@ -55,6 +58,11 @@ def load(build_if_missing: bool = True):
     lib.stc_cell_fwd.restype = c_int
     lib.stc_cell_fwd.argtypes = [POINTER(StcDims), POINTER(StcSupport), c_void_p, c_void_p, c_int64, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.stc_cell_saved_layout.restype = c_int
+    lib.stc_cell_saved_layout.argtypes = [POINTER(StcDims), POINTER(c_int64), c_int32]
+    lib.stc_cell_fwd_stage.restype = c_int
+    lib.stc_cell_fwd_stage.argtypes = [POINTER(StcDims), c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.stc_cell_bwd.restype = c_int
     lib.stc_cell_bwd.argtypes = [POINTER(StcDims), POINTER(StcSupport), c_void_p, c_void_p, c_int64, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -75,6 +83,14 @@ def load(build_if_missing: bool = True):
         raise RuntimeError(f"libstc_b200.so ABI {lib.stc_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
     _lib = lib
     return lib
+
+
+def saved_layout(dims: StcDims) -> dict:
+    """{region name: offset in floats} of the `saved` buffer of one cell call."""
+    lib = load()
+    offs = (c_int64 * len(SAVED_REGIONS))()
+    check(lib.stc_cell_saved_layout(dims, offs, len(SAVED_REGIONS)), "stc_cell_saved_layout")
+    return {n: int(offs[i]) for i, n in enumerate(SAVED_REGIONS)}
 
 
 def check(status: int, what: str) -> None:

@@ -225,85 +225,166 @@ int stc_tf32x3_gemm(const float* a, const float* b, float* d, int32_t M, int32_t
   return launch_tf32x3_gemm(a, b, d, M, N, K, (cudaStream_t)stream);
 }
 
-int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
-                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* bg, const float* Wc,
-                 const float* bc, float* h_out, void* wsv, size_t ws_bytes, void* stream) {  // wsv = `saved`
-  reset_launch_count();
-  STC_TRY(check_dims(dp));
-  const StcDims& d = *dp;
-  if (!gs || !gc || !xt || !h_prev || !Wg || !Wc || !h_out || !wsv) {
-    set_error("stc_cell_fwd: NULL argument");
-    return STC_ERR_BAD_ARG;
-  }
-  if (d.has_bias && (!bg || !bc)) {
-    set_error("stc_cell_fwd: has_bias set but bias pointer is NULL");
-    return STC_ERR_BAD_ARG;
-  }
-  const WsLayout w = make_layout(d);
-  if (ws_bytes < w.saved_total * sizeof(float)) {
-    set_error("saved buffer too small: %zu < %zu bytes", ws_bytes, w.saved_total * sizeof(float));
-    return STC_ERR_WORKSPACE;
-  }
-  if (d.B == 0) return STC_OK;
-  STC_TRY(check_arch());
-  cudaStream_t st = (cudaStream_t)stream;
-  float* ws = (float*)wsv;
+// ---- forward pieces (stc_cell_fwd runs all four; the row-partitioned path runs the two node-local ones and does
+//      the spatial hops itself, with a halo exchange before each) ----
+struct FwdCtx {
+  const StcDims& d;
+  const WsLayout& w;
+  const StcSupport* gs;
+  const float* gc;
+  const float* xt;
+  int64_t xt_bs;
+  const float* h_prev;
+  float* ws;
+  cudaStream_t st;
+};
+
+// spatial Chebyshev terms of Xt and H:  Y_1 = Gs^T Y_0,  Y_k = 2 Gs^T Y_{k-1} - Y_{k-2}
+static int fwd_terms_xh(const FwdCtx& f) {
+  const StcDims& d = f.d;
+  const WsLayout& w = f.w;
+  float* ws = f.ws;
   const size_t Rh = w.R * d.h, Rx = w.R * d.Din;
   const int CD = d.C * d.Din, CH = d.C * d.h;
   const long long nbs_h = (long long)d.N * CH;
-
-  if (d.Kc > 1) STC_TRY(launch_cheby_small(gc, d.C, d.Kc, ws + w.Q, st));
-
-  // spatial Chebyshev terms of Xt and H:  Y_1 = Gs^T Y_0,  Y_k = 2 Gs^T Y_{k-1} - Y_{k-2}
   for (int k = 1; k < d.Ks; ++k) {
     const float alpha = k == 1 ? 1.f : 2.f, beta = k == 1 ? 0.f : -1.f;
-    const float* xin = k == 1 ? xt : ws + w.Yx + (size_t)(k - 2) * Rx;
-    const int64_t xin_bs = k == 1 ? xt_batch_stride : (int64_t)d.N * CD;
-    const float* xz = k == 1 ? nullptr : (k == 2 ? xt : ws + w.Yx + (size_t)(k - 3) * Rx);
-    const int64_t xz_bs = k == 2 ? xt_batch_stride : (int64_t)d.N * CD;
-    STC_TRY(launch_support_apply(*gs, d.N, d.B, CD, true, xin, xin_bs, xz, xz_bs, ws + w.Yx + (size_t)(k - 1) * Rx,
-                                 alpha, beta, nullptr, 0.f, st));
-    const float* hin = k == 1 ? h_prev : ws + w.Yh + (size_t)(k - 2) * Rh;
-    const float* hz = k == 1 ? nullptr : (k == 2 ? h_prev : ws + w.Yh + (size_t)(k - 3) * Rh);
-    STC_TRY(launch_support_apply(*gs, d.N, d.B, CH, true, hin, nbs_h, hz, nbs_h, ws + w.Yh + (size_t)(k - 1) * Rh,
-                                 alpha, beta, nullptr, 0.f, st));
+    const float* xin = k == 1 ? f.xt : ws + w.Yx + (size_t)(k - 2) * Rx;
+    const int64_t xin_bs = k == 1 ? f.xt_bs : (int64_t)d.N * CD;
+    const float* xz = k == 1 ? nullptr : (k == 2 ? f.xt : ws + w.Yx + (size_t)(k - 3) * Rx);
+    const int64_t xz_bs = k == 2 ? f.xt_bs : (int64_t)d.N * CD;
+    STC_TRY(launch_support_apply(*f.gs, d.N, d.B, CD, true, xin, xin_bs, xz, xz_bs, ws + w.Yx + (size_t)(k - 1) * Rx,
+                                 alpha, beta, nullptr, 0.f, f.st));
+    const float* hin = k == 1 ? f.h_prev : ws + w.Yh + (size_t)(k - 2) * Rh;
+    const float* hz = k == 1 ? nullptr : (k == 2 ? f.h_prev : ws + w.Yh + (size_t)(k - 3) * Rh);
+    STC_TRY(launch_support_apply(*f.gs, d.N, d.B, CH, true, hin, nbs_h, hz, nbs_h, ws + w.Yh + (size_t)(k - 1) * Rh,
+                                 alpha, beta, nullptr, 0.f, f.st));
   }
+  return STC_OK;
+}
 
-  // gates:  [u|r] = sigmoid(conv([Xt,H])),  rH = r*H
-  {
-    ConvArgs a = base_args(d, xt, xt_batch_stride, Wg, ws + w.Q, ws, w, 0);
-    a.h0 = h_prev;
-    a.yh = ws + w.Yh;
-    a.bias = d.has_bias ? bg : nullptr;
-    a.Hprev = h_prev;
-    a.u = ws + w.u;
-    a.r = ws + w.r;
-    a.rH = ws + w.Yr;
-    a.Psave = ws + w.Pg;
-    STC_TRY(launch_conv_fwd(a, st));
-  }
-  // spatial terms of r*H
+// gates:  [u|r] = sigmoid(conv([Xt,H])),  rH = r*H   (also builds the Chebyshev terms of Gc)
+static int fwd_gates(const FwdCtx& f, const float* Wg, const float* bg) {
+  const StcDims& d = f.d;
+  const WsLayout& w = f.w;
+  float* ws = f.ws;
+  if (d.Kc > 1) STC_TRY(launch_cheby_small(f.gc, d.C, d.Kc, ws + w.Q, f.st));
+  ConvArgs a = base_args(d, f.xt, f.xt_bs, Wg, ws + w.Q, ws, w, 0);
+  a.h0 = f.h_prev;
+  a.yh = ws + w.Yh;
+  a.bias = d.has_bias ? bg : nullptr;
+  a.Hprev = f.h_prev;
+  a.u = ws + w.u;
+  a.r = ws + w.r;
+  a.rH = ws + w.Yr;
+  a.Psave = ws + w.Pg;
+  return launch_conv_fwd(a, f.st);
+}
+
+// spatial terms of r*H
+static int fwd_terms_rh(const FwdCtx& f) {
+  const StcDims& d = f.d;
+  const WsLayout& w = f.w;
+  float* ws = f.ws;
+  const size_t Rh = w.R * d.h;
+  const int CH = d.C * d.h;
+  const long long nbs_h = (long long)d.N * CH;
   for (int k = 1; k < d.Ks; ++k) {
     const float alpha = k == 1 ? 1.f : 2.f, beta = k == 1 ? 0.f : -1.f;
     const float* in = ws + w.Yr + (size_t)(k - 1) * Rh;
     const float* z = k == 1 ? nullptr : ws + w.Yr + (size_t)(k - 2) * Rh;
-    STC_TRY(launch_support_apply(*gs, d.N, d.B, CH, true, in, nbs_h, z, nbs_h, ws + w.Yr + (size_t)k * Rh, alpha, beta,
-                                 nullptr, 0.f, st));
-  }
-  // candidate:  c = tanh(conv([Xt, rH])),  H' = (1-u) H + u c
-  {
-    ConvArgs a = base_args(d, xt, xt_batch_stride, Wc, ws + w.Q, ws, w, 1);
-    a.h0 = ws + w.Yr;
-    a.yh = ws + w.Yr + Rh;
-    a.bias = d.has_bias ? bc : nullptr;
-    a.Hprev = h_prev;
-    a.u = ws + w.u;
-    a.c = ws + w.c;
-    a.Hnew = h_out;
-    a.Psave = ws + w.Pc;
-    STC_TRY(launch_conv_fwd(a, st));
+    STC_TRY(launch_support_apply(*f.gs, d.N, d.B, CH, true, in, nbs_h, z, nbs_h, ws + w.Yr + (size_t)k * Rh, alpha, beta,
+                                 nullptr, 0.f, f.st));
   }
   return STC_OK;
+}
+
+// candidate:  c = tanh(conv([Xt, rH])),  H' = (1-u) H + u c
+static int fwd_candi(const FwdCtx& f, const float* Wc, const float* bc, float* h_out) {
+  const StcDims& d = f.d;
+  const WsLayout& w = f.w;
+  float* ws = f.ws;
+  const size_t Rh = w.R * d.h;
+  ConvArgs a = base_args(d, f.xt, f.xt_bs, Wc, ws + w.Q, ws, w, 1);
+  a.h0 = ws + w.Yr;
+  a.yh = ws + w.Yr + Rh;
+  a.bias = d.has_bias ? bc : nullptr;
+  a.Hprev = f.h_prev;
+  a.u = ws + w.u;
+  a.c = ws + w.c;
+  a.Hnew = h_out;
+  a.Psave = ws + w.Pc;
+  return launch_conv_fwd(a, f.st);
+}
+
+static int check_fwd_args(const StcDims* dp, const float* gc, const float* xt, const float* h_prev, const float* Wg,
+                          const float* bg, const float* Wc, const float* bc, float* h_out, void* wsv, size_t ws_bytes,
+                          const char* who) {
+  STC_TRY(check_dims(dp));
+  if (!gc || !xt || !h_prev || !Wg || !Wc || !h_out || !wsv) {
+    set_error("%s: NULL argument", who);
+    return STC_ERR_BAD_ARG;
+  }
+  if (dp->has_bias && (!bg || !bc)) {
+    set_error("%s: has_bias set but bias pointer is NULL", who);
+    return STC_ERR_BAD_ARG;
+  }
+  const WsLayout w = make_layout(*dp);
+  if (ws_bytes < w.saved_total * sizeof(float)) {
+    set_error("saved buffer too small: %zu < %zu bytes", ws_bytes, w.saved_total * sizeof(float));
+    return STC_ERR_WORKSPACE;
+  }
+  return STC_OK;
+}
+
+int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* bg, const float* Wc,
+                 const float* bc, float* h_out, void* wsv, size_t ws_bytes, void* stream) {  // wsv = `saved`
+  reset_launch_count();
+  STC_TRY(check_fwd_args(dp, gc, xt, h_prev, Wg, bg, Wc, bc, h_out, wsv, ws_bytes, "stc_cell_fwd"));
+  if (!gs) {
+    set_error("stc_cell_fwd: NULL support");
+    return STC_ERR_BAD_ARG;
+  }
+  const StcDims& d = *dp;
+  if (d.B == 0) return STC_OK;
+  STC_TRY(check_arch());
+  const WsLayout w = make_layout(d);
+  const FwdCtx f{d, w, gs, gc, xt, xt_batch_stride, h_prev, (float*)wsv, (cudaStream_t)stream};
+  STC_TRY(fwd_terms_xh(f));
+  STC_TRY(fwd_gates(f, Wg, bg));
+  STC_TRY(fwd_terms_rh(f));
+  STC_TRY(fwd_candi(f, Wc, bc, h_out));
+  return STC_OK;
+}
+
+int stc_cell_saved_layout(const StcDims* dp, int64_t* offsets, int32_t n_offsets) {
+  STC_TRY(check_dims(dp));
+  if (!offsets || n_offsets < STC_SAVED_REGIONS) {
+    set_error("stc_cell_saved_layout: need room for %d offsets", (int)STC_SAVED_REGIONS);
+    return STC_ERR_BAD_ARG;
+  }
+  const WsLayout w = make_layout(*dp);
+  const size_t v[STC_SAVED_REGIONS] = {w.u, w.r, w.c, w.Yr, w.Yx, w.Yh, w.Q, w.Pg, w.Pc};
+  for (int i = 0; i < STC_SAVED_REGIONS; ++i) offsets[i] = (int64_t)v[i];
+  return STC_OK;
+}
+
+int stc_cell_fwd_stage(const StcDims* dp, int32_t stage, const float* gc, const float* xt, int64_t xt_batch_stride,
+                       const float* h_prev, const float* Wg, const float* bg, const float* Wc, const float* bc,
+                       float* h_out, void* wsv, size_t ws_bytes, void* stream) {
+  reset_launch_count();
+  STC_TRY(check_fwd_args(dp, gc, xt, h_prev, Wg, bg, Wc, bc, h_out, wsv, ws_bytes, "stc_cell_fwd_stage"));
+  if (stage != STC_STAGE_GATES && stage != STC_STAGE_CANDI) {
+    set_error("stc_cell_fwd_stage: bad stage %d", stage);
+    return STC_ERR_BAD_ARG;
+  }
+  const StcDims& d = *dp;
+  if (d.B == 0) return STC_OK;
+  STC_TRY(check_arch());
+  const WsLayout w = make_layout(d);
+  const FwdCtx f{d, w, nullptr, gc, xt, xt_batch_stride, h_prev, (float*)wsv, (cudaStream_t)stream};
+  return stage == STC_STAGE_GATES ? fwd_gates(f, Wg, bg) : fwd_candi(f, Wc, bc, h_out);
 }
 
 // reverse of the feature-side recurrence Y_k = 2 A^T Y_{k-1} - Y_{k-2} (Y_1 = A^T Y_0) for one operand:

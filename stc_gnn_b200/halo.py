@@ -1,0 +1,245 @@
+"""Spatial row-partition of a constant CSR support with per-hop halo exchange (BASELINE config 4).
+
+The spatial mode product `Y[b,m,:] = sum_n Gs[n,m] X[b,n,:]` (`framework/STC_GNN.py:37`) is independent per
+output node given the features of that node's in-neighbours.  Nodes are split in `world` contiguous blocks
+(callers order nodes so that blocks are spatially compact, e.g. Morton / strip order); rank r owns block r of
+every [B, N, C, L] tensor.  One Chebyshev hop = exchange the boundary-node slabs (`halo` rows of width B*C*L)
+with the ranks that own them, then apply the local operator whose columns are renumbered into
+`[local nodes | halo nodes]`.  The categorical mix and the gate contraction are node-local and never communicate.
+The adjoint (backward: `dX[b,n,:] = sum_m Gs[n,m] dY[b,m,:]`) is the same scheme on the un-transposed graph and
+has its own (generally different) halo set.
+
+Everything here is host logic + `torch.distributed` plumbing (NCCL all-to-all over NVSwitch on the GPU box, gloo in
+the CPU tests); the arithmetic is `stc_support_apply` of libstc_b200.so.  There is no CPU arithmetic path: on
+non-CUDA tensors `apply` requires the caller to inject `apply_fn` (the tests inject a CPU checker).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .dp import shard_bounds
+
+
+@dataclass
+class HaloPlan:
+    """Exchange + local operator of ONE direction for ONE rank.
+
+    Operator rows are this rank's output nodes (local numbering 0..nloc-1); its columns index the extended input
+    `[local nodes (nloc) | halo nodes (nhalo)]`, halo nodes ordered by owner rank, then by global id.
+    """
+    rank: int
+    world: int
+    start: int                      # first global node of this rank's block
+    nloc: int
+    nhalo: int
+    send_idx: List[torch.Tensor]    # per peer: LOCAL indices of the rows this rank sends (sorted by global id)
+    recv_counts: List[int]          # per peer: rows received
+    halo_global: torch.Tensor       # [nhalo] global ids of the halo nodes, in extended order
+    op_row: torch.Tensor            # COO of the local operator: output node (local)
+    op_col: torch.Tensor            #                            input node (extended numbering)
+    op_val: torch.Tensor
+
+    @property
+    def next(self) -> int:
+        return self.nloc + self.nhalo
+
+    @property
+    def send_counts(self) -> List[int]:
+        return [int(s.numel()) for s in self.send_idx]
+
+
+def _csr_to_coo(rowptr: torch.Tensor, col: torch.Tensor):
+    rowptr = rowptr.long().cpu()
+    counts = rowptr[1:] - rowptr[:-1]
+    row = torch.repeat_interleave(torch.arange(rowptr.numel() - 1), counts)
+    return row, col.long().cpu()
+
+
+def build_plan(out_idx: torch.Tensor, in_idx: torch.Tensor, vals: torch.Tensor, num_nodes: int, rank: int,
+               world: int) -> HaloPlan:
+    """Plan for the operator `Y[out] += val * X[in]` given as global COO triplets (host tensors).
+
+    Deterministic and communication-free: every rank derives what each peer needs from the replicated graph.
+    """
+    out_idx, in_idx, vals = out_idx.long().cpu(), in_idx.long().cpu(), vals.float().cpu()
+    bounds = [shard_bounds(num_nodes, p, world) for p in range(world)]
+    starts = torch.tensor([b[0] for b in bounds] + [num_nodes])
+    owner_of = lambda idx: torch.bucketize(idx, starts[1:], right=True)   # block index of each global node
+    out_owner, in_owner = owner_of(out_idx), owner_of(in_idx)
+
+    def halo_of(p: int) -> torch.Tensor:   # sorted global ids rank p needs from other ranks
+        need = in_idx[(out_owner == p) & (in_owner != p)]
+        return torch.unique(need)          # sorted ascending => grouped by owner (blocks are contiguous)
+
+    s, e = bounds[rank]
+    my_halo = halo_of(rank)
+    my_halo_owner = owner_of(my_halo)
+    recv_counts = [int((my_halo_owner == p).sum()) for p in range(world)]
+    send_idx = []
+    for p in range(world):
+        if p == rank:
+            send_idx.append(torch.empty(0, dtype=torch.long))
+            continue
+        hp = halo_of(p)
+        send_idx.append(hp[(hp >= s) & (hp < e)] - s)
+    mine = out_owner == rank
+    r_loc = out_idx[mine] - s
+    c_glob = in_idx[mine]
+    c_local = (c_glob >= s) & (c_glob < e)
+    pos = torch.searchsorted(my_halo, c_glob.clamp(min=0))      # extended slot of halo columns
+    c_ext = torch.where(c_local, c_glob - s, (e - s) + pos)
+    return HaloPlan(rank=rank, world=world, start=s, nloc=e - s, nhalo=int(my_halo.numel()), send_idx=send_idx,
+                    recv_counts=recv_counts, halo_global=my_halo, op_row=r_loc, op_col=c_ext, op_val=vals[mine])
+
+
+def exchange(plan: HaloPlan, X_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """[B, nloc, W] -> [B, nloc + nhalo, W]: append the halo rows received from their owners.
+
+    One all-to-all of packed rows (`[rows, B*W]`, row-major so that split sizes count rows).  With a single rank
+    (or no halo anywhere) it degenerates to a copy."""
+    B, nloc, W = X_local.shape
+    assert nloc == plan.nloc, (nloc, plan.nloc)
+    send_rows = [X_local[:, idx.to(X_local.device)].permute(1, 0, 2).reshape(-1, B * W) for idx in plan.send_idx]
+    send = torch.cat(send_rows, dim=0).contiguous() if send_rows else X_local.new_empty(0, B * W)
+    recv = X_local.new_empty(plan.nhalo, B * W)
+    if plan.world > 1:
+        dist.all_to_all_single(recv, send, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts,
+                               group=group)
+    halo = recv.view(plan.nhalo, B, W).permute(1, 0, 2)
+    return torch.cat([X_local, halo], dim=1).contiguous()
+
+
+class PartitionedSupport:
+    """A constant CSR spatial support `Gs` [N, N] row-partitioned over `world` ranks.
+
+    `rowptr, col, vals` is the GLOBAL `Gs` in CSR on the host (replicated; N = 65,536, nnz ~ 0.5 M is 6 MB).
+    `fwd` is the plan of the forward mode product (operator Gs^T: output m, input n for every Gs[n,m] != 0),
+    `bwd` the plan of its adjoint (operator Gs).
+    """
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, vals: torch.Tensor, num_nodes: int, rank: int,
+                 world: int, group: Optional[dist.ProcessGroup] = None):
+        n_idx, m_idx = _csr_to_coo(rowptr, col)      # Gs[n, m]
+        self.N, self.rank, self.world, self.group = int(num_nodes), rank, world, group
+        self.fwd = build_plan(m_idx, n_idx, vals, num_nodes, rank, world)
+        self.bwd = build_plan(n_idx, m_idx, vals, num_nodes, rank, world)
+        self.start, self.nloc = self.fwd.start, self.fwd.nloc
+        self._dev = {}
+
+    @classmethod
+    def from_dense(cls, G: torch.Tensor, rank: int, world: int, group=None) -> "PartitionedSupport":
+        s = G.detach().cpu().to_sparse_csr()
+        return cls(s.crow_indices(), s.col_indices(), s.values(), G.shape[0], rank, world, group)
+
+    def local_slice(self, X: torch.Tensor, node_dim: int = 1) -> torch.Tensor:
+        """This rank's node block of a global tensor."""
+        return X.narrow(node_dim, self.start, self.nloc)
+
+    # -- device form of the local operators (square, padded with empty rows so the square C-ABI kernel applies) --
+    def device_support(self, direction: str, device):
+        """CsrSupport G_loc with `support_apply(G_loc, X_ext, transpose=(direction == 'fwd'))[:, :nloc]` == operator."""
+        key = (direction, str(device))
+        if key not in self._dev:
+            from .support import CsrSupport
+            plan = self.fwd if direction == "fwd" else self.bwd
+            n = plan.next
+            # fwd: operator A_f[m_loc, n_ext] is applied as G_loc^T with G_loc[n_ext, m_loc]; bwd: G_loc = A_b
+            r, c = (plan.op_col, plan.op_row) if direction == "fwd" else (plan.op_row, plan.op_col)
+            g = torch.sparse_coo_tensor(torch.stack([r, c]), plan.op_val, size=(n, n)).coalesce().to_sparse_csr()
+            self._dev[key] = CsrSupport(g.crow_indices().to(device), g.col_indices().to(device),
+                                        g.values().to(device), n)
+        return self._dev[key]
+
+    def apply(self, X_local: torch.Tensor, direction: str = "fwd", alpha: float = 1.0, beta: float = 0.0,
+              Z_local: Optional[torch.Tensor] = None,
+              apply_fn: Optional[Callable[[HaloPlan, torch.Tensor], torch.Tensor]] = None) -> torch.Tensor:
+        """One hop on this rank's block: `alpha * A X + beta * Z`, A = Gs^T ('fwd') or Gs ('bwd').
+
+        X_local, Z_local: [B, nloc, ...feature axes]; returns the same shape.  `apply_fn(plan, X_ext) -> [B, nloc, W]`
+        replaces the CUDA kernel (tests inject a CPU checker; there is no built-in CPU arithmetic)."""
+        plan = self.fwd if direction == "fwd" else self.bwd
+        shape = X_local.shape
+        B = shape[0]
+        X3 = X_local.reshape(B, plan.nloc, -1)
+        X_ext = exchange(plan, X3, self.group)
+        if apply_fn is not None:
+            Y = apply_fn(plan, X_ext)
+            Y = alpha * Y + (beta * Z_local.reshape(B, plan.nloc, -1) if beta != 0.0 else 0.0)
+            return Y.reshape(shape)
+        if not X_local.is_cuda:
+            raise RuntimeError("PartitionedSupport.apply needs CUDA tensors (there is no CPU path)")
+        from .support import support_apply
+        Z_ext = None
+        if beta != 0.0:
+            Z3 = Z_local.reshape(B, plan.nloc, -1)
+            Z_ext = torch.cat([Z3, Z3.new_zeros(B, plan.nhalo, Z3.shape[-1])], dim=1)
+        Y_ext = support_apply(self.device_support(direction, X_local.device), X_ext, transpose=(direction == "fwd"),
+                              alpha=alpha, beta=beta, Z=Z_ext)
+        return Y_ext[:, :plan.nloc].reshape(shape)
+
+    def spatial_terms(self, X_local: torch.Tensor, Ks: int, apply_fn=None) -> List[torch.Tensor]:
+        """Feature-side Chebyshev terms Y_0..Y_{Ks-1} of this rank's block (Y_1 = Gs^T Y_0, Y_k = 2 Gs^T Y_{k-1} - Y_{k-2};
+        `framework/STC_GNN.py:24-29` applied on the feature side): Ks-1 hops, one halo exchange each."""
+        terms = [X_local]
+        for k in range(1, Ks):
+            if k == 1:
+                terms.append(self.apply(terms[0], "fwd", apply_fn=apply_fn))
+            else:
+                terms.append(self.apply(terms[k - 1], "fwd", alpha=2.0, beta=-1.0, Z_local=terms[k - 2], apply_fn=apply_fn))
+        return terms
+
+
+def partitioned_cell_forward(ps: PartitionedSupport, Gc: torch.Tensor, Xt: torch.Tensor, Ht_1: torch.Tensor,
+                             Wg: torch.Tensor, bg: Optional[torch.Tensor], Wc: torch.Tensor,
+                             bc: Optional[torch.Tensor], Ks: int, Kc: int, activation=None) -> torch.Tensor:
+    """`STC_Cell.forward` (`framework/STC_GNN.py:65-79`) on this rank's node block of a row-partitioned graph.
+
+    Xt [B, nloc, C, Din], Ht_1 [B, nloc, C, h] are the local blocks; returns the local block of H'.  The spatial
+    hops run here (halo exchange + `stc_support_apply`), the two node-local stages are `stc_cell_fwd_stage`
+    (include/stc_b200.h).  Forward only (inference / roll-out): gradients through the partitioned path are not
+    implemented yet, so inputs that require grad are rejected rather than silently detached.
+    """
+    from . import _lib
+    from .cell import _activation_code, _ptr
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (Gc, Xt, Ht_1, Wg, bg, Wc, bc)):
+        raise RuntimeError("partitioned_cell_forward is forward-only: call it under torch.no_grad()")
+    for name, t in (("Gc", Gc), ("Xt", Xt), ("Ht_1", Ht_1), ("gates.W", Wg), ("candi.W", Wc)):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"partitioned cell: {name} must be a float32 CUDA tensor (there is no CPU path)")
+    lib = _lib.load()
+    B, n, C, Din = Xt.shape
+    h = Ht_1.shape[-1]
+    if n != ps.nloc or Ht_1.shape != (B, n, C, h):
+        raise RuntimeError(f"local block has {n} nodes, the partition owns {ps.nloc}; Ht_1 {tuple(Ht_1.shape)}")
+    Xt, Ht_1, Gc = Xt.contiguous(), Ht_1.contiguous(), Gc.contiguous()
+    Wg, Wc = Wg.contiguous(), Wc.contiguous()
+    dims = _lib.StcDims(B, n, C, Din, h, Ks, Kc, _activation_code(activation), 1 if bg is not None else 0)
+    lay = _lib.saved_layout(dims)
+    saved = torch.empty(lib.stc_cell_saved_bytes(dims) // 4, dtype=torch.float32, device=Xt.device)
+    Hn = torch.empty_like(Ht_1)
+    R = B * n * C
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def region(name, k, width):
+        o = lay[name] + k * R * width
+        return saved[o:o + R * width].view(B, n, C, width)
+
+    def stage(which):
+        _lib.check(lib.stc_cell_fwd_stage(dims, which, Gc.data_ptr(), Xt.data_ptr(), n * C * Din, Ht_1.data_ptr(),
+                                          Wg.data_ptr(), _ptr(bg), Wc.data_ptr(), _ptr(bc), Hn.data_ptr(),
+                                          saved.data_ptr(), saved.numel() * 4, stream), "stc_cell_fwd_stage")
+        _lib.note_launches()
+
+    for k, y in enumerate(ps.spatial_terms(Xt, Ks)[1:]):
+        region("Yx", k, Din).copy_(y)
+    for k, y in enumerate(ps.spatial_terms(Ht_1, Ks)[1:]):
+        region("Yh", k, h).copy_(y)
+    stage(_lib.STAGE_GATES)
+    for k, y in enumerate(ps.spatial_terms(region("Yr", 0, h), Ks)[1:]):
+        region("Yr", k + 1, h).copy_(y)
+    stage(_lib.STAGE_CANDI)
+    return Hn

@@ -1,0 +1,87 @@
+"""GPU tests of the row-partitioned path: staged cell forward (C ABI) + halo hops through stc_support_apply.
+
+World size 1 runs on any GPU box; the 2-rank NCCL test needs two visible GPUs (`gpurun --gpus 2`) and is skipped otherwise.
+"""
+import os
+import socket
+import traceback
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import stc_oracle as O
+from tests.helpers import random_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _cell_block(rank, world, device, cfg, seed):
+    import stc_gnn_b200 as S
+    t = random_case(cfg["B"], cfg["N"], cfg["C"], cfg["Din"], cfg["h"], cfg["Ks"], cfg["Kc"], seed=seed, sparse_frac=0.85)
+    want = O.stc_cell(t["Gs"], t["Gc"], t["Xt"], t["H"], t["Wg"], t["bg"], t["Wc"], t["bc"], cfg["Ks"], cfg["Kc"])
+    ps = S.halo.PartitionedSupport.from_dense(t["Gs"], rank, world)
+    f = lambda x: x.float().to(device)
+    with torch.no_grad():
+        got = S.halo.partitioned_cell_forward(ps, f(t["Gc"]), f(ps.local_slice(t["Xt"])), f(ps.local_slice(t["H"])),
+                                              f(t["Wg"]), f(t["bg"]), f(t["Wc"]), f(t["bc"]), cfg["Ks"], cfg["Kc"])
+        # one adjoint hop as well (backward direction of the exchange)
+        dY = torch.randn(cfg["B"], cfg["N"], cfg["C"], cfg["h"], generator=torch.Generator().manual_seed(seed + 1)).double()
+        got_b = ps.apply(f(ps.local_slice(dY)), "bwd")
+    torch.cuda.synchronize()
+    O.assert_close(got.cpu(), ps.local_slice(want), f"partitioned cell forward (rank {rank}/{world})")
+    O.assert_close(got_b.cpu(), ps.local_slice(torch.einsum("nm,bmcl->bncl", t["Gs"], dY)), f"adjoint hop (rank {rank})")
+    return ps
+
+
+@pytest.mark.parametrize("cfg", [dict(B=2, N=96, C=5, Din=16, h=16, Ks=2, Kc=2), dict(B=3, N=70, C=4, Din=3, h=8, Ks=4, Kc=2)])
+def test_staged_cell_forward_single_rank(cfg):
+    ps = _cell_block(0, 1, torch.device("cuda:0"), cfg, seed=21)
+    assert ps.fwd.nhalo == 0
+    import stc_gnn_b200 as S
+    t = random_case(2, 16, 2, 2, 8, 2, 2, seed=1)
+    ps2 = S.halo.PartitionedSupport.from_dense(t["Gs"], 0, 1)
+    f = lambda x: x.float().cuda().requires_grad_(True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        S.halo.partitioned_cell_forward(ps2, f(t["Gc"]), f(t["Xt"]), f(t["H"]), f(t["Wg"]), f(t["bg"]), f(t["Wc"]),
+                                        f(t["bc"]), 2, 2)
+
+
+def _nccl_worker(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        for cfg in (dict(B=2, N=101, C=5, Din=16, h=16, Ks=3, Kc=2), dict(B=1, N=64, C=8, Din=1, h=8, Ks=4, Kc=2)):
+            ps = _cell_block(rank, world, dev, cfg, seed=33)
+            assert ps.fwd.nhalo > 0
+        # DP bucket over NCCL: sum of rank-dependent gradients
+        import stc_gnn_b200 as S
+        p = torch.nn.Parameter(torch.ones(1000, device=dev))
+        p.grad = torch.full_like(p, float(rank + 1))
+        S.dp.GradBucket([p]).allreduce()
+        assert torch.allclose(p.grad, torch.full_like(p, float(sum(range(1, world + 1)))))
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, None))
+    except Exception:  # pragma: no cover
+        q.put((rank, traceback.format_exc()))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_halo_cell_forward_two_ranks_nccl():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    errs = [f"rank {r}:\n{e}" for r, e in results if e]
+    assert not errs, "\n".join(errs)

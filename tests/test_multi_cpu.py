@@ -1,0 +1,192 @@
+"""World-size-2 `gloo` tests of the multi-GPU host logic (no GPU needed):
+
+* dp.py    -- flat-bucket gradient all-reduce: DP gradients == single-process gradients of the concatenated batch
+* halo.py  -- partition plans + halo exchange: partitioned spatial terms / cell == the unpartitioned oracle
+
+The arithmetic in these tests is the oracle's (tests may use it); the product arithmetic is CUDA-only.
+"""
+import os
+import socket
+import traceback
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import stc_oracle as O
+from stc_gnn_b200 import dp, halo
+from tests.helpers import random_case
+
+WORLD = 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, fn, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        torch.set_num_threads(1)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        fn(rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, None))
+    except Exception:  # pragma: no cover - reported by the parent
+        q.put((rank, traceback.format_exc()))
+
+
+def run_ranks(fn, world=WORLD):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fn, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    errs = [f"rank {r}:\n{e}" for r, e in results if e]
+    assert not errs, "\n".join(errs)
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers (module level: spawn pickles the worker functions)
+# ------------------------------------------------------------------------------------------------
+def _sparse_graph(N, seed, keep=0.08):
+    g = torch.Generator().manual_seed(seed)
+    G = torch.rand(N, N, generator=g) * (torch.rand(N, N, generator=g) < keep)
+    idx = torch.arange(N)
+    G[idx, (idx + 1) % N] = 0.5          # every node has an out- and an in-neighbour, some across the block boundary
+    G[(idx + 7) % N, idx] += 0.25
+    return (G / G.sum(0, keepdim=True).clamp(min=1e-3)).double()
+
+
+def _oracle_apply(plan, X_ext):
+    A = torch.sparse_coo_tensor(torch.stack([plan.op_row, plan.op_col]), plan.op_val.to(X_ext.dtype),
+                                size=(plan.nloc, plan.next)).coalesce()
+    B, n, W = X_ext.shape
+    return torch.sparse.mm(A, X_ext.permute(1, 0, 2).reshape(n, B * W)).view(plan.nloc, B, W).permute(1, 0, 2)
+
+
+def _dp_case(rank, world):
+    cfg = dict(B=6, N=12, C=3, Din=2, h=4, Ks=3, Kc=2)
+    t = random_case(cfg["B"], cfg["N"], cfg["C"], cfg["Din"], cfg["h"], cfg["Ks"], cfg["Kc"], seed=3)
+    names = ["Gs", "Gc", "Wg", "bg", "Wc", "bc"]
+
+    def grads(Xt, H, dHn):
+        leaves = {k: t[k].clone().requires_grad_(True) for k in names}
+        Hn = O.stc_cell(leaves["Gs"], leaves["Gc"], Xt, H, leaves["Wg"], leaves["bg"], leaves["Wc"], leaves["bc"],
+                        cfg["Ks"], cfg["Kc"])
+        Hn.backward(dHn)
+        return leaves
+
+    full = grads(t["Xt"], t["H"], t["dHn"])
+    s, e = dp.shard_bounds(cfg["B"], rank, world)
+    assert (s, e) == (rank * 3, rank * 3 + 3)
+    mine = grads(dp.shard_batch(t["Xt"], rank, world), dp.shard_batch(t["H"], rank, world),
+                 dp.shard_batch(t["dHn"], rank, world))
+    leaves32 = []
+    for k in names:                                 # the bucket is fp32 (what the GPU path reduces)
+        p = mine[k].detach().float().requires_grad_(True)
+        p.grad = mine[k].grad.float()
+        leaves32.append(p)
+    leaves32[3].grad = None                         # an absent gradient must count as zeros on this rank only
+    if rank == 0:
+        leaves32[3].grad = mine["bg"].grad.float() + (grads(dp.shard_batch(t["Xt"], 1, world),
+                                                            dp.shard_batch(t["H"], 1, world),
+                                                            dp.shard_batch(t["dHn"], 1, world))["bg"].grad.float())
+    bucket = dp.GradBucket(leaves32)
+    assert bucket.numel == sum(p.numel() for p in leaves32)
+    bucket.allreduce()
+    for k, p in zip(names, leaves32):
+        O.assert_close(p.grad, full[k].grad, f"DP-reduced d{k} (rank {rank})", rtol=1e-4, atol_scale=1e-5)
+
+
+def _halo_case(rank, world):
+    N, B, C, L, Ks = 37, 3, 2, 5, 4                 # odd N: uneven blocks
+    G = _sparse_graph(N, seed=11)
+    ps = halo.PartitionedSupport.from_dense(G, rank, world)
+    assert ps.nloc == (19 if rank == 0 else 18) and ps.fwd.nhalo > 0 and ps.bwd.nhalo > 0
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(B, N, C, L, generator=g, dtype=torch.float64)
+    # forward terms: Ks-1 hops with a halo exchange each
+    want = O.spatial_terms(X, G, Ks)
+    got = ps.spatial_terms(ps.local_slice(X), Ks, apply_fn=_oracle_apply)
+    for k in range(Ks):
+        O.assert_close(got[k], ps.local_slice(want[k]), f"partitioned spatial term {k} (rank {rank})", 1e-9, 1e-10)
+    # adjoint hop on the un-transposed graph
+    dY = torch.randn(B, N, C, L, generator=g, dtype=torch.float64)
+    want_b = torch.einsum("nm,bmcl->bncl", G, dY)
+    got_b = ps.apply(ps.local_slice(dY), "bwd", apply_fn=_oracle_apply)
+    O.assert_close(got_b, ps.local_slice(want_b), f"partitioned adjoint hop (rank {rank})", 1e-9, 1e-10)
+    # exchange bookkeeping: what I receive is exactly the owner's rows
+    ext = halo.exchange(ps.fwd, ps.local_slice(X).reshape(B, ps.nloc, -1))
+    torch.testing.assert_close(ext[:, ps.nloc:], X.reshape(B, N, -1)[:, ps.fwd.halo_global])
+
+
+def _halo_cell_case(rank, world):
+    """Whole cell on a row partition: spatial terms via halo hops, everything else node-local."""
+    cfg = dict(B=2, N=26, C=3, Din=2, h=4, Ks=3, Kc=2)
+    t = random_case(cfg["B"], cfg["N"], cfg["C"], cfg["Din"], cfg["h"], cfg["Ks"], cfg["Kc"], seed=9, sparse_frac=0.8)
+    ps = halo.PartitionedSupport.from_dense(t["Gs"], rank, world)
+    want = O.stc_cell(t["Gs"], t["Gc"], t["Xt"], t["H"], t["Wg"], t["bg"], t["Wc"], t["bc"], cfg["Ks"], cfg["Kc"])
+    got = O.stc_cell(None, t["Gc"], ps.local_slice(t["Xt"]), ps.local_slice(t["H"]), t["Wg"], t["bg"], t["Wc"], t["bc"],
+                     cfg["Ks"], cfg["Kc"], spatial_terms_fn=lambda X: ps.spatial_terms(X, cfg["Ks"], apply_fn=_oracle_apply))
+    O.assert_close(got, ps.local_slice(want), f"partitioned cell (rank {rank})", 1e-9, 1e-10)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_shard_bounds_cover_the_batch():
+    for total in (0, 1, 7, 32, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [dp.shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+    with pytest.raises(ValueError):
+        dp.shard_bounds(4, 2, 2)
+
+
+def test_plan_is_consistent_across_ranks():
+    """What rank p sends to q is exactly what q expects from p (no communication needed to agree)."""
+    G = _sparse_graph(41, seed=2)
+    for world in (2, 3, 4):
+        plans = [halo.PartitionedSupport.from_dense(G, r, world) for r in range(world)]
+        for direction in ("fwd", "bwd"):
+            for p in range(world):
+                for q in range(world):
+                    a = getattr(plans[p], direction)
+                    b = getattr(plans[q], direction)
+                    assert a.send_counts[q] == b.recv_counts[p]
+                    sent_global = a.send_idx[q] + a.start
+                    off = sum(b.recv_counts[:p])
+                    assert torch.equal(sent_global, b.halo_global[off:off + b.recv_counts[p]])
+        assert sum(pl.nloc for pl in plans) == 41
+
+
+def test_single_rank_plan_has_no_halo():
+    G = _sparse_graph(16, seed=4)
+    ps = halo.PartitionedSupport.from_dense(G, 0, 1)
+    assert ps.nloc == 16 and ps.fwd.nhalo == 0 and ps.bwd.nhalo == 0
+    X = torch.randn(2, 16, 3, dtype=torch.float64)
+    got = ps.apply(X, "fwd", apply_fn=_oracle_apply)
+    O.assert_close(got, torch.einsum("nm,bnw->bmw", G, X), "1-rank partition", 1e-9, 1e-10)
+    with pytest.raises(RuntimeError):
+        ps.apply(X.float(), "fwd")          # CPU tensors without an injected apply_fn: no CPU path
+
+
+def test_dp_bucket_allreduce_matches_concatenated_batch():
+    run_ranks(_dp_case)
+
+
+def test_halo_partitioned_terms_match_unpartitioned():
+    run_ranks(_halo_case)
+
+
+def test_halo_partitioned_cell_matches_unpartitioned():
+    run_ranks(_halo_cell_case)

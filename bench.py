@@ -190,6 +190,8 @@ def workload_config(B, n_gpus, reference=False):
         "T": SF["T"], "horizon": SF["horizon"], "batch_per_gpu": B, "global_batch": B * (1 if reference else n_gpus),
         "parallelism": "cpu" if reference else f"dp{n_gpus}",
         "l2": "inputs+activations exceed L2 (no flush needed)" if B >= 1024 else "working set may fit L2",
+        "bytes_model": "per-kernel compulsory bytes of the multi-kernel pipeline (DESIGN.md section 4); the fused-cell floor "
+                       "of SURVEY 8d is 9.94 MB per sample fwd+bwd",
     }
 
 
@@ -220,16 +222,12 @@ def run_b200(args):
     Gs = Gs_h.to(dev).requires_grad_(True)
     Gc = Gc_h.to(dev).requires_grad_(True)
     X_res, y_res = Xh.to(dev), yh.to(dev)
-    grads_flat = None
+    # data-parallel: one flat fp32 bucket (cell parameters + dGs + dGc), one NCCL all-reduce per step (dp.py)
+    bucket = S.dp.GradBucket(params + [Gs, Gc]) if world > 1 else None
 
     def allreduce_grads():
-        nonlocal grads_flat
-        if world == 1:
-            return
-        gl = [p.grad for p in params] + [Gs.grad, Gc.grad]
-        flat = torch.cat([g.reshape(-1) for g in gl])
-        dist.all_reduce(flat)
-        grads_flat = flat
+        if bucket is not None:
+            bucket.allreduce()
 
     def step(X, y):
         for p in params:
@@ -307,8 +305,9 @@ def run_b200(args):
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "avg_launch_us": 1e3 * kms / kn, "alg_bytes_per_launch": kbytes / kn,
                     "share_of_kernel_time": kms / tot_ms,
-                    "note": "FFMA general path: this kernel is FP32-pipe bound, not HBM bound; frac is reported "
-                            "against the HBM roofline the metric names"}
+                    "note": "achieved = this kernel's own compulsory bytes (inputs it must read + outputs it must write, "
+                            "formula beside its launcher) / its mean launch time; 3xTF32 tcgen05 kernel, latency- and "
+                            "issue-bound rather than HBM-bound at this size (see DESIGN.md section 4)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

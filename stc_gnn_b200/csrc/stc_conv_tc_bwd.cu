@@ -25,6 +25,7 @@ struct TcDxPlan {
   int tmem_cols, ntiles;
   int DP;         // row stride of the plain Ds tile (floats)
   int PW;         // (Kc-1) * Hout: width of the saved partial-output tile
+  int x_vec;      // x-part adjoints can be written (and accumulated) with 16-byte accesses
   uint32_t off_a, off_b, off_ds, off_dh, off_ps, off_q, off_acc, off_bar, smem_bytes;
 };
 
@@ -282,9 +283,20 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
           float* dbase = (k == 0 ? a.dYx0 : a.dYx + (size_t)(k - 1) * R * Din);
           if (dbase == nullptr) continue;
           float* dst = dbase + gr * Din + xi;
+          if (p.x_vec && xi + 8 <= Din) {   // both 16-byte halves in flight at once (the accumulate is a read-modify-write)
+            float4 o0 = make_float4(v[0], v[1], v[2], v[3]), o1 = make_float4(v[4], v[5], v[6], v[7]);
+            if (a.accum_x) {
+              const float4 p0 = reinterpret_cast<const float4*>(dst)[0], p1 = reinterpret_cast<const float4*>(dst)[1];
+              o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+              o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+            }
+            reinterpret_cast<float4*>(dst)[0] = o0;
+            reinterpret_cast<float4*>(dst)[1] = o1;
+          } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (xi + i < Din) dst[i] = a.accum_x ? dst[i] + v[i] : v[i];
+            for (int i = 0; i < 8; ++i)
+              if (xi + i < Din) dst[i] = a.accum_x ? dst[i] + v[i] : v[i];
+          }
         }
       }
     }
@@ -321,6 +333,7 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
   while (p.tmem_cols < (p.KA + 1) * p.Npad) p.tmem_cols *= 2;
   p.DP = a.Hout + 4;
   p.PW = (a.Kc - 1) * a.Hout;
+  p.x_vec = (a.Din % 4 == 0) && aligned16b(a.dYx0) && aligned16b(a.dYx);
   const long long total_nodes = (long long)a.B * a.N;
   p.ntiles = ceil_div(total_nodes, p.npt);
   const size_t atomB = (size_t)p.Npad * ATOM_ROW_BYTES;

@@ -54,6 +54,28 @@ struct ScopedKernelTimer {  // declare right before a launch; the destructor rec
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// exact division of a 32-bit unsigned by a launch-invariant divisor: multiply-high + one correction step
+// (M = floor((2^(32+s) - 1) / d), s = floor(log2 d): the estimate is q or q - 1 for every n < 2^32)
+struct FastDiv {
+  uint32_t d, M, s;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d ? d : 1;
+  f.s = 0;
+  while ((2u << f.s) <= f.d && f.s < 31) ++f.s;
+  f.M = (uint32_t)(((((uint64_t)1) << (32 + f.s)) - 1) / f.d);
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv f) {
+  if (f.d == 1) return n;
+  uint32_t q = __umulhi(n, f.M) >> f.s;
+  if (n - q * f.d >= f.d) ++q;
+  return q;
+}
+#endif
+
 int device_sm_count();   // cached, current device
 int check_arch();        // STC_OK when the current device is compute capability 10.x
 

@@ -121,6 +121,10 @@ __device__ inline void unmix_add_tile(const float* src, float* dst, const float*
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU.EX2 / MUFU.RCP forms for the tensor-core epilogues (7 instructions instead of ~45): relative error ~1e-6 for
+// the sigmoid, absolute error ~2e-7 for tanh -- two orders below the parity tolerance (rtol 1e-4 + 1e-5 mean|ref|)
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_fast(float x) { return __fdividef(2.f, 1.f + __expf(-2.f * x)) - 1.f; }
 
 template <typename K>
 static inline int set_smem(K kernel, size_t smem) {

@@ -279,7 +279,7 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
       }
       if (a.phase == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = sigmoidf_acc(v[i]);
+        for (int i = 0; i < 8; ++i) v[i] = sigmoidf_fast(v[i]);
         if (c0 < h) {
           float4* dst = reinterpret_cast<float4*>(a.u + gr * h + c0);
           dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -304,7 +304,7 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
         *reinterpret_cast<float4*>(hp + 4) = *reinterpret_cast<const float4*>(a.Hprev + o + 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          cc[i] = tanhf(v[i]);
+          cc[i] = tanhf_fast(v[i]);
           hn[i] = fmaf(uu[i], cc[i] - hp[i], hp[i]);
         }
         float4* dc = reinterpret_cast<float4*>(a.c + o);

@@ -101,7 +101,8 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   const int lane_base = (warp & 3) * 32, half = warp >> 2;
   const int erow = lane_base + lane;
   const uint32_t tl = tmem_base + ((uint32_t)lane_base << 16);
-  float db_acc = 0.f;  // thread j < Hout owns bias-gradient column j
+  float db_acc = 0.f;  // thread (group g, column j) owns rows g, g + groups, ... of bias-gradient column j
+  const int db_groups = CV_THREADS / Hout, db_col = tid % Hout, db_grp = tid / Hout;
   uint32_t mma_phase = 0, load_phase = 0;
   bool mma_pending = false;
 
@@ -166,9 +167,9 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       }
     }
     __syncthreads();
-    if (a.dbias && tid < Hout) {
+    if (a.dbias && tid < db_groups * Hout) {   // every thread sums a strided slice of rows of its column
       float s = 0.f;
-      for (int row = 0; row < rows_valid; ++row) s += Dsm[row * DP + tid];
+      for (int row = db_grp; row < rows_valid; row += db_groups) s += Dsm[row * DP + db_col];
       db_acc += s;
     }
     // ---- 2. DD atoms + MMAs ----
@@ -303,7 +304,7 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
     fence_before_sync();
     __syncthreads();  // Dsm / Dh / Psm are rewritten by the next tile's prologue
   }
-  if (a.dbias && tid < Hout) atomicAdd(&a.dbias[tid], db_acc);
+  if (a.dbias && tid < db_groups * Hout) atomicAdd(&a.dbias[db_col], db_acc);
   __syncthreads();
   if (want_dQ)
     for (int i = tid; i < (a.Kc - 1) * C * C; i += CV_THREADS) atomicAdd(&a.dQ[C * C + i], dQacc[i]);

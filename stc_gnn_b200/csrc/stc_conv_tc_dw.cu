@@ -27,6 +27,8 @@ struct TcDwPlan {
   int tmem_cols;
   long long ntiles;
   int x_vec;      // x-part rows can be read with float4 loads
+  int idx32;      // every row index fits 32 bits: divisions by C and N use the multiply-high form
+  FastDiv divC, divN;
   uint32_t off_a, off_b, off_bar, smem_bytes;
 };
 
@@ -103,10 +105,16 @@ tc_conv_bwd_dw_kernel(const ConvArgs a, const TcDwPlan p) {
     if (akind == 0) return __ldg(reinterpret_cast<const float4*>(asrc + gr * astride));
     const float* s;
     if (akind == 2) {  // Xt[b][n][cat][xi..]: the batch axis carries a stride (STC_GNN.py:111 hands in a view)
-      const long long g = gr / C;
-      const int cat = (int)(gr - g * C);
-      const long long b = g / a.N;
-      s = asrc + b * a.x0_bs + ((g - b * a.N) * C + cat) * (long long)Din + axi;
+      if (p.idx32) {
+        const uint32_t g = fast_div((uint32_t)gr, p.divC), b = fast_div(g, p.divN);
+        // (g - b N) C + cat = gr - b N C
+        s = asrc + (long long)b * a.x0_bs + (long long)((uint32_t)gr - b * (uint32_t)(a.N * C)) * Din + axi;
+      } else {
+        const long long g = gr / C;
+        const int cat = (int)(gr - g * C);
+        const long long b = g / a.N;
+        s = asrc + b * a.x0_bs + ((g - b * a.N) * C + cat) * (long long)Din + axi;
+      }
       if (p.x_vec) return __ldg(reinterpret_cast<const float4*>(s));
     } else {
       s = asrc + gr * astride;
@@ -255,6 +263,9 @@ int try_launch_conv_bwd_dw_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
   const long long R = (long long)a.B * a.N * a.C;
   p.ntiles = (R + DW_TR - 1) / DW_TR;
   p.x_vec = (a.Din % 4 == 0) && (a.x0_bs % 4 == 0) && aligned16d(a.x0) && aligned16d(a.yx);
+  p.idx32 = R < (1LL << 31) ? 1 : 0;
+  p.divC = make_fastdiv((uint32_t)a.C);
+  p.divN = make_fastdiv((uint32_t)a.N);
   size_t o = 0;
   p.off_a = (uint32_t)o; o += 2 * (size_t)p.mblk * DW_TR * ATOM_ROW_BYTES;
   p.off_b = (uint32_t)o; o += 2 * (size_t)p.nblk * DW_TR * ATOM_ROW_BYTES;

@@ -306,9 +306,7 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
 #pragma unroll
   for (int i = 0; i < 4; ++i) soff[i] = atom_chunk_offset(r0 + 32 * i, q);
   float4 ra[4], rb[4];
-  auto fetch = [&](long long seq) {   // seq = local atom index -> (sample, atom within sample)
-    const long long s = seq / p.atoms_per_sample;
-    const int at = (int)(seq - s * p.atoms_per_sample);
+  auto fetch = [&](int s, int at) {   // s-th sample of this CTA, atom `at` within the sample
     const long long b = blockIdx.x + s * (long long)gridDim.x;
     const int j = at * ATOM_K + q * 4;
     const bool ok = j < W;               // W % 4 == 0
@@ -384,7 +382,8 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
     since_drain = 0;
   };
 
-  if (natoms > 0) fetch(0);
+  if (natoms > 0) fetch(0, 0);
+  int cur_s = 0, at = 0;               // (sample, atom) of `seq`, advanced without divisions
   for (long long seq = 0; seq < natoms; ++seq) {
     const int buf = (int)(seq & 1);
     if (pend[buf]) {   // the MMAs that read this buffer two atoms ago
@@ -395,7 +394,6 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
     stage(buf);
     fence_async_smem();
     __syncthreads();
-    const int at = (int)(seq % p.atoms_per_sample);
     const int kleft = W - at * ATOM_K;
     const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
     const int mi = since_drain % 3;
@@ -411,7 +409,11 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
     acc_small = true;
     pend[buf] = true;
     ++since_drain;
-    if (seq + 1 < natoms) fetch(seq + 1);
+    if (++at == p.atoms_per_sample) {
+      at = 0;
+      ++cur_s;
+    }
+    if (seq + 1 < natoms) fetch(cur_s, at);
     if (since_drain >= TO_DRAIN) drain();
   }
   if (since_drain > 0) drain();

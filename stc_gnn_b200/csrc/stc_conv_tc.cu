@@ -41,7 +41,7 @@ struct TcFwdPlan {
   int ntiles;
   int x_bulk;     // x-part can be staged with bulk copies (16-byte aligned rows)
   int PS;         // row stride (floats) of the epilogue exchange buffer
-  uint32_t off_a, off_b, off_sh, off_sx, off_q, off_bar, smem_bytes;
+  uint32_t off_a, off_b, off_sh, off_sx, off_se, off_q, off_bar, smem_bytes;
 };
 
 // thread 0: stage every spatial term of tile `tile` with bulk copies that complete on `bar`
@@ -105,14 +105,17 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   float* stage_h = reinterpret_cast<float*>(smem + p.off_sh);   // [Ks][128][h]
   float* stage_x = reinterpret_cast<float*>(smem + p.off_sx);   // [Ks][128][Din]
   float* Qs = reinterpret_cast<float*>(smem + p.off_q);         // [(Kc-1)][C][C]
+  float* stage_e = reinterpret_cast<float*>(smem + p.off_se);   // [2][128][h]: H tile, u tile (epilogue operands)
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* load_bar = mma_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 2);
+  uint64_t* epi_bar = mma_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 3);
 
   // ---- one-time setup ----
   if (tid == 0) {
     mbar_init(mma_bar, 1);
     mbar_init(load_bar, 1);
+    mbar_init(epi_bar, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -158,7 +161,7 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   const int enode = erow / C, ecat = erow - enode * C;
   const uint32_t tl = tmem_base + ((uint32_t)lane_base << 16);
 
-  uint32_t mma_phase = 0, load_phase = 0;
+  uint32_t mma_phase = 0, load_phase = 0, epi_phase = 0;
   bool mma_pending = false;
   if (tid == 0 && (int)blockIdx.x < p.ntiles) tc_issue_tile_loads(a, p, blockIdx.x, stage_h, stage_x, load_bar);
 
@@ -166,6 +169,12 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
     const long long g0 = (long long)tile * p.npt;
     const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
     const int rows_valid = nodes_valid * C;
+    if (tid == 0) {  // the epilogue's own operands (H, and u for the candidate) travel under the builds and the MMAs
+      const uint32_t eb = (uint32_t)(rows_valid * h * 4);
+      mbar_arrive_expect_tx(epi_bar, a.phase == 0 ? eb : 2 * eb);
+      bulk_g2s(stage_e, a.Hprev + g0 * C * h, eb, epi_bar);
+      if (a.phase != 0) bulk_g2s(stage_e + 128 * h, a.u + g0 * C * h, eb, epi_bar);
+    }
     mbar_wait(load_bar, load_phase);
     load_phase ^= 1u;
     if (!p.x_bulk) {  // unaligned x-part (e.g. Din = 1): plain loads, it is tiny
@@ -243,6 +252,8 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
     mma_phase ^= 1u;
     mma_pending = false;
     fence_after_sync();
+    mbar_wait(epi_bar, epi_phase);
+    epi_phase ^= 1u;
     const bool valid = erow < rows_valid;
     const long long gr = g0 * C + erow;
     for (int c0 = half * 8; c0 < Hout; c0 += 16) {
@@ -286,8 +297,8 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
           dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         } else {
           const long long o = gr * h + (c0 - h);
-          const float4 h0 = *reinterpret_cast<const float4*>(a.Hprev + o);
-          const float4 h1 = *reinterpret_cast<const float4*>(a.Hprev + o + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(stage_e + erow * h + (c0 - h));
+          const float4 h1 = *reinterpret_cast<const float4*>(stage_e + erow * h + (c0 - h) + 4);
           float4* dr = reinterpret_cast<float4*>(a.r + o);
           dr[0] = make_float4(v[0], v[1], v[2], v[3]);
           dr[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -298,10 +309,10 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
       } else {
         const long long o = gr * h + c0;
         float uu[8], hp[8], cc[8], hn[8];
-        *reinterpret_cast<float4*>(uu) = *reinterpret_cast<const float4*>(a.u + o);
-        *reinterpret_cast<float4*>(uu + 4) = *reinterpret_cast<const float4*>(a.u + o + 4);
-        *reinterpret_cast<float4*>(hp) = *reinterpret_cast<const float4*>(a.Hprev + o);
-        *reinterpret_cast<float4*>(hp + 4) = *reinterpret_cast<const float4*>(a.Hprev + o + 4);
+        *reinterpret_cast<float4*>(uu) = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + c0);
+        *reinterpret_cast<float4*>(uu + 4) = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + c0 + 4);
+        *reinterpret_cast<float4*>(hp) = *reinterpret_cast<const float4*>(stage_e + erow * h + c0);
+        *reinterpret_cast<float4*>(hp + 4) = *reinterpret_cast<const float4*>(stage_e + erow * h + c0 + 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           cc[i] = tanhf_fast(v[i]);
@@ -316,6 +327,7 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
       }
     }
     fence_before_sync();  // TMEM reads are ordered before the next tile's first (overwriting) MMA,
+    fence_async_smem();   // the epilogue's reads of its staged operands precede the next tile's bulk copies into them,
     __syncthreads();      // and the exchange buffer is free before the next tile's A build
   }
   __syncthreads();
@@ -343,7 +355,8 @@ bool conv_tc_eligible(const ConvArgs& a) {
   if (Nf > 256 || (a.Ks * KB + 1) * Nf > 512) return false;
   if ((size_t)128 * (a.Hout + 4) * sizeof(float) > 2 * 128 * ATOM_ROW_BYTES) return false;
   const size_t fwd_smem = 2 * 128 * ATOM_ROW_BYTES + 2 * (size_t)a.Ks * KB * Nf * ATOM_ROW_BYTES +
-                          (size_t)a.Ks * 128 * (a.h + a.Din) * sizeof(float) + (size_t)a.Kc * a.C * a.C * sizeof(float) + 64;
+                          (size_t)a.Ks * 128 * (a.h + a.Din) * sizeof(float) + (size_t)2 * 128 * a.h * sizeof(float) +
+                          (size_t)a.Kc * a.C * a.C * sizeof(float) + 64;
   if (fwd_smem > 200 * 1024) return false;
   // backward dx: N = Ks*KBL, K = Kc*Hout
   const int Nb = (a.Ks * KBL + 15) & ~15, KA = (a.Kc * a.Hout + ATOM_K - 1) / ATOM_K;
@@ -387,9 +400,10 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
   p.off_b = (uint32_t)o; o += 2 * (size_t)p.nacc * atomB;               // resident W atoms hi/lo
   p.off_sh = (uint32_t)o; o += (size_t)a.Ks * 128 * a.h * sizeof(float);
   p.off_sx = (uint32_t)o; o += round_up((size_t)a.Ks * 128 * a.Din * sizeof(float), 16);
+  p.off_se = (uint32_t)o; o += (size_t)2 * 128 * a.h * sizeof(float);
   p.off_q = (uint32_t)o; o += (size_t)(a.Kc > 1 ? a.Kc - 1 : 0) * a.C * a.C * sizeof(float);
   o = round_up(o, 16);
-  p.off_bar = (uint32_t)o; o += 32;
+  p.off_bar = (uint32_t)o; o += 48;
   p.smem_bytes = (uint32_t)o;
   if (p.smem_bytes > 200 * 1024) return STC_OK;  // not an SF-class shape: the FFMA path handles it
   STC_TRY(set_smem(tc_conv_fwd_kernel, p.smem_bytes));

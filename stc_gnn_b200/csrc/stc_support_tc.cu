@@ -23,12 +23,14 @@ constexpr int TS_NT = 64;                    // (b,j) columns per tile = GEMM N
 constexpr int TS_PROD_WARPS = 8, TS_EPI_WARPS = 4;
 constexpr int TS_THREADS = 32 * (1 + TS_PROD_WARPS + TS_EPI_WARPS);
 constexpr int TS_SLOTS = 8;                  // 16-byte chunks per producer thread per tile (Kp <= 128)
+constexpr int TS_MAX_STAGES = 4;             // X ring depth (as many as fit)
+constexpr int TS_ACC_COLS = 4 * TS_NT;       // 2 accumulator buffers x (main + cross-term)
 
 struct TcSupPlan {
-  int N, Kp, Mimg, W, transpose;
+  int N, Kp, W, transpose, stages;
   long long total_cols, ntiles;
   int tmem_cols;
-  uint32_t off_g, off_x, off_bar, smem_bytes, imgG, imgX;
+  uint32_t off_x, off_bar, smem_bytes, imgX;
 };
 
 __global__ void __launch_bounds__(TS_THREADS, 1)
@@ -38,73 +40,84 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, Kp = p.Kp, W = p.W;
-  uint8_t* G_hi = smem + p.off_g;               // [4 column blocks of 32 m][Kp rows][128 B]
-  uint8_t* G_lo = G_hi + p.imgG;
-  uint8_t* Xbuf = smem + p.off_x;               // [2 buffers][hi | lo][2 column blocks][Kp][128 B]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [2] producers -> MMA
-  uint64_t* empty = full + 2;                                       // [2] MMA -> producers
-  uint64_t* accfull = full + 4;                                     // [2] MMA -> epilogue
-  uint64_t* accempty = full + 6;                                    // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 8);
+  uint8_t* Xbuf = smem + p.off_x;               // [stages][hi | lo][2 column blocks][Kp][128 B]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [stages] producers -> MMA
+  uint64_t* empty = full + TS_MAX_STAGES;                           // [stages] MMA -> producers
+  uint64_t* accfull = empty + TS_MAX_STAGES;                        // [2] MMA -> epilogue
+  uint64_t* accempty = accfull + 2;                                 // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
   const uint32_t colblk = (uint32_t)Kp * ATOM_ROW_BYTES;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < TS_MAX_STAGES; ++i) {
       mbar_init(&full[i], TS_PROD_WARPS);
       mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&accfull[i], 1);
       mbar_init(&accempty[i], TS_EPI_WARPS);
     }
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  // support image: element (k = input node, m = output node) = A(m, k):  Gs[k][m] (transpose) or Gs[m][k]
-  for (int it = tid; it < Kp * 32; it += TS_THREADS) {
-    const int k = it >> 5, ch = it & 31;
-    float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = ch * 4 + i;
-      v[i] = (k < N && m < N) ? (p.transpose ? G[(size_t)k * N + m] : G[(size_t)m * N + k]) : 0.f;
-    }
-    store_split4(G_hi, G_lo, (uint32_t)(ch >> 3) * colblk + mn32_chunk_offset(k, ch & 7), make_float4(v[0], v[1], v[2], v[3]));
-  }
   // rows N..Kp-1 of the X images are never written by the producers: zero them once
-  for (uint32_t i = tid * 16u; i < 4 * p.imgX; i += TS_THREADS * 16u)
+  for (uint32_t i = tid * 16u; i < 2u * (uint32_t)p.stages * p.imgX; i += TS_THREADS * 16u)
     *reinterpret_cast<float4*>(Xbuf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // The support is the A operand and lives in TENSOR MEMORY for the whole kernel: lane m = output node, column k =
+  // input node, A(m,k) = Gs[k][m] (transpose) or Gs[m][k]; hi part in columns [TS_ACC_COLS, +Kp), lo part right after.
+  // (Shared memory then only holds the streamed X ring, and each MMA reads a third of the bytes from it.)
+  const uint32_t tG = tmem_base + TS_ACC_COLS;
+  if (warp < 12) {   // three warps per TMEM lane quarter share the K columns
+    const int q = warp & 3, part = warp >> 2;
+    const int m = q * 32 + lane;
+    const uint32_t tl = tG + ((uint32_t)(q * 32) << 16);
+    for (int k0 = part * 8; k0 < Kp; k0 += 24) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = k0 + i;
+        const float v = (k < N && m < N) ? (p.transpose ? G[(size_t)k * N + m] : G[(size_t)m * N + k]) : 0.f;
+        split_tf32(v, hi[i], lo[i]);
+      }
+      tmem_st8(tl + (uint32_t)k0, hi);
+      tmem_st8(tl + (uint32_t)(Kp + k0), lo);
+    }
+    tmem_st_wait();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
   const long long stride = gridDim.x;
 
   if (warp == 0) {
     // =========================== MMA issuer (one thread) ===========================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_mn(128, TS_NT);
-      const uint64_t gh0 = make_smem_desc_mn32(smem_u32(G_hi), colblk, MN32_GROUP_BYTES);
-      const uint64_t gl0 = make_smem_desc_mn32(smem_u32(G_lo), colblk, MN32_GROUP_BYTES);
+      const uint32_t idesc = make_idesc_tf32_atmem_bmn(128, TS_NT);
       int it = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
-        const int buf = it & 1;
-        const uint32_t par = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&accempty[buf], par ^ 1u);     // the epilogue drained this accumulator pair (first use: passes)
-        mbar_wait(&full[buf], par);              // the producers staged this X tile
+        const int st = it % p.stages, ab = it & 1;
+        mbar_wait(&accempty[ab], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator pair
+        mbar_wait(&full[st], (uint32_t)(it / p.stages) & 1u);        // the producers staged this X tile
         fence_after_sync();
-        const uint32_t xhi = smem_u32(Xbuf + (size_t)buf * 2 * p.imgX);
+        const uint32_t xhi = smem_u32(Xbuf + (size_t)st * 2 * p.imgX);
         const uint64_t xh0 = make_smem_desc_mn32(xhi, colblk, MN32_GROUP_BYTES);
         const uint64_t xl0 = make_smem_desc_mn32(xhi + p.imgX, colblk, MN32_GROUP_BYTES);
-        const uint32_t d_main = tmem_base + (uint32_t)(buf * 2 * TS_NT), d_small = d_main + TS_NT;
+        const uint32_t d_main = tmem_base + (uint32_t)(ab * 2 * TS_NT), d_small = d_main + TS_NT;
 #pragma unroll 1
         for (int ks = 0; ks < Kp / 8; ++ks) {
           const uint64_t o = (uint64_t)(ks * ((2 * MN32_GROUP_BYTES) >> 4));   // K = 8 rows further down
-          mma_tf32(d_small, gl0 + o, xh0 + o, idesc, ks > 0 ? 1u : 0u);
-          mma_tf32(d_small, gh0 + o, xl0 + o, idesc, 1u);
-          mma_tf32(d_main, gh0 + o, xh0 + o, idesc, ks > 0 ? 1u : 0u);
+          const uint32_t gh = tG + (uint32_t)(ks * 8), gl = gh + (uint32_t)Kp;
+          mma_tf32_atmem(d_small, gl, xh0 + o, idesc, ks > 0 ? 1u : 0u);
+          mma_tf32_atmem(d_small, gh, xl0 + o, idesc, 1u);
+          mma_tf32_atmem(d_main, gh, xh0 + o, idesc, ks > 0 ? 1u : 0u);
         }
-        mma_commit(&empty[buf]);      // X buffer may be refilled once these MMAs have read it
-        mma_commit(&accfull[buf]);    // ... and the accumulators are complete
+        mma_commit(&empty[st]);       // X stage may be refilled once these MMAs have read it
+        mma_commit(&accfull[ab]);     // ... and the accumulators are complete
       }
     }
   } else if (warp <= TS_PROD_WARPS) {
@@ -125,16 +138,16 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
       }
     };
     auto stage = [&](int it, const float4 (&r)[TS_SLOTS]) {
-      const int buf = it & 1;
-      mbar_wait(&empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // MMAs of the tile two back have read this buffer
-      uint8_t* hi = Xbuf + (size_t)buf * 2 * p.imgX;
+      const int st = it % p.stages;
+      mbar_wait(&empty[st], ((uint32_t)(it / p.stages) & 1u) ^ 1u);   // MMAs of the tile `stages` back have read it
+      uint8_t* hi = Xbuf + (size_t)st * 2 * p.imgX;
       uint8_t* lo = hi + p.imgX;
 #pragma unroll
       for (int i = 0; i < TS_SLOTS; ++i)
         if (r0 + 16 * i < N) store_split4(hi, lo, soff0 + (uint32_t)(16 * i) * ATOM_ROW_BYTES, r[i]);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[buf]);
+      if (lane == 0) mbar_arrive(&full[st]);
     };
     long long tile = blockIdx.x;
     fetch(tile, ra[0]);
@@ -154,33 +167,34 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
     const int m = sp * 32 + lane;
     const bool live = m < N;
     const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
+    const bool use_z = beta != 0.f;
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
-      const int buf = it & 1;
-      long long cg = tile * TS_NT;
-      long long b = cg / W;
-      int j = (int)(cg - b * W);
-      mbar_wait(&accfull[buf], (uint32_t)(it >> 1) & 1u);
+      const int ab = it & 1;
+      const long long cg0 = tile * TS_NT;
+      const long long b0 = cg0 / W;
+      const int j0 = (int)(cg0 - b0 * W);
+      // every Z chunk of the tile is requested before waiting for the accumulators: one exposed latency per tile
+      float4 zz[TS_NT / 4];
+      if (use_z) {
+        long long cb = b0, cg = cg0;
+        int cj = j0;
+#pragma unroll
+        for (int g = 0; g < TS_NT / 4; ++g) {
+          zz[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && cg < p.total_cols) zz[g] = __ldg(reinterpret_cast<const float4*>(Z + cb * z_bs + (long long)m * W + cj));
+          cj += 4; cg += 4;
+          if (cj >= W) { cj = 0; ++cb; }
+        }
+      }
+      mbar_wait(&accfull[ab], (uint32_t)(it >> 1) & 1u);
       fence_after_sync();
+      long long b = b0, cg = cg0;
+      int j = j0;
 #pragma unroll
       for (int hh = 0; hh < TS_NT / 16; ++hh) {    // 16 columns at a time
         uint32_t vm[16], vs[16];
-        float4 zz[4];
-        // Z first: its latency hides behind the TMEM loads
-        {
-          long long cb = b;
-          int cj = j;
-          long long cgg = cg;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            zz[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (beta != 0.f && live && cgg < p.total_cols)
-              zz[g] = *reinterpret_cast<const float4*>(Z + cb * z_bs + (long long)m * W + cj);
-            cj += 4; cgg += 4;
-            if (cj >= W) { cj = 0; ++cb; }
-          }
-        }
-        const uint32_t a0 = tl + (uint32_t)(buf * 2 * TS_NT + hh * 16);
+        const uint32_t a0 = tl + (uint32_t)(ab * 2 * TS_NT + hh * 16);
         tmem_ld16_async(a0, vm);
         tmem_ld16_async(a0 + TS_NT, vs);
         tmem_ld_wait();
@@ -190,10 +204,14 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
         for (int g = 0; g < 4; ++g) {
           if (live && cg < p.total_cols) {
             float4 o;
-            o.x = fmaf(beta, zz[g].x, alpha * (__uint_as_float(vm[4 * g + 0]) + __uint_as_float(vs[4 * g + 0])));
-            o.y = fmaf(beta, zz[g].y, alpha * (__uint_as_float(vm[4 * g + 1]) + __uint_as_float(vs[4 * g + 1])));
-            o.z = fmaf(beta, zz[g].z, alpha * (__uint_as_float(vm[4 * g + 2]) + __uint_as_float(vs[4 * g + 2])));
-            o.w = fmaf(beta, zz[g].w, alpha * (__uint_as_float(vm[4 * g + 3]) + __uint_as_float(vs[4 * g + 3])));
+            o.x = alpha * (__uint_as_float(vm[4 * g + 0]) + __uint_as_float(vs[4 * g + 0]));
+            o.y = alpha * (__uint_as_float(vm[4 * g + 1]) + __uint_as_float(vs[4 * g + 1]));
+            o.z = alpha * (__uint_as_float(vm[4 * g + 2]) + __uint_as_float(vs[4 * g + 2]));
+            o.w = alpha * (__uint_as_float(vm[4 * g + 3]) + __uint_as_float(vs[4 * g + 3]));
+            if (use_z) {
+              const float4 z = zz[hh * 4 + g];
+              o.x = fmaf(beta, z.x, o.x); o.y = fmaf(beta, z.y, o.y); o.z = fmaf(beta, z.z, o.z); o.w = fmaf(beta, z.w, o.w);
+            }
             *reinterpret_cast<float4*>(Y + (b * N + m) * (long long)W + j) = o;
           }
           j += 4; cg += 4;
@@ -202,7 +220,7 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&accempty[buf]);
+      if (lane == 0) mbar_arrive(&accempty[ab]);
     }
   }
   __syncthreads();
@@ -231,21 +249,20 @@ int try_launch_support_tc(const float* G, int N, int B, int width, bool transpos
   TcSupPlan p;
   p.N = N;
   p.Kp = (N + 7) & ~7;
-  p.Mimg = 128;
   if (p.Kp > 16 * TS_SLOTS) return STC_OK;
   p.W = width;
   p.transpose = transpose ? 1 : 0;
   p.total_cols = (long long)B * width;
   p.ntiles = (p.total_cols + TS_NT - 1) / TS_NT;
-  p.imgG = (uint32_t)4 * p.Kp * ATOM_ROW_BYTES;
   p.imgX = (uint32_t)(TS_NT / 32) * p.Kp * ATOM_ROW_BYTES;
-  p.tmem_cols = 256;   // 2 x (main + cross-term) x 64 columns
+  p.tmem_cols = 512;   // 2 x (main + cross-term) x 64 accumulator columns + the support (2 x Kp <= 256 columns)
+  const size_t fixed = 8 * (2 * TS_MAX_STAGES + 4) + 32;
+  p.stages = TS_MAX_STAGES;
+  while (p.stages > 2 && 2 * (size_t)p.stages * p.imgX + fixed > 227 * 1024) --p.stages;
   size_t o = 0;
-  p.off_g = (uint32_t)o; o += 2 * (size_t)p.imgG;
-  o = round_up(o, 1024);
-  p.off_x = (uint32_t)o; o += 4 * (size_t)p.imgX;
+  p.off_x = (uint32_t)o; o += 2 * (size_t)p.stages * p.imgX;
   o = round_up(o, 16);
-  p.off_bar = (uint32_t)o; o += 96;
+  p.off_bar = (uint32_t)o; o += 8 * (2 * TS_MAX_STAGES + 4) + 16;
   p.smem_bytes = (uint32_t)o;
   if (p.smem_bytes > 227 * 1024) return STC_OK;   // larger N: the FFMA kernel tiles it
   STC_TRY(set_smem(tc_support_kernel, p.smem_bytes));

@@ -255,3 +255,44 @@ def test_tf32x3_mn_major_block(mnk, monkeypatch):
     torch.cuda.synchronize()
     ref = A.double().cpu() @ Bm.double().cpu()
     O.assert_close(D.cpu(), ref, "tf32x3 gemm, MN-major operands")
+
+
+# ---- the large-N CSR configurations of BASELINE.json (configs 3 and 4) at their real node counts ------------------
+def _csr_case(N, deg, B, C, Din, h, Ks, Kc, seed):
+    g = torch.Generator().manual_seed(seed)
+    col = torch.randint(0, N, (N, deg), generator=g)
+    rowptr = torch.arange(0, N * deg + 1, deg)
+    vals = (torch.rand(N * deg, generator=g) + 0.5) / deg
+    Gs = torch.sparse_csr_tensor(rowptr, col.reshape(-1), vals.double(), size=(N, N))
+    p = O.xavier_cell_params(Din, h, Ks, Kc, g, dtype=torch.float32, bias_scale=0.1)
+    f = lambda x: x.float().double()
+    t = dict(Gs=Gs, Gc=f(torch.rand(C, C, generator=g) / C), Xt=f(torch.randn(B, N, C, Din, generator=g)),
+             H=f(torch.randn(B, N, C, h, generator=g) * 0.5), dHn=f(torch.randn(B, N, C, h, generator=g)),
+             Wg=f(p.Wg), Wc=f(p.Wc), bg=f(p.bg), bc=f(p.bc))
+    return t, rowptr, col.reshape(-1), vals
+
+
+def test_config3_grid4096_f64_csr_cell():
+    """N = 4096 regions, C = 16, F = 64 (BASELINE config 3 shapes), constant CSR support: forward + every gradient."""
+    N, C, Din, h = 4096, 16, 64, 64
+    cfg = dict(B=1, N=N, C=C, Din=Din, h=h, Ks=2, Kc=2, activation=None)
+    t, rowptr, col, vals = _csr_case(N, 8, 1, C, Din, h, 2, 2, seed=7)
+    csr = S.CsrSupport(rowptr.to(DEV), col.to(DEV), vals.float().to(DEV), N)
+    Hn, g = run_cuda_cell(t, cfg, Gs_override=csr)
+    Hn_o, g_o = oracle_cell_with_grads(t, cfg)
+    O.assert_close(Hn, Hn_o, "config3 Hn")
+    for k in ("dXt", "dH", "dWg", "dWc", "dbg", "dbc", "dGc"):
+        O.assert_close(g[k], g_o[k], f"config3 {k}")
+
+
+def test_config4_knn65536_csr_forward():
+    """N = 65,536 nodes, C = 8, Ks = 4 (3 hops) on a degree-8 CSR graph (BASELINE config 4 node count): forward only,
+    hidden width 16 so that the fp64 oracle stays within a few GB on the host."""
+    N, C, Din, h, Ks = 65536, 8, 1, 16, 4
+    t, rowptr, col, vals = _csr_case(N, 8, 1, C, Din, h, Ks, 2, seed=8)
+    csr = S.CsrSupport(rowptr.to(DEV), col.to(DEV), vals.float().to(DEV), N)
+    f = lambda x: x.float().to(DEV)
+    with torch.no_grad():
+        Hn = S.stc_cell_forward(csr, f(t["Gc"]), f(t["Xt"]), f(t["H"]), f(t["Wg"]), f(t["bg"]), f(t["Wc"]), f(t["bc"]), Ks, 2)
+        ref = O.stc_cell(t["Gs"], t["Gc"], t["Xt"], t["H"], t["Wg"], t["bg"], t["Wc"], t["bc"], Ks, 2)
+    O.assert_close(Hn.cpu(), ref, "config4 Hn")

@@ -101,8 +101,21 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   const int lane_base = (warp & 3) * 32, half = warp >> 2;
   const int erow = lane_base + lane;
   const uint32_t tl = tmem_base + ((uint32_t)lane_base << 16);
-  float db_acc = 0.f;  // thread (group g, column j) owns rows g, g + groups, ... of bias-gradient column j
+  // bias gradient: a thread's column chunk j is the same for every prologue item it handles (CV_THREADS % (h/4) == 0),
+  // so the column sums live in registers for the whole kernel; otherwise a per-tile pass over the Ds tile is used
+  const bool db_fast = a.dbias != nullptr && (CV_THREADS % (h >> 2)) == 0;
+  float4 dbs0 = make_float4(0.f, 0.f, 0.f, 0.f), dbs1 = dbs0;
+  float db_acc = 0.f;  // slow path: thread (group g, column j) owns rows g, g + groups, ... of bias-gradient column j
   const int db_groups = CV_THREADS / Hout, db_col = tid % Hout, db_grp = tid / Hout;
+  // dT_1(Gc) fast path (Kc == 2, C <= DQ_C): thread (node slot, 4-channel chunk) keeps the C x C partial sums in
+  // registers across tiles -- conflict-free 16-byte reads of the P and Ds tiles, one reduction at the end
+  constexpr int DQ_C = 5;
+  const int dq_chunks = Hout >> 2;
+  const bool dq_fast = want_dQ && a.Kc == 2 && C <= DQ_C && p.npt * dq_chunks <= CV_THREADS;
+  const int dq_node = tid / dq_chunks, dq_oc = (tid - dq_node * dq_chunks) << 2;
+  float dq[DQ_C * DQ_C];
+#pragma unroll
+  for (int i = 0; i < DQ_C * DQ_C; ++i) dq[i] = 0.f;
   uint32_t mma_phase = 0, load_phase = 0;
   bool mma_pending = false;
 
@@ -160,6 +173,10 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
           *reinterpret_cast<float4*>(a.dpre + (row0 + row) * p.Kdd + h + j) = g1v;
         }
       }
+      if (db_fast) {
+        dbs0.x += g0v.x; dbs0.y += g0v.y; dbs0.z += g0v.z; dbs0.w += g0v.w;
+        dbs1.x += g1v.x; dbs1.y += g1v.y; dbs1.z += g1v.z; dbs1.w += g1v.w;
+      }
       *reinterpret_cast<float4*>(Dsm + row * DP + j) = g0v;
       if (a.phase == 0) {
         *reinterpret_cast<float4*>(Dsm + row * DP + h + j) = g1v;
@@ -167,7 +184,7 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       }
     }
     __syncthreads();
-    if (a.dbias && tid < db_groups * Hout) {   // every thread sums a strided slice of rows of its column
+    if (a.dbias && !db_fast && tid < db_groups * Hout) {   // every thread sums a strided slice of rows of its column
       float s = 0.f;
       for (int row = db_grp; row < rows_valid; row += db_groups) s += Dsm[row * DP + db_col];
       db_acc += s;
@@ -223,7 +240,26 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       load_phase ^= 1u;
       const int npairs = (a.Kc - 1) * C * C;
       const int groups = CV_THREADS / npairs;      // node groups working on the same pair
-      if (groups >= 1) {
+      if (dq_fast) {
+        if (dq_node < nodes_valid) {
+          float4 pv[DQ_C], dv[DQ_C];
+#pragma unroll
+          for (int i = 0; i < DQ_C; ++i) {
+            const int ci = i < C ? i : 0;
+            pv[i] = *reinterpret_cast<const float4*>(Psm + (dq_node * C + ci) * p.PW + dq_oc);
+            dv[i] = *reinterpret_cast<const float4*>(Dsm + (dq_node * C + ci) * DP + dq_oc);
+          }
+#pragma unroll
+          for (int cp = 0; cp < DQ_C; ++cp)
+#pragma unroll
+            for (int d = 0; d < DQ_C; ++d) {
+              float s = dq[cp * DQ_C + d];
+              s = fmaf(pv[cp].x, dv[d].x, s); s = fmaf(pv[cp].y, dv[d].y, s);
+              s = fmaf(pv[cp].z, dv[d].z, s); s = fmaf(pv[cp].w, dv[d].w, s);
+              dq[cp * DQ_C + d] = s;
+            }
+        }
+      } else if (groups >= 1) {
         const int pr = tid % npairs, grp = tid / npairs;
         if (grp < groups) {
           const int c = pr / (C * C), rem = pr - c * C * C, cp = rem / C, d = rem - cp * C;
@@ -260,16 +296,29 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
     {
       const bool valid = erow < rows_valid;
       const long long gr = row0 + erow;
-      for (int n0 = half * 8; n0 < p.Npad; n0 += 16) {
-        float v[8], t[8];
-        tmem_ld8(tl + (uint32_t)(p.KA * p.Npad + n0), v);
-        for (int m = 0; m < p.KA; ++m) {
-          tmem_ld8(tl + (uint32_t)(m * p.Npad + n0), t);
+      int k = 0, kb = half * 8;                      // (spatial term, column within its [h | x] block) of chunk n0
+      for (int n0 = half * 8; n0 < p.Npad; n0 += 16, kb += 16) {
+        float v[8];
+        if (p.KA == 2) {                               // the common case: all three accumulators in flight, one wait
+          uint32_t t0[8], t1[8], t2[8];
+          tmem_ld8_async(tl + (uint32_t)(2 * p.Npad + n0), t2);
+          tmem_ld8_async(tl + (uint32_t)n0, t0);
+          tmem_ld8_async(tl + (uint32_t)(p.Npad + n0), t1);
+          tmem_ld_wait();
+          tmem_ld_pin8(t0); tmem_ld_pin8(t1); tmem_ld_pin8(t2);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] += t[i];
+          for (int i = 0; i < 8; ++i) v[i] = (__uint_as_float(t2[i]) + __uint_as_float(t0[i])) + __uint_as_float(t1[i]);
+        } else {
+          float t[8];
+          tmem_ld8(tl + (uint32_t)(p.KA * p.Npad + n0), v);
+          for (int m = 0; m < p.KA; ++m) {
+            tmem_ld8(tl + (uint32_t)(m * p.Npad + n0), t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += t[i];
+          }
         }
+        while (kb >= p.KBL) { kb -= p.KBL; ++k; }      // KBL % 8 == 0: a chunk never straddles terms or parts
         if (!valid || n0 >= p.N1) continue;
-        const int k = n0 / p.KBL, kb = n0 - k * p.KBL;   // KBL % 8 == 0: a chunk never straddles terms or parts
         if (kb < h) {
           float* dst = (k == 0 ? a.dYh0 : a.dYh + (size_t)(k - 1) * R * h) + gr * h + kb;
           if (k == 0 && a.phase == 0) {
@@ -304,7 +353,27 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
     fence_before_sync();
     __syncthreads();  // Dsm / Dh / Psm are rewritten by the next tile's prologue
   }
-  if (a.dbias && tid < db_groups * Hout) atomicAdd(&a.dbias[db_col], db_acc);
+  if (a.dbias && !db_fast && tid < db_groups * Hout) atomicAdd(&a.dbias[db_col], db_acc);
+  __syncthreads();   // every tile is done: Dsm is free and serves as the reduction scratch
+  if (db_fast) {
+    for (int i = tid; i < Hout; i += CV_THREADS) Dsm[i] = 0.f;
+    __syncthreads();
+    const int j = (tid % (h >> 2)) << 2;
+    atomicAdd(&Dsm[j + 0], dbs0.x); atomicAdd(&Dsm[j + 1], dbs0.y); atomicAdd(&Dsm[j + 2], dbs0.z); atomicAdd(&Dsm[j + 3], dbs0.w);
+    if (a.phase == 0) {
+      atomicAdd(&Dsm[h + j + 0], dbs1.x); atomicAdd(&Dsm[h + j + 1], dbs1.y);
+      atomicAdd(&Dsm[h + j + 2], dbs1.z); atomicAdd(&Dsm[h + j + 3], dbs1.w);
+    }
+    __syncthreads();
+    for (int i = tid; i < Hout; i += CV_THREADS) atomicAdd(&a.dbias[i], Dsm[i]);
+  }
+  if (dq_fast && tid < p.npt * dq_chunks) {
+#pragma unroll
+    for (int cp = 0; cp < DQ_C; ++cp)
+#pragma unroll
+      for (int d = 0; d < DQ_C; ++d)
+        if (cp < C && d < C) atomicAdd(&dQacc[cp * C + d], dq[cp * DQ_C + d]);
+  }
   __syncthreads();
   if (want_dQ)
     for (int i = tid; i < (a.Kc - 1) * C * C; i += CV_THREADS) atomicAdd(&a.dQ[C * C + i], dQacc[i]);

@@ -30,9 +30,9 @@ __device__ __forceinline__ uint32_t atom_chunk_offset(int row, int q) {
 
 // round-to-nearest TF32 (cvt.rna): the result has its low 13 mantissa bits clear
 __device__ __forceinline__ float to_tf32_rn(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+  // the integer form of cvt.rna.tf32.f32 (round to nearest, ties away from zero, on the sign-magnitude bits): two
+  // instructions instead of the four the cvt expands to (it also special-cases inf/nan, which never occur here)
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 // hi = RN_tf32(v), lo = v - hi (exact).  The tensor core ignores lo's 13 low mantissa bits; because hi is
 // rounded to nearest, lo has no preferred sign and that truncation is unbiased: |v - hi - tf32(lo)| <= 2^-21 |v|

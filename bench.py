@@ -211,7 +211,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     _lib.load()
 
     B = args.batch
@@ -284,13 +285,15 @@ def run_b200(args):
            "h2d_bytes_per_step": Xh.numel() * 4 + yh.numel() * 4, "d2h_bytes_per_step": 4}
 
     # ---- instrumented pass: per-kernel device time + algorithmic bytes over the same K steps ----
+    # (every rank runs the pass -- step() contains the gradient all-reduce -- but only rank 0 records and reports)
     roofline, breakdown = None, None
     if rank == 0:
         _lib.timing_enable(True)
         _lib.timing_collect()
-        for _ in range(args.steps):
-            step(X_res, y_res)
-        torch.cuda.synchronize()
+    for _ in range(args.steps):
+        step(X_res, y_res)
+    sync_all()
+    if rank == 0:
         _lib.timing_enable(False)
         kinds = _lib.timing_collect()
         peak, peak_src = measured_peaks()

@@ -42,7 +42,7 @@ void reset_launch_count();
 // ---- optional per-kernel timing (stc_timing_* in the ABI) ---------------------------------------
 enum KernelKind {
   KK_SUPPORT_DENSE = 0, KK_SUPPORT_CSR, KK_SUPPORT_OUTER, KK_CHEBY_SMALL, KK_CONV_FWD, KK_CONV_BWD_DX,
-  KK_CONV_BWD_DW, KK_TC_CONV_FWD, KK_TC_CONV_BWD_DX, KK_TC_CONV_BWD_DW, KK_TC_SUPPORT, KK_TC_GEMM_TEST, KK_TC_OUTER, KK_COUNT
+  KK_CONV_BWD_DW, KK_TC_CONV_FWD, KK_TC_CONV_BWD_DX, KK_TC_CONV_BWD_DW, KK_TC_SUPPORT, KK_TC_GEMM_TEST, KK_TC_OUTER, KK_TC_CELL_FWD, KK_COUNT
 };
 struct ScopedKernelTimer {  // declare right before a launch; the destructor records the stop event
   ScopedKernelTimer(int kind, cudaStream_t st, double alg_bytes);
@@ -142,6 +142,11 @@ struct ConvArgs {
   float* dQ;           // [Kc][C][C] atomically accumulated, or null
   float* dW;           // atomically accumulated
 };
+// fused forward cell (stc_cell_fused.cu): dense support that fits one tile, Ks = Kc = 2, h = 16
+bool cell_fused_eligible(const StcDims& d, const StcSupport& gs);
+int launch_cell_fwd_fused(const StcDims& d, const StcSupport& gs, const float* Q, const float* xt, long long xt_bs,
+                          const float* h_prev, const float* Wg, const float* bg, const float* Wc, const float* bc,
+                          float* h_out, float* ws, const WsLayout& w, cudaStream_t st);
 int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, cudaStream_t st);
 int launch_conv_fwd(const ConvArgs& a, cudaStream_t st);
 bool conv_tc_eligible(const ConvArgs& a);  // shape-only test shared by forward and backward

@@ -44,6 +44,9 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-batch", type=int, default=32, help="windows per CPU-baseline step (bounded sample)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-roofline", action="store_true", help="skip the instrumented per-kernel pass")
+    p.add_argument("--cuda-graph", action="store_true",
+                   help="capture the whole fwd+bwd step once and replay it (stc_gnn_b200.GraphedStep; N=1 only)")
     return p.parse_args()
 
 
@@ -182,13 +185,14 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(B, n_gpus, reference=False):
+def workload_config(B, n_gpus, reference=False, graph=False):
     return {
         "workload": "sf_cell_stack: encoder 2x9 + decoder 3x2 = 24 STC cell steps/sample, fwd+bwd incl. dGs,dGc "
                     "(BASELINE.json configs[1], SF shape)",
         "N": SF["N"], "C": SF["C"], "hidden": SF["h"], "Ks": SF["Ks"], "Kc": SF["Kc"], "layers": SF["layers"],
         "T": SF["T"], "horizon": SF["horizon"], "batch_per_gpu": B, "global_batch": B * (1 if reference else n_gpus),
         "parallelism": "cpu" if reference else f"dp{n_gpus}",
+        "launch": "cuda-graph replay of the captured step" if graph else "eager (one C-ABI call per cell and direction)",
         "l2": "inputs+activations exceed L2 (no flush needed)" if B >= 1024 else "working set may fit L2",
         "bytes_model": "per-kernel compulsory bytes of the multi-kernel pipeline (DESIGN.md section 4); the fused-cell floor "
                        "of SURVEY 8d is 9.94 MB per sample fwd+bwd",
@@ -263,18 +267,32 @@ def run_b200(args):
         return ms
 
     # ---- device-resident throughput ----
-    for _ in range(max(args.warmup, 3)):
+    graphed = None
+    if args.cuda_graph:
+        if world > 1:
+            raise SystemExit("--cuda-graph is a single-GPU option")
+        l0 = _lib.LAUNCHES
         step(X_res, y_res)
+        per_step_launches = _lib.LAUNCHES - l0
+        graphed = S.GraphedStep(lambda X, y: loss_fn(stack(Gs, Gc, X), y), [X_res, y_res], params + [Gs, Gc],
+                                warmup=max(args.warmup, 3))
+        run_resident = lambda: graphed.replay(X_res, y_res)
+    else:
+        run_resident = lambda: step(X_res, y_res)
+    for _ in range(max(args.warmup, 3)):
+        run_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = _lib.LAUNCHES
-    ms_total = timed(lambda: step(X_res, y_res), args.steps)
-    launches = _lib.LAUNCHES - l0
+    ms_total = timed(run_resident, args.steps)
+    launches = (per_step_launches * args.steps) if graphed else (_lib.LAUNCHES - l0)
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
 
     # ---- end to end through the module API: pinned host inputs in, loss out, every step ----
     def e2e_step():
+        if graphed:
+            return float(graphed.replay(Xh, yh).item())   # pinned host -> the graph's static inputs, replay, loss out
         X = Xh.to(dev, non_blocking=True)
         y = yh.to(dev, non_blocking=True)
         return float(step(X, y).item())
@@ -287,13 +305,14 @@ def run_b200(args):
     # ---- instrumented pass: per-kernel device time + algorithmic bytes over the same K steps ----
     # (every rank runs the pass -- step() contains the gradient all-reduce -- but only rank 0 records and reports)
     roofline, breakdown = None, None
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
         _lib.timing_enable(True)
         _lib.timing_collect()
-    for _ in range(args.steps):
-        step(X_res, y_res)
+    if not args.no_roofline:
+        for _ in range(args.steps):
+            step(X_res, y_res)
     sync_all()
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
         _lib.timing_enable(False)
         kinds = _lib.timing_collect()
         peak, peak_src = measured_peaks()
@@ -323,7 +342,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world, graph=bool(graphed)),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown,
         }

@@ -19,7 +19,7 @@ EXPORTED = (
     "stc_abi_version", "stc_last_error", "stc_cell_saved_bytes", "stc_cell_bwd_scratch_bytes",
     "stc_cell_fwd", "stc_cell_bwd", "stc_support_apply", "stc_last_launch_count",
     "stc_timing_enable", "stc_timing_collect", "stc_kernel_kind_name", "stc_tf32x3_gemm",
-    "stc_cell_saved_layout", "stc_cell_fwd_stage",
+    "stc_cell_saved_layout", "stc_cell_fwd_stage", "stc_debug_trace_set",
 )
 STAGE_GATES, STAGE_CANDI = 0, 1
 SAVED_REGIONS = ("u", "r", "c", "Yr", "Yx", "Yh", "Q", "Pg", "Pc")
@@ -77,6 +77,8 @@ def load(build_if_missing: bool = True):
     lib.stc_timing_enable.argtypes = [c_int32]
     lib.stc_timing_collect.restype = c_int
     lib.stc_timing_collect.argtypes = [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(ctypes.c_double), c_int32]
+    lib.stc_debug_trace_set.restype = c_int
+    lib.stc_debug_trace_set.argtypes = [c_void_p, c_int64]
     lib.stc_kernel_kind_name.restype = c_char_p
     lib.stc_kernel_kind_name.argtypes = [c_int32]
     if lib.stc_abi_version() != ABI_VERSION:

@@ -2,6 +2,7 @@
 // launch sequence of one cell forward / backward on the general path.
 #include "stc_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -86,6 +87,22 @@ int check_arch() {
   return STC_OK;
 }
 
+// ---- tuning switches and the phase trace ----
+static long long* g_trace_buf = nullptr;
+static int g_trace_tiles = 0;
+int conv_opt_flags() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("STC_OPT");
+    cached = (e && e[0]) ? (atoi(e) & 0x7fffffff) : 0x7fffffff;
+  }
+  return cached;
+}
+void conv_trace_target(long long** buf, int* tiles) {
+  *buf = g_trace_buf;
+  *tiles = g_trace_tiles;
+}
+
 WsLayout make_layout(const StcDims& d) {
   WsLayout w;
   const size_t A = 64;  // 256-byte alignment of every region
@@ -150,6 +167,9 @@ static ConvArgs base_args(const StcDims& d, const float* xt, int64_t xt_bs, cons
   a.W = W;
   a.Q = Q;
   a.dpre_ld = conv_tc_eligible(a) ? a.Kc * a.Hout : a.Hout;
+  a.opt = conv_opt_flags();
+  conv_trace_target(&a.trace, &a.trace_tiles);
+  if (a.trace) a.trace += (size_t)phase * a.trace_tiles * TRACE_SLOTS;   // gates stamps first, candidate stamps after them
   return a;
 }
 
@@ -187,6 +207,13 @@ const char* stc_kernel_kind_name(int32_t kind) {
                                         "conv_fwd",      "conv_bwd_dx", "conv_bwd_dw", "tc_conv_fwd", "tc_conv_bwd_dx", "tc_conv_bwd_dw",
                                         "tc_support", "tc_gemm_test", "tc_outer", "tc_cell_fwd"};
   return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "?";
+}
+
+int stc_debug_trace_set(void* dev_buf, int64_t n_slots) {
+  std::lock_guard<std::mutex> lk(g_tmu);
+  g_trace_buf = (long long*)dev_buf;
+  g_trace_tiles = dev_buf ? (int)(n_slots / (2 * TRACE_SLOTS)) : 0;
+  return STC_OK;
 }
 
 int stc_abi_version(void) { return STC_ABI_VERSION; }

@@ -132,6 +132,12 @@ static inline int set_smem(K kernel, size_t smem) {
   return STC_OK;
 }
 
+// phase trace of the tcgen05 kernels (stc_debug_trace_set): `tracing` / `trace_it` are locals of the kernel
+#define STC_TRACE(slot)                                                                              \
+  do {                                                                                               \
+    if (tracing && trace_it < a.trace_tiles) a.trace[trace_it * TRACE_SLOTS + (slot)] = clock64();   \
+  } while (0)
+
 // tcgen05 path (stc_conv_tc.cu): returns STC_OK and sets *handled when it took the launch
 int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled);
 int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled);

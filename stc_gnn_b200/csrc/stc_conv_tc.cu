@@ -78,8 +78,49 @@ __device__ __forceinline__ void tc_issue_tile_loads(const ConvArgs& a, const TcF
   }
 }
 
+// one lane: pull tile `tile`'s spatial terms and epilogue operands towards L2 (same ranges as tc_issue_tile_loads)
+__device__ __forceinline__ void tc_prefetch_tile(const ConvArgs& a, const TcFwdPlan& p, int tile) {
+  const long long total_nodes = (long long)a.B * a.N;
+  const long long g0 = (long long)tile * p.npt;
+  const int nv = (int)min((long long)p.npt, total_nodes - g0);
+  const long long R = total_nodes * a.C;
+  const int CH = a.C * a.h, CD = a.C * a.Din;
+  const uint32_t hb = (uint32_t)(nv * CH * 4), xb = (uint32_t)(nv * CD * 4);
+  for (int k = 0; k < a.Ks; ++k) {
+    l2_prefetch((k == 0 ? a.h0 : a.yh + (long long)(k - 1) * R * a.h) + g0 * CH, hb);
+    if (!p.x_bulk) continue;
+    if (k > 0) {
+      l2_prefetch(a.yx + (long long)(k - 1) * R * a.Din + g0 * CD, xb);
+    } else {
+      long long g = g0;
+      int left = nv;
+      while (left > 0) {
+        const long long b = g / a.N;
+        const int m = (int)(g - b * a.N);
+        const int seg = min(left, a.N - m);
+        l2_prefetch(a.x0 + b * a.x0_bs + (long long)m * CD, (uint32_t)(seg * CD * 4));
+        g += seg;
+        left -= seg;
+      }
+    }
+  }
+  if (a.Hprev != a.h0) l2_prefetch(a.Hprev + g0 * CH, hb);
+  if (a.phase != 0) l2_prefetch(a.u + g0 * CH, hb);
+}
+
 // sum of the per-atom partials of 8 accumulator columns starting at column c0 (cross terms first, fp32 RN adds)
-__device__ __forceinline__ void tc_read_acc8(uint32_t tl, const TcFwdPlan& p, int c0, float (&v)[8]) {
+__device__ __forceinline__ void tc_read_acc8(uint32_t tl, const TcFwdPlan& p, int c0, float (&v)[8], bool batched) {
+  if (batched && p.nacc == 2) {   // all three accumulators in flight, one wait; same summation order as below
+    uint32_t t0[8], t1[8], t2[8];
+    tmem_ld8_async(tl + (uint32_t)(2 * p.Npad + c0), t2);
+    tmem_ld8_async(tl + (uint32_t)c0, t0);
+    tmem_ld8_async(tl + (uint32_t)(p.Npad + c0), t1);
+    tmem_ld_wait();
+    tmem_ld_pin8(t0); tmem_ld_pin8(t1); tmem_ld_pin8(t2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (__uint_as_float(t2[i]) + __uint_as_float(t0[i])) + __uint_as_float(t1[i]);
+    return;
+  }
   float t[8];
   tmem_ld8(tl + (uint32_t)(p.nacc * p.Npad + c0), v);
   for (int m = 0; m < p.nacc; ++m) {
@@ -163,12 +204,17 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
 
   uint32_t mma_phase = 0, load_phase = 0, epi_phase = 0;
   bool mma_pending = false;
+  const bool batched_ld = (a.opt & OPT_ASYNC_TMEM_LD) != 0;
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
+  int trace_it = 0;
   if (tid == 0 && (int)blockIdx.x < p.ntiles) tc_issue_tile_loads(a, p, blockIdx.x, stage_h, stage_x, load_bar);
 
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long g0 = (long long)tile * p.npt;
     const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
     const int rows_valid = nodes_valid * C;
+    STC_TRACE(0);
+    if ((a.opt & OPT_L2_PREFETCH) && tid == 32 && tile + (int)gridDim.x < p.ntiles) tc_prefetch_tile(a, p, tile + gridDim.x);
     if (tid == 0) {  // the epilogue's own operands (H, and u for the candidate) travel under the builds and the MMAs
       const uint32_t eb = (uint32_t)(rows_valid * h * 4);
       mbar_arrive_expect_tx(epi_bar, a.phase == 0 ? eb : 2 * eb);
@@ -196,6 +242,7 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
       }
       __syncthreads();
     }
+    STC_TRACE(1);
     bool acc_small = false;
     int ai = 0;
     for (int k = 0; k < a.Ks; ++k) {
@@ -206,6 +253,7 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
           mbar_wait(mma_bar, mma_phase);
           mma_phase ^= 1u;
           mma_pending = false;
+          if (ai == p.nacc - 1) STC_TRACE(3);
         }
         const int kb = j * ATOM_K + q * 4;
         if (kb < h) {
@@ -230,6 +278,7 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
         }
         fence_async_smem();
         __syncthreads();
+        if (ai == 0) STC_TRACE(2);
         if (tid == 0) {
           // the stage is dead after the last build of this tile: prefetch the next tile under the MMAs + epilogue
           if (ai == p.nacc - 1 && tile + (int)gridDim.x < p.ntiles)
@@ -248,20 +297,23 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
       }
     }
     // ---- epilogue ----
+    STC_TRACE(4);
     mbar_wait(mma_bar, mma_phase);   // a commit covers every MMA issued before it; the A atoms are free too
     mma_phase ^= 1u;
     mma_pending = false;
     fence_after_sync();
+    STC_TRACE(5);
     mbar_wait(epi_bar, epi_phase);
     epi_phase ^= 1u;
+    STC_TRACE(6);
     const bool valid = erow < rows_valid;
     const long long gr = g0 * C + erow;
     for (int c0 = half * 8; c0 < Hout; c0 += 16) {
       float v[8];
-      tc_read_acc8(tl, p, c0, v);                                   // P_0
+      tc_read_acc8(tl, p, c0, v, batched_ld);                       // P_0
       for (int c = 1; c < a.Kc; ++c) {                              // + T_c(Gc)^T-mix of P_c over the node's categories
         float t[8];
-        tc_read_acc8(tl, p, c * Hout + c0, t);
+        tc_read_acc8(tl, p, c * Hout + c0, t, batched_ld);
         __syncthreads();                                            // previous users of Pm are done
         *reinterpret_cast<float4*>(Pm + erow * p.PS + c0) = make_float4(t[0], t[1], t[2], t[3]);
         *reinterpret_cast<float4*>(Pm + erow * p.PS + c0 + 4) = make_float4(t[4], t[5], t[6], t[7]);
@@ -326,6 +378,8 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
         dh[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
       }
     }
+    STC_TRACE(7);
+    ++trace_it;
     fence_before_sync();  // TMEM reads are ordered before the next tile's first (overwriting) MMA,
     fence_async_smem();   // the epilogue's reads of its staged operands precede the next tile's bulk copies into them,
     __syncthreads();      // and the exchange buffer is free before the next tile's A build

@@ -29,6 +29,80 @@ struct TcDxPlan {
   uint32_t off_a, off_b, off_ds, off_dh, off_ps, off_q, off_acc, off_bar, smem_bytes;
 };
 
+// operands of one prologue item (4 hidden channels of one row)
+struct DxIn {
+  float4 dhn, uu, cc, hp, rr, drh;
+};
+__device__ __forceinline__ void dx_load(const ConvArgs& a, long long o, DxIn& in) {
+  in.dhn = *reinterpret_cast<const float4*>(a.dHn + o);
+  in.uu = *reinterpret_cast<const float4*>(a.u + o);
+  in.cc = *reinterpret_cast<const float4*>(a.c + o);
+  if (a.phase == 0) {
+    in.hp = *reinterpret_cast<const float4*>(a.Hprev + o);
+    in.rr = *reinterpret_cast<const float4*>(a.r + o);
+    in.drh = *reinterpret_cast<const float4*>(a.drH + o);
+  }
+}
+// GRU / activation adjoint: g0v = pre-activation gradient of the candidate (phase 1) or of u (phase 0),
+// g1v = of r, dir = the direct dH terms
+__device__ __forceinline__ void dx_adjoint(const ConvArgs& a, const DxIn& in, float4& g0v, float4& g1v, float4& dir) {
+  const float4 dhn = in.dhn, uu = in.uu, cc = in.cc;
+  if (a.phase == 1) {
+    g0v = make_float4(dhn.x * uu.x * (1.f - cc.x * cc.x), dhn.y * uu.y * (1.f - cc.y * cc.y),
+                      dhn.z * uu.z * (1.f - cc.z * cc.z), dhn.w * uu.w * (1.f - cc.w * cc.w));
+    if (a.act == STC_ACT_RELU) {
+      if (!(cc.x > 0.f)) g0v.x = 0.f;
+      if (!(cc.y > 0.f)) g0v.y = 0.f;
+      if (!(cc.z > 0.f)) g0v.z = 0.f;
+      if (!(cc.w > 0.f)) g0v.w = 0.f;
+    }
+  } else {
+    const float4 hp = in.hp, rr = in.rr, drh = in.drh;
+    g0v = make_float4(dhn.x * (cc.x - hp.x) * uu.x * (1.f - uu.x), dhn.y * (cc.y - hp.y) * uu.y * (1.f - uu.y),
+                      dhn.z * (cc.z - hp.z) * uu.z * (1.f - uu.z), dhn.w * (cc.w - hp.w) * uu.w * (1.f - uu.w));
+    g1v = make_float4(drh.x * hp.x * rr.x * (1.f - rr.x), drh.y * hp.y * rr.y * (1.f - rr.y),
+                      drh.z * hp.z * rr.z * (1.f - rr.z), drh.w * hp.w * rr.w * (1.f - rr.w));
+    if (a.act == STC_ACT_RELU) {
+      if (!(uu.x > 0.5f)) g0v.x = 0.f;
+      if (!(uu.y > 0.5f)) g0v.y = 0.f;
+      if (!(uu.z > 0.5f)) g0v.z = 0.f;
+      if (!(uu.w > 0.5f)) g0v.w = 0.f;
+      if (!(rr.x > 0.5f)) g1v.x = 0.f;
+      if (!(rr.y > 0.5f)) g1v.y = 0.f;
+      if (!(rr.z > 0.5f)) g1v.z = 0.f;
+      if (!(rr.w > 0.5f)) g1v.w = 0.f;
+    }
+    dir = make_float4(dhn.x * (1.f - uu.x) + drh.x * rr.x, dhn.y * (1.f - uu.y) + drh.y * rr.y,
+                      dhn.z * (1.f - uu.z) + drh.z * rr.z, dhn.w * (1.f - uu.w) + drh.w * rr.w);
+  }
+}
+
+// one lane: pull the next tile's operands (and the x-part adjoints the gates pass accumulates into) towards L2
+__device__ __forceinline__ void dx_prefetch_tile(const ConvArgs& a, const TcDxPlan& p, int tile, bool want_dQ) {
+  const long long total_nodes = (long long)a.B * a.N;
+  const long long g0 = (long long)tile * p.npt;
+  const int nv = (int)min((long long)p.npt, total_nodes - g0);
+  const long long row0 = g0 * a.C;
+  const uint32_t hb = (uint32_t)(nv * a.C * a.h * 4);
+  l2_prefetch(a.dHn + row0 * a.h, hb);
+  l2_prefetch(a.u + row0 * a.h, hb);
+  l2_prefetch(a.c + row0 * a.h, hb);
+  if (a.phase == 0) {
+    l2_prefetch(a.Hprev + row0 * a.h, hb);
+    l2_prefetch(a.r + row0 * a.h, hb);
+    l2_prefetch(a.drH + row0 * a.h, hb);
+  }
+  if (want_dQ) l2_prefetch(a.Psave + row0 * p.PW, (uint32_t)(nv * a.C * p.PW * 4));
+  if (a.accum_x && p.x_vec) {
+    const uint32_t xb = (uint32_t)(nv * a.C * a.Din * 4);
+    const long long R = total_nodes * a.C;
+    if (a.dYx0) l2_prefetch(a.dYx0 + row0 * a.Din, xb);
+    if (a.dYx)
+      for (int k = 1; k < a.Ks; ++k) l2_prefetch(a.dYx + (size_t)(k - 1) * R * a.Din + row0 * a.Din, xb);
+  }
+}
+
+template <bool BATCHED>
 __global__ void __launch_bounds__(CV_THREADS, 2)
 tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -118,6 +192,8 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   for (int i = 0; i < DQ_C * DQ_C; ++i) dq[i] = 0.f;
   uint32_t mma_phase = 0, load_phase = 0;
   bool mma_pending = false;
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
+  int trace_it = 0;
 
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long g0 = (long long)tile * p.npt;
@@ -129,49 +205,15 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       mbar_arrive_expect_tx(load_bar, bytes);
       bulk_g2s(Psm, a.Psave + row0 * p.PW, bytes, load_bar);
     }
+    STC_TRACE(0);
+    if ((a.opt & OPT_L2_PREFETCH) && tid == 32 && tile + (int)gridDim.x < p.ntiles)
+      dx_prefetch_tile(a, p, tile + gridDim.x, want_dQ);
     // ---- 1. elementwise adjoint: one float4 of hidden channels per item ----
     const int cpr = h >> 2;
-    for (int it = tid; it < 128 * cpr; it += CV_THREADS) {
-      const int row = it / cpr, j = (it - row * cpr) << 2;
-      float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
-      if (row < rows_valid) {
-        const long long o = (row0 + row) * h + j;
-        const float4 dhn = *reinterpret_cast<const float4*>(a.dHn + o);
-        const float4 uu = *reinterpret_cast<const float4*>(a.u + o);
-        const float4 cc = *reinterpret_cast<const float4*>(a.c + o);
-        if (a.phase == 1) {
-          g0v = make_float4(dhn.x * uu.x * (1.f - cc.x * cc.x), dhn.y * uu.y * (1.f - cc.y * cc.y),
-                            dhn.z * uu.z * (1.f - cc.z * cc.z), dhn.w * uu.w * (1.f - cc.w * cc.w));
-          if (a.act == STC_ACT_RELU) {
-            if (!(cc.x > 0.f)) g0v.x = 0.f;
-            if (!(cc.y > 0.f)) g0v.y = 0.f;
-            if (!(cc.z > 0.f)) g0v.z = 0.f;
-            if (!(cc.w > 0.f)) g0v.w = 0.f;
-          }
-          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * p.Kdd + j) = g0v;
-        } else {
-          const float4 hp = *reinterpret_cast<const float4*>(a.Hprev + o);
-          const float4 rr = *reinterpret_cast<const float4*>(a.r + o);
-          const float4 drh = *reinterpret_cast<const float4*>(a.drH + o);
-          g0v = make_float4(dhn.x * (cc.x - hp.x) * uu.x * (1.f - uu.x), dhn.y * (cc.y - hp.y) * uu.y * (1.f - uu.y),
-                            dhn.z * (cc.z - hp.z) * uu.z * (1.f - uu.z), dhn.w * (cc.w - hp.w) * uu.w * (1.f - uu.w));
-          g1v = make_float4(drh.x * hp.x * rr.x * (1.f - rr.x), drh.y * hp.y * rr.y * (1.f - rr.y),
-                            drh.z * hp.z * rr.z * (1.f - rr.z), drh.w * hp.w * rr.w * (1.f - rr.w));
-          if (a.act == STC_ACT_RELU) {
-            if (!(uu.x > 0.5f)) g0v.x = 0.f;
-            if (!(uu.y > 0.5f)) g0v.y = 0.f;
-            if (!(uu.z > 0.5f)) g0v.z = 0.f;
-            if (!(uu.w > 0.5f)) g0v.w = 0.f;
-            if (!(rr.x > 0.5f)) g1v.x = 0.f;
-            if (!(rr.y > 0.5f)) g1v.y = 0.f;
-            if (!(rr.z > 0.5f)) g1v.z = 0.f;
-            if (!(rr.w > 0.5f)) g1v.w = 0.f;
-          }
-          dir = make_float4(dhn.x * (1.f - uu.x) + drh.x * rr.x, dhn.y * (1.f - uu.y) + drh.y * rr.y,
-                            dhn.z * (1.f - uu.z) + drh.z * rr.z, dhn.w * (1.f - uu.w) + drh.w * rr.w);
-          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * p.Kdd + j) = g0v;
-          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * p.Kdd + h + j) = g1v;
-        }
+    auto emit_item = [&](int row, int j, const float4& g0v, const float4& g1v, const float4& dir, bool live) {
+      if (live) {
+        *reinterpret_cast<float4*>(a.dpre + (row0 + row) * p.Kdd + j) = g0v;
+        if (a.phase == 0) *reinterpret_cast<float4*>(a.dpre + (row0 + row) * p.Kdd + h + j) = g1v;
       }
       if (db_fast) {
         dbs0.x += g0v.x; dbs0.y += g0v.y; dbs0.z += g0v.z; dbs0.w += g0v.w;
@@ -182,8 +224,43 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
         *reinterpret_cast<float4*>(Dsm + row * DP + h + j) = g1v;
         *reinterpret_cast<float4*>(Dh + row * h + j) = dir;
       }
+    };
+    if (BATCHED) {   // two items per round: all twelve 16-byte loads in flight before the first use
+      for (int it0 = tid; it0 < 128 * cpr; it0 += 2 * CV_THREADS) {
+        DxIn in[2];
+        int row[2], j[2];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int it = it0 + u * CV_THREADS;
+          row[u] = it / cpr;
+          j[u] = (it - row[u] * cpr) << 2;
+          live[u] = it < 128 * cpr && row[u] < rows_valid;
+          if (live[u]) dx_load(a, (row0 + row[u]) * h + j[u], in[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (it0 + u * CV_THREADS >= 128 * cpr) continue;
+          float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
+          if (live[u]) dx_adjoint(a, in[u], g0v, g1v, dir);
+          emit_item(row[u], j[u], g0v, g1v, dir, live[u]);
+        }
+      }
+    } else {
+      for (int it = tid; it < 128 * cpr; it += CV_THREADS) {
+        const int row = it / cpr, j = (it - row * cpr) << 2;
+        float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
+        const bool live = row < rows_valid;
+        if (live) {
+          DxIn in;
+          dx_load(a, (row0 + row) * h + j, in);
+          dx_adjoint(a, in, g0v, g1v, dir);
+        }
+        emit_item(row, j, g0v, g1v, dir, live);
+      }
     }
     __syncthreads();
+    STC_TRACE(1);
     if (a.dbias && !db_fast && tid < db_groups * Hout) {   // every thread sums a strided slice of rows of its column
       float s = 0.f;
       for (int row = db_grp; row < rows_valid; row += db_groups) s += Dsm[row * DP + db_col];
@@ -221,6 +298,7 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       }
       fence_async_smem();
       __syncthreads();
+      if (ja == 0) STC_TRACE(2);
       if (tid == 0) {
         fence_after_sync();
         const int kleft = p.Kdd - ja * ATOM_K;
@@ -234,6 +312,7 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       acc_small = true;
       mma_pending = true;
     }
+    STC_TRACE(3);
     // ---- 4 (overlaps the MMAs). dQ_c[c'][d] += sum_{node,o} P_c[(node,c')][o] * Ds[(node,d)][o] ----
     if (want_dQ) {
       mbar_wait(load_bar, load_phase);
@@ -289,10 +368,12 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       }
     }
     // ---- 3. epilogue: dY_k tiles ----
+    STC_TRACE(4);
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1u;
     mma_pending = false;
     fence_after_sync();
+    STC_TRACE(5);
     {
       const bool valid = erow < rows_valid;
       const long long gr = row0 + erow;
@@ -350,8 +431,11 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
         }
       }
     }
+    STC_TRACE(6);
     fence_before_sync();
     __syncthreads();  // Dsm / Dh / Psm are rewritten by the next tile's prologue
+    STC_TRACE(7);
+    ++trace_it;
   }
   if (a.dbias && !db_fast && tid < db_groups * Hout) atomicAdd(&a.dbias[db_col], db_acc);
   __syncthreads();   // every tile is done: Dsm is free and serves as the reduction scratch
@@ -421,7 +505,8 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
     set_error("tcgen05 backward tile does not fit (%u B) although the forward ran on the tensor-core path", p.smem_bytes);
     return STC_ERR_UNSUPPORTED;
   }
-  STC_TRY(set_smem(tc_conv_bwd_dx_kernel, p.smem_bytes));
+  const bool batched = (a.opt & OPT_BATCHED_PROLOGUE) != 0;
+  STC_TRY(batched ? set_smem(tc_conv_bwd_dx_kernel<true>, p.smem_bytes) : set_smem(tc_conv_bwd_dx_kernel<false>, p.smem_bytes));
   int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 2) ctas_per_sm = 2;
@@ -435,7 +520,10 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
   ScopedKernelTimer _t(KK_TC_CONV_BWD_DX, st,
                        4.0 * R * ((a.phase == 0 ? 6 * a.h + a.Ks * a.Din : 3 * a.h) + a.Hout + a.Ks * L +
                                   ((a.dQ && a.Kc > 1) ? p.PW : 0)) + 4.0 * a.Ks * a.Kc * L * a.Hout);
-  tc_conv_bwd_dx_kernel<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
+  if (batched)
+    tc_conv_bwd_dx_kernel<true><<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
+  else
+    tc_conv_bwd_dx_kernel<false><<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
   STC_LAUNCH_OK("tc_conv_bwd_dx_kernel");
   *handled = true;
   return STC_OK;

@@ -235,6 +235,11 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
                "r"(bytes)
                : "memory");
 }
+// hint: pull [gsrc, gsrc + bytes) into L2 (no destination, no completion to wait for).  gsrc 16-byte aligned, bytes a
+// multiple of 16.  Used one tile ahead so that the tile's own loads see L2 latency instead of HBM latency.
+__device__ __forceinline__ void l2_prefetch(const void* gsrc, uint32_t bytes) {
+  if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of this thread's committed bulk stores have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

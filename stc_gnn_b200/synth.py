@@ -27,3 +27,42 @@ def sf_supports(seed: int = 0, rows: int = 10, cols: int = 10, C: int = 5):
     ac = torch.sigmoid(torch.randn(C, C, generator=g))
     Gc = ac * Ac + (1 - ac) * Pc
     return Gs.contiguous(), Gc.contiguous()
+
+
+def grid_csr(rows: int, cols: int, scale: float = 1.0 / 8.0):
+    """8-neighbour grid adjacency scaled by `scale`, as CSR (rowptr, col, vals) host tensors."""
+    A = (grid_adjacency(rows, cols) * scale).to_sparse_csr()
+    return A.crow_indices().to(torch.int32), A.col_indices().to(torch.int32), A.values().float()
+
+
+def knn_csr(N: int, k: int = 8, seed: int = 0):
+    """Symmetric k-nearest-neighbour graph of N points ~ U([0,1]^2), values 1/deg(row), nodes in Morton order so that
+    contiguous row blocks are spatially compact.  CSR (rowptr, col, vals) host tensors."""
+    import numpy as np
+    from scipy.spatial import cKDTree
+
+    rng = np.random.default_rng(seed)
+    pts = rng.random((N, 2))
+    q = (pts * 65535).astype(np.uint64)
+
+    def spread(v):
+        v = (v | (v << 16)) & 0x0000FFFF0000FFFF
+        v = (v | (v << 8)) & 0x00FF00FF00FF00FF
+        v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0F
+        v = (v | (v << 2)) & 0x3333333333333333
+        v = (v | (v << 1)) & 0x5555555555555555
+        return v
+
+    order = np.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << 1), kind="stable")
+    pts = pts[order]
+    _, nbr = cKDTree(pts).query(pts, k=k + 1)
+    src = np.repeat(np.arange(N), k)
+    dst = nbr[:, 1:].reshape(-1)
+    a = np.concatenate([src, dst])
+    b = np.concatenate([dst, src])
+    key = np.unique(a.astype(np.int64) * N + b)
+    row, col = key // N, key % N
+    deg = np.bincount(row, minlength=N)
+    rowptr = np.concatenate([[0], np.cumsum(deg)])
+    vals = (1.0 / deg[row]).astype(np.float32)
+    return (torch.from_numpy(rowptr.astype(np.int32)), torch.from_numpy(col.astype(np.int32)), torch.from_numpy(vals))

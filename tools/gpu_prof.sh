@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_gpu_prof.sh TAG KERNEL_REGEX SKIP COUNT [BATCH] -- one --set full capture (with source) of selected kernels
+# usage: tools/gpu_prof.sh TAG KERNEL_REGEX SKIP COUNT [BATCH] -- one --set full capture (with source) of selected kernels
 mkdir -p gpurun_out
 TAG=$1; RX=$2; SKIP=${3:-30}; CNT=${4:-2}; BATCH=${5:-4096}
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$RX" -s $SKIP -c $CNT \

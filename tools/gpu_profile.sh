@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_gpu_profile.sh TAG [BATCH] [list|full|both] -- ncu launch list of one bench command and/or one
+# usage: tools/gpu_profile.sh TAG [BATCH] [list|full|both] -- ncu launch list of one bench command and/or one
 # --set full capture of the tensor-core kernels (skipping warm-up launches).  Outputs -> gpurun_out/
 mkdir -p gpurun_out
 TAG=${1:-r1}; BATCH=${2:-4096}; WHAT=${3:-both}

@@ -2,7 +2,7 @@
 """Per-CUDA-source-line hot spots: joins the SASS page of an .ncu-rep (stall samples, executed instructions
 per SASS instruction) with nvdisasm --print-line-info of the SAME build of libstc_b200.so.
 
-usage: tools_ncu_lines.py report.ncu-rep kernel_regex [launch_index] [top_n]
+usage: tools/ncu_lines.py report.ncu-rep kernel_regex [launch_index] [top_n]
 """
 import collections, csv, glob, io, os, re, subprocess, sys, tempfile
 rep, rx = sys.argv[1], sys.argv[2]

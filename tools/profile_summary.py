@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Summarise ncu outputs brought back in gpurun_out/ into small text files under profiles/.
 
-  python tools_profile_summary.py launches gpurun_out/launches_X.csv profiles/X_launches.txt
-  python tools_profile_summary.py full     gpurun_out/prof_X.ncu-rep profiles/X_ncu_full.txt
+  python tools/profile_summary.py launches gpurun_out/launches_X.csv profiles/X_launches.txt
+  python tools/profile_summary.py full     gpurun_out/prof_X.ncu-rep profiles/X_ncu_full.txt
 """
 import collections
 import csv

@@ -94,7 +94,7 @@ int conv_opt_flags() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("STC_OPT");
-    cached = (e && e[0]) ? (atoi(e) & 0x7fffffff) : 0x7fffffff;
+    cached = (e && e[0]) ? (atoi(e) & 0x7fffffff) : OPT_L2_PREFETCH;   // default: measured-best switches
   }
   return cached;
 }

@@ -36,12 +36,13 @@ struct TcFwdPlan {
   int KB;         // 32-wide atoms per spatial term
   int Ntot;       // Kc * Hout (GEMM N)
   int Npad;       // Ntot rounded up to 16
-  int nacc;       // main accumulators = Ks*KB (one per atom); the cross-term accumulator follows them
+  int nacc;       // atoms along K = Ks*KB
+  int nmain;      // main accumulators = ceil(nacc / TC_APM); the cross-term accumulator follows them
   int tmem_cols;  // power of two
   int ntiles;
   int x_bulk;     // x-part can be staged with bulk copies (16-byte aligned rows)
   int PS;         // row stride (floats) of the epilogue exchange buffer
-  uint32_t off_a, off_b, off_sh, off_sx, off_se, off_q, off_bar, smem_bytes;
+  uint32_t off_a, off_b, off_sh, off_sx, off_se, off_q, off_bias, off_bar, smem_bytes;
 };
 
 // thread 0: stage every spatial term of tile `tile` with bulk copies that complete on `bar`
@@ -108,28 +109,131 @@ __device__ __forceinline__ void tc_prefetch_tile(const ConvArgs& a, const TcFwdP
   if (a.phase != 0) l2_prefetch(a.u + g0 * CH, hb);
 }
 
-// sum of the per-atom partials of 8 accumulator columns starting at column c0 (cross terms first, fp32 RN adds)
-__device__ __forceinline__ void tc_read_acc8(uint32_t tl, const TcFwdPlan& p, int c0, float (&v)[8], bool batched) {
-  if (batched && p.nacc == 2) {   // all three accumulators in flight, one wait; same summation order as below
-    uint32_t t0[8], t1[8], t2[8];
-    tmem_ld8_async(tl + (uint32_t)(2 * p.Npad + c0), t2);
-    tmem_ld8_async(tl + (uint32_t)c0, t0);
+constexpr int TC_APM = 3;  // atoms (4 K-steps each) chained into one main accumulator: 12 K-steps, inside the <= 13
+                           // the accumulate-truncation measurements allow (profiles/r1_tc_precision.txt)
+
+// sum of the partial accumulators of 8 columns starting at column c0 (cross terms first, fp32 RN adds)
+__device__ __forceinline__ void tc_read_acc8(uint32_t tl, const TcFwdPlan& p, int c0, float (&v)[8]) {
+  if (p.nmain == 1) {   // both accumulators in flight, one wait
+    uint32_t t0[8], t1[8];
     tmem_ld8_async(tl + (uint32_t)(p.Npad + c0), t1);
+    tmem_ld8_async(tl + (uint32_t)c0, t0);
     tmem_ld_wait();
-    tmem_ld_pin8(t0); tmem_ld_pin8(t1); tmem_ld_pin8(t2);
+    tmem_ld_pin8(t0); tmem_ld_pin8(t1);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (__uint_as_float(t2[i]) + __uint_as_float(t0[i])) + __uint_as_float(t1[i]);
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(t1[i]) + __uint_as_float(t0[i]);
     return;
   }
   float t[8];
-  tmem_ld8(tl + (uint32_t)(p.nacc * p.Npad + c0), v);
-  for (int m = 0; m < p.nacc; ++m) {
+  tmem_ld8(tl + (uint32_t)(p.nmain * p.Npad + c0), v);
+  for (int m = 0; m < p.nmain; ++m) {
     tmem_ld8(tl + (uint32_t)(m * p.Npad + c0), t);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += t[i];
   }
 }
 
+template <int CPT>
+__device__ __forceinline__ void tmem_ld_cols_async(uint32_t taddr, uint32_t (&r)[CPT]) {
+  static_assert(CPT == 8 || CPT == 16, "8 or 16 columns per thread");
+  if constexpr (CPT == 8) tmem_ld8_async(taddr, r); else tmem_ld16_async(taddr, r);
+}
+template <int CPT>
+__device__ __forceinline__ void tmem_ld_pin(uint32_t (&r)[CPT]) {
+  if constexpr (CPT == 8) tmem_ld_pin8(r); else tmem_ld_pin16(r);
+}
+
+// Epilogue of the common shape (Kc = 2, one main accumulator, Hout = 2 * CPT): each thread owns accumulator row
+// `erow` and CPT CONTIGUOUS output columns [half*CPT, (half+1)*CPT) -- for the gates convolution the lower four
+// warps produce u and the upper four r and r*H, with no divergence inside a warp.  One exchange of the P_1 tile
+// through shared memory (one block-wide barrier) feeds the C x C categorical mix.
+template <int CPT>
+__device__ __forceinline__ void tc_fwd_epilogue_fast(const ConvArgs& a, const TcFwdPlan& p, uint32_t tl, float* Pm,
+                                                     const float* Qs, const float* bias_s, const float* stage_e,
+                                                     int erow, int enode, int ecat, int half, bool valid,
+                                                     long long gr) {
+  const int h = a.h, C = a.C, Hout = a.Hout;
+  const int c0 = half * CPT;
+  uint32_t sm1[CPT], mn1[CPT];
+  tmem_ld_cols_async<CPT>(tl + (uint32_t)(p.Npad + Hout + c0), sm1);     // P_1: cross terms, then main
+  tmem_ld_cols_async<CPT>(tl + (uint32_t)(Hout + c0), mn1);
+  tmem_ld_wait();
+  tmem_ld_pin<CPT>(sm1); tmem_ld_pin<CPT>(mn1);
+  {
+    float t[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) t[i] = __uint_as_float(sm1[i]) + __uint_as_float(mn1[i]);
+    float* pm = Pm + erow * p.PS + c0;
+#pragma unroll
+    for (int i = 0; i < CPT; i += 4) *reinterpret_cast<float4*>(pm + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+    if (a.Psave && valid) {   // backward forms dGc from these partials (no recomputation of the GEMM)
+      float* ps = a.Psave + gr * (long long)Hout + c0;
+#pragma unroll
+      for (int i = 0; i < CPT; i += 4) *reinterpret_cast<float4*>(ps + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+    }
+  }
+  uint32_t sm0[CPT], mn0[CPT];
+  tmem_ld_cols_async<CPT>(tl + (uint32_t)(p.Npad + c0), sm0);            // P_0 travels under the barrier
+  tmem_ld_cols_async<CPT>(tl + (uint32_t)c0, mn0);
+  __syncthreads();
+  tmem_ld_wait();
+  tmem_ld_pin<CPT>(sm0); tmem_ld_pin<CPT>(mn0);
+  float v[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) v[i] = __uint_as_float(sm0[i]) + __uint_as_float(mn0[i]);
+  {
+    const float* pp = Pm + (enode * C) * p.PS + c0;
+    for (int cp = 0; cp < C; ++cp) {
+      const float w = Qs[cp * C + ecat];
+#pragma unroll
+      for (int i = 0; i < CPT; i += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(pp + cp * p.PS + i);
+        v[i] = fmaf(w, x.x, v[i]); v[i + 1] = fmaf(w, x.y, v[i + 1]);
+        v[i + 2] = fmaf(w, x.z, v[i + 2]); v[i + 3] = fmaf(w, x.w, v[i + 3]);
+      }
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int i = 0; i < CPT; i += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+  }
+  if (a.act == STC_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (a.phase == 0) {   // CPT == h: half 0 -> u, half 1 -> r and r*H
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) v[i] = sigmoidf_fast(v[i]);
+    float* dst = (half == 0 ? a.u : a.r) + gr * h;
+#pragma unroll
+    for (int i = 0; i < CPT; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    if (half != 0) {
+      float* drh = a.rH + gr * h;
+#pragma unroll
+      for (int i = 0; i < CPT; i += 4) {
+        const float4 hp = *reinterpret_cast<const float4*>(stage_e + erow * h + i);
+        *reinterpret_cast<float4*>(drh + i) = make_float4(v[i] * hp.x, v[i + 1] * hp.y, v[i + 2] * hp.z, v[i + 3] * hp.w);
+      }
+    }
+  } else {              // 2 * CPT == h: c = tanh, H' = H + u (c - H)
+    const long long o = gr * h + c0;
+#pragma unroll
+    for (int i = 0; i < CPT; i += 4) {
+      const float4 uu = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + c0 + i);
+      const float4 hp = *reinterpret_cast<const float4*>(stage_e + erow * h + c0 + i);
+      const float4 cc = make_float4(tanhf_fast(v[i]), tanhf_fast(v[i + 1]), tanhf_fast(v[i + 2]), tanhf_fast(v[i + 3]));
+      *reinterpret_cast<float4*>(a.c + o + i) = cc;
+      *reinterpret_cast<float4*>(a.Hnew + o + i) =
+          make_float4(fmaf(uu.x, cc.x - hp.x, hp.x), fmaf(uu.y, cc.y - hp.y, hp.y), fmaf(uu.z, cc.z - hp.z, hp.z),
+                      fmaf(uu.w, cc.w - hp.w, hp.w));
+    }
+  }
+}
+
+// CPT = 0: general epilogue (any Kc, any Hout % 16 == 0); CPT = 8 / 16: tc_fwd_epilogue_fast
+template <int CPT>
 __global__ void __launch_bounds__(CV_THREADS, 2)
 tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -146,6 +250,7 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   float* stage_h = reinterpret_cast<float*>(smem + p.off_sh);   // [Ks][128][h]
   float* stage_x = reinterpret_cast<float*>(smem + p.off_sx);   // [Ks][128][Din]
   float* Qs = reinterpret_cast<float*>(smem + p.off_q);         // [(Kc-1)][C][C]
+  float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);  // [Hout] (zeros without a bias)
   float* stage_e = reinterpret_cast<float*>(smem + p.off_se);   // [2][128][h]: H tile, u tile (epilogue operands)
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint64_t* load_bar = mma_bar + 1;
@@ -161,6 +266,7 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   }
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   for (int i = tid; i < (a.Kc - 1) * C * C; i += CV_THREADS) Qs[i] = a.Q[C * C + i];
+  for (int i = tid; i < Hout; i += CV_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
   for (int i = tid; i < a.Ks * 128 * h; i += CV_THREADS) stage_h[i] = 0.f;
   for (int i = tid; i < a.Ks * 128 * Din; i += CV_THREADS) stage_x[i] = 0.f;
   // resident B atoms: Bt[(c,o)][kb] = W[((k*Kc + c)*L + l(kb))*Hout + o]
@@ -187,16 +293,19 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t idesc = make_idesc_tf32(128, p.Npad);
-  const uint32_t d_small = tmem_base + (uint32_t)(p.nacc * p.Npad);
+  const uint32_t d_small = tmem_base + (uint32_t)(p.nmain * p.Npad);
   const long long total_nodes = (long long)a.B * a.N;
   const long long R = total_nodes * C;
+  // operand descriptors are launch constants: only the 16-byte-granular address field moves (K-step: +32 B, atom: +atomB)
+  const uint64_t dA_hi = make_smem_desc_sw128(smem_u32(A_hi)), dA_lo = make_smem_desc_sw128(smem_u32(A_lo));
+  const uint64_t dB_hi = make_smem_desc_sw128(smem_u32(B_hi)), dB_lo = make_smem_desc_sw128(smem_u32(B_lo));
 
   // build mapping: this thread always writes chunk column q of rows r0 + 32 i
   const int q = tid & 7, r0 = tid >> 3;
   uint32_t aoff[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) aoff[i] = atom_chunk_offset(r0 + 32 * i, q);
-  // epilogue mapping: this thread owns accumulator row erow and every second 8-column chunk
+  // epilogue mapping: this thread owns accumulator row erow (and, general path, every second 8-column chunk)
   const int lane_base = (warp & 3) * 32, half = warp >> 2;
   const int erow = lane_base + lane;
   const int enode = erow / C, ecat = erow - enode * C;
@@ -204,22 +313,22 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
 
   uint32_t mma_phase = 0, load_phase = 0, epi_phase = 0;
   bool mma_pending = false;
-  const bool batched_ld = (a.opt & OPT_ASYNC_TMEM_LD) != 0;
   const bool tracing = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
   int trace_it = 0;
-  if (tid == 0 && (int)blockIdx.x < p.ntiles) tc_issue_tile_loads(a, p, blockIdx.x, stage_h, stage_x, load_bar);
+  // thread 32 (warp 1) owns every bulk copy and prefetch; thread 0 (warp 0) only issues MMAs
+  if (tid == 32 && (int)blockIdx.x < p.ntiles) tc_issue_tile_loads(a, p, blockIdx.x, stage_h, stage_x, load_bar);
 
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long g0 = (long long)tile * p.npt;
     const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
     const int rows_valid = nodes_valid * C;
     STC_TRACE(0);
-    if ((a.opt & OPT_L2_PREFETCH) && tid == 32 && tile + (int)gridDim.x < p.ntiles) tc_prefetch_tile(a, p, tile + gridDim.x);
-    if (tid == 0) {  // the epilogue's own operands (H, and u for the candidate) travel under the builds and the MMAs
+    if (tid == 32) {  // the epilogue's own operands (H, and u for the candidate) travel under the builds and the MMAs
       const uint32_t eb = (uint32_t)(rows_valid * h * 4);
       mbar_arrive_expect_tx(epi_bar, a.phase == 0 ? eb : 2 * eb);
       bulk_g2s(stage_e, a.Hprev + g0 * C * h, eb, epi_bar);
       if (a.phase != 0) bulk_g2s(stage_e + 128 * h, a.u + g0 * C * h, eb, epi_bar);
+      if ((a.opt & OPT_L2_PREFETCH) && tile + (int)gridDim.x < p.ntiles) tc_prefetch_tile(a, p, tile + gridDim.x);
     }
     mbar_wait(load_bar, load_phase);
     load_phase ^= 1u;
@@ -256,14 +365,13 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
           if (ai == p.nacc - 1) STC_TRACE(3);
         }
         const int kb = j * ATOM_K + q * 4;
-        if (kb < h) {
+        const bool from_h = kb < h;
+        if (from_h || (p.x_bulk && kb - h < Din)) {   // whole 16-byte chunks of the h-part or of an aligned x-part: one path
+          const float* bp = from_h ? sh + kb : sx + (kb - h);
+          const int st = from_h ? h : Din;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            store_split4(A_hi, A_lo, aoff[i], *reinterpret_cast<const float4*>(sh + (r0 + 32 * i) * h + kb));
-        } else if (p.x_bulk && kb - h < Din) {  // Din % 4 == 0: whole chunks
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            store_split4(A_hi, A_lo, aoff[i], *reinterpret_cast<const float4*>(sx + (r0 + 32 * i) * Din + (kb - h)));
+            store_split4(A_hi, A_lo, aoff[i], *reinterpret_cast<const float4*>(bp + (r0 + 32 * i) * st));
         } else {
           const int xi = kb - h;
 #pragma unroll
@@ -279,17 +387,25 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
         fence_async_smem();
         __syncthreads();
         if (ai == 0) STC_TRACE(2);
+        // the stage is dead after the last build of this tile: fetch the next tile under the MMAs + epilogue
+        if (tid == 32 && ai == p.nacc - 1 && tile + (int)gridDim.x < p.ntiles)
+          tc_issue_tile_loads(a, p, tile + gridDim.x, stage_h, stage_x, load_bar);
         if (tid == 0) {
-          // the stage is dead after the last build of this tile: prefetch the next tile under the MMAs + epilogue
-          if (ai == p.nacc - 1 && tile + (int)gridDim.x < p.ntiles)
-            tc_issue_tile_loads(a, p, tile + gridDim.x, stage_h, stage_x, load_bar);
           fence_after_sync();
           const int kleft = p.KBL - j * ATOM_K;
           const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
-          const size_t bofs = (size_t)ai * atomB;
-          bool acc_main = false;
-          mma_atom_3x_split(tmem_base + (uint32_t)(ai * p.Npad), d_small, smem_u32(A_hi), smem_u32(A_lo),
-                            smem_u32(B_hi + bofs), smem_u32(B_lo + bofs), ksteps, idesc, acc_main, acc_small);
+          const uint64_t bo = (uint64_t)(((uint32_t)ai * atomB) >> 4);
+          const uint32_t d_main = tmem_base + (uint32_t)((ai / TC_APM) * p.Npad);
+          uint32_t acc_main = (ai % TC_APM) != 0 ? 1u : 0u;
+#pragma unroll 4
+          for (int ks = 0; ks < ksteps; ++ks) {   // small cross terms into their own accumulator, then the main product
+            const uint64_t ko = (uint64_t)(ks * 2);
+            mma_tf32(d_small, dA_lo + ko, dB_hi + bo + ko, idesc, acc_small ? 1u : 0u);
+            mma_tf32(d_small, dA_hi + ko, dB_lo + bo + ko, idesc, 1u);
+            mma_tf32(d_main, dA_hi + ko, dB_hi + bo + ko, idesc, acc_main);
+            acc_main = 1u;
+            acc_small = true;
+          }
           mma_commit(mma_bar);
         }
         acc_small = true;
@@ -308,74 +424,78 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
     STC_TRACE(6);
     const bool valid = erow < rows_valid;
     const long long gr = g0 * C + erow;
-    for (int c0 = half * 8; c0 < Hout; c0 += 16) {
-      float v[8];
-      tc_read_acc8(tl, p, c0, v, batched_ld);                       // P_0
-      for (int c = 1; c < a.Kc; ++c) {                              // + T_c(Gc)^T-mix of P_c over the node's categories
-        float t[8];
-        tc_read_acc8(tl, p, c * Hout + c0, t, batched_ld);
-        __syncthreads();                                            // previous users of Pm are done
-        *reinterpret_cast<float4*>(Pm + erow * p.PS + c0) = make_float4(t[0], t[1], t[2], t[3]);
-        *reinterpret_cast<float4*>(Pm + erow * p.PS + c0 + 4) = make_float4(t[4], t[5], t[6], t[7]);
-        if (a.Psave && valid) {  // backward forms dGc from these partials (no recomputation of the GEMM)
-          float4* ps = reinterpret_cast<float4*>(a.Psave + gr * (long long)((a.Kc - 1) * Hout) + (c - 1) * Hout + c0);
-          ps[0] = make_float4(t[0], t[1], t[2], t[3]);
-          ps[1] = make_float4(t[4], t[5], t[6], t[7]);
+    if constexpr (CPT != 0) {
+      tc_fwd_epilogue_fast<CPT>(a, p, tl, Pm, Qs, bias_s, stage_e, erow, enode, ecat, half, valid, gr);
+    } else {
+      for (int c0 = half * 8; c0 < Hout; c0 += 16) {
+        float v[8];
+        tc_read_acc8(tl, p, c0, v);                                   // P_0
+        for (int c = 1; c < a.Kc; ++c) {                              // + T_c(Gc)^T-mix of P_c over the node's categories
+          float t[8];
+          tc_read_acc8(tl, p, c * Hout + c0, t);
+          __syncthreads();                                            // previous users of Pm are done
+          *reinterpret_cast<float4*>(Pm + erow * p.PS + c0) = make_float4(t[0], t[1], t[2], t[3]);
+          *reinterpret_cast<float4*>(Pm + erow * p.PS + c0 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+          if (a.Psave && valid) {  // backward forms dGc from these partials (no recomputation of the GEMM)
+            float4* ps = reinterpret_cast<float4*>(a.Psave + gr * (long long)((a.Kc - 1) * Hout) + (c - 1) * Hout + c0);
+            ps[0] = make_float4(t[0], t[1], t[2], t[3]);
+            ps[1] = make_float4(t[4], t[5], t[6], t[7]);
+          }
+          __syncthreads();
+          const float* Qc = Qs + (size_t)(c - 1) * C * C;
+          const float* pp = Pm + (enode * C) * p.PS + c0;
+          for (int cp = 0; cp < C; ++cp) {
+            const float w = Qc[cp * C + ecat];
+            const float4 x0 = *reinterpret_cast<const float4*>(pp + cp * p.PS);
+            const float4 x1 = *reinterpret_cast<const float4*>(pp + cp * p.PS + 4);
+            v[0] = fmaf(w, x0.x, v[0]); v[1] = fmaf(w, x0.y, v[1]); v[2] = fmaf(w, x0.z, v[2]); v[3] = fmaf(w, x0.w, v[3]);
+            v[4] = fmaf(w, x1.x, v[4]); v[5] = fmaf(w, x1.y, v[5]); v[6] = fmaf(w, x1.z, v[6]); v[7] = fmaf(w, x1.w, v[7]);
+          }
         }
-        __syncthreads();
-        const float* Qc = Qs + (size_t)(c - 1) * C * C;
-        const float* pp = Pm + (enode * C) * p.PS + c0;
-        for (int cp = 0; cp < C; ++cp) {
-          const float w = Qc[cp * C + ecat];
-          const float4 x0 = *reinterpret_cast<const float4*>(pp + cp * p.PS);
-          const float4 x1 = *reinterpret_cast<const float4*>(pp + cp * p.PS + 4);
-          v[0] = fmaf(w, x0.x, v[0]); v[1] = fmaf(w, x0.y, v[1]); v[2] = fmaf(w, x0.z, v[2]); v[3] = fmaf(w, x0.w, v[3]);
-          v[4] = fmaf(w, x1.x, v[4]); v[5] = fmaf(w, x1.y, v[5]); v[6] = fmaf(w, x1.z, v[6]); v[7] = fmaf(w, x1.w, v[7]);
-        }
-      }
-      if (!valid) continue;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float pre = v[i] + (a.bias ? a.bias[c0 + i] : 0.f);
-        if (a.act == STC_ACT_RELU) pre = fmaxf(pre, 0.f);
-        v[i] = pre;
-      }
-      if (a.phase == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = sigmoidf_fast(v[i]);
-        if (c0 < h) {
-          float4* dst = reinterpret_cast<float4*>(a.u + gr * h + c0);
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        } else {
-          const long long o = gr * h + (c0 - h);
-          const float4 h0 = *reinterpret_cast<const float4*>(stage_e + erow * h + (c0 - h));
-          const float4 h1 = *reinterpret_cast<const float4*>(stage_e + erow * h + (c0 - h) + 4);
-          float4* dr = reinterpret_cast<float4*>(a.r + o);
-          dr[0] = make_float4(v[0], v[1], v[2], v[3]);
-          dr[1] = make_float4(v[4], v[5], v[6], v[7]);
-          float4* drh = reinterpret_cast<float4*>(a.rH + o);
-          drh[0] = make_float4(v[0] * h0.x, v[1] * h0.y, v[2] * h0.z, v[3] * h0.w);
-          drh[1] = make_float4(v[4] * h1.x, v[5] * h1.y, v[6] * h1.z, v[7] * h1.w);
-        }
-      } else {
-        const long long o = gr * h + c0;
-        float uu[8], hp[8], cc[8], hn[8];
-        *reinterpret_cast<float4*>(uu) = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + c0);
-        *reinterpret_cast<float4*>(uu + 4) = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + c0 + 4);
-        *reinterpret_cast<float4*>(hp) = *reinterpret_cast<const float4*>(stage_e + erow * h + c0);
-        *reinterpret_cast<float4*>(hp + 4) = *reinterpret_cast<const float4*>(stage_e + erow * h + c0 + 4);
+        if (!valid) continue;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          cc[i] = tanhf_fast(v[i]);
-          hn[i] = fmaf(uu[i], cc[i] - hp[i], hp[i]);
+          float pre = v[i] + bias_s[c0 + i];
+          if (a.act == STC_ACT_RELU) pre = fmaxf(pre, 0.f);
+          v[i] = pre;
         }
-        float4* dc = reinterpret_cast<float4*>(a.c + o);
-        dc[0] = make_float4(cc[0], cc[1], cc[2], cc[3]);
-        dc[1] = make_float4(cc[4], cc[5], cc[6], cc[7]);
-        float4* dh = reinterpret_cast<float4*>(a.Hnew + o);
-        dh[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        dh[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        if (a.phase == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = sigmoidf_fast(v[i]);
+          if (c0 < h) {
+            float4* dst = reinterpret_cast<float4*>(a.u + gr * h + c0);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            const long long o = gr * h + (c0 - h);
+            const float4 h0 = *reinterpret_cast<const float4*>(stage_e + erow * h + (c0 - h));
+            const float4 h1 = *reinterpret_cast<const float4*>(stage_e + erow * h + (c0 - h) + 4);
+            float4* dr = reinterpret_cast<float4*>(a.r + o);
+            dr[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dr[1] = make_float4(v[4], v[5], v[6], v[7]);
+            float4* drh = reinterpret_cast<float4*>(a.rH + o);
+            drh[0] = make_float4(v[0] * h0.x, v[1] * h0.y, v[2] * h0.z, v[3] * h0.w);
+            drh[1] = make_float4(v[4] * h1.x, v[5] * h1.y, v[6] * h1.z, v[7] * h1.w);
+          }
+        } else {
+          const long long o = gr * h + c0;
+          float uu[8], hp[8], cc[8], hn[8];
+          *reinterpret_cast<float4*>(uu) = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + c0);
+          *reinterpret_cast<float4*>(uu + 4) = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + c0 + 4);
+          *reinterpret_cast<float4*>(hp) = *reinterpret_cast<const float4*>(stage_e + erow * h + c0);
+          *reinterpret_cast<float4*>(hp + 4) = *reinterpret_cast<const float4*>(stage_e + erow * h + c0 + 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            cc[i] = tanhf_fast(v[i]);
+            hn[i] = fmaf(uu[i], cc[i] - hp[i], hp[i]);
+          }
+          float4* dc = reinterpret_cast<float4*>(a.c + o);
+          dc[0] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+          dc[1] = make_float4(cc[4], cc[5], cc[6], cc[7]);
+          float4* dh = reinterpret_cast<float4*>(a.Hnew + o);
+          dh[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          dh[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        }
       }
     }
     STC_TRACE(7);
@@ -440,8 +560,9 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
   p.Npad = (p.Ntot + 15) & ~15;
   if (p.Npad > 256) return STC_OK;
   p.nacc = a.Ks * p.KB;
+  p.nmain = (p.nacc + TC_APM - 1) / TC_APM;
   p.tmem_cols = 32;
-  while (p.tmem_cols < (p.nacc + 1) * p.Npad) p.tmem_cols *= 2;
+  while (p.tmem_cols < (p.nmain + 1) * p.Npad) p.tmem_cols *= 2;
   if (p.tmem_cols > 512) return STC_OK;
   p.PS = a.Hout + 4;
   if ((size_t)128 * p.PS * sizeof(float) > 2 * 128 * ATOM_ROW_BYTES) return STC_OK;  // exchange buffer aliases A
@@ -457,10 +578,17 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
   p.off_se = (uint32_t)o; o += (size_t)2 * 128 * a.h * sizeof(float);
   p.off_q = (uint32_t)o; o += (size_t)(a.Kc > 1 ? a.Kc - 1 : 0) * a.C * a.C * sizeof(float);
   o = round_up(o, 16);
+  p.off_bias = (uint32_t)o; o += (size_t)a.Hout * sizeof(float);
+  o = round_up(o, 16);
   p.off_bar = (uint32_t)o; o += 48;
   p.smem_bytes = (uint32_t)o;
   if (p.smem_bytes > 200 * 1024) return STC_OK;  // not an SF-class shape: the FFMA path handles it
-  STC_TRY(set_smem(tc_conv_fwd_kernel, p.smem_bytes));
+  // contiguous-column epilogue: Kc = 2, one main accumulator, and a thread's CPT = Hout/2 columns are 8 or 16 wide
+  // (gates: CPT = h, candidate: CPT = h/2)
+  int cpt = 0;
+  if (a.Kc == 2 && p.nmain == 1 && (a.Hout == 16 || a.Hout == 32) && !(a.opt & OPT_GENERIC_EPILOGUE)) cpt = a.Hout / 2;
+  auto kern = cpt == 16 ? tc_conv_fwd_kernel<16> : (cpt == 8 ? tc_conv_fwd_kernel<8> : tc_conv_fwd_kernel<0>);
+  STC_TRY(set_smem(kern, p.smem_bytes));
   int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 2) ctas_per_sm = 2;
@@ -470,7 +598,7 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
   const double R = (double)total_nodes * a.C;
   ScopedKernelTimer _t(KK_TC_CONV_FWD, st,
                        4.0 * R * (a.Ks * L + (a.phase == 0 ? 3 * a.h : 4 * a.h)) + 4.0 * P * L * a.Hout);
-  tc_conv_fwd_kernel<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
+  kern<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
   STC_LAUNCH_OK("tc_conv_fwd_kernel");
   *handled = true;
   return STC_OK;

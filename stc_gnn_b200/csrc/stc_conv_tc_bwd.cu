@@ -16,12 +16,15 @@ namespace stc {
 
 using namespace tc;
 
+constexpr int DX_APM = 3;  // atoms chained into one main accumulator (12 K-steps; see TC_APM in stc_conv_tc.cu)
+
 struct TcDxPlan {
   int npt, Dp, KBL;
   int N1;         // Ks * KBL  (GEMM N: every spatial term's [h | x] block)
   int Npad;       // N1 rounded up to 16
   int Kdd;        // Kc * Hout (GEMM K)
   int KA;         // 32-wide atoms along K
+  int nmain;      // main accumulators = ceil(KA / DX_APM); the cross-term accumulator follows them
   int tmem_cols, ntiles;
   int DP;         // row stride of the plain Ds tile (floats)
   int PW;         // (Kc-1) * Hout: width of the saved partial-output tile
@@ -102,7 +105,8 @@ __device__ __forceinline__ void dx_prefetch_tile(const ConvArgs& a, const TcDxPl
   }
 }
 
-template <bool BATCHED>
+// FAST: contiguous-column epilogue of the common shape (Ks = 2, h = 16, Din <= 16, one main accumulator)
+template <bool FAST>
 __global__ void __launch_bounds__(CV_THREADS, 2)
 tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -159,7 +163,10 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t idesc = make_idesc_tf32(128, p.Npad);
-  const uint32_t d_small = tmem_base + (uint32_t)(p.KA * p.Npad);
+  const uint32_t d_small = tmem_base + (uint32_t)(p.nmain * p.Npad);
+  // operand descriptors are launch constants: only the 16-byte-granular address field moves (K-step: +32 B, atom: +atomB)
+  const uint64_t dA_hi = make_smem_desc_sw128(smem_u32(A_hi)), dA_lo = make_smem_desc_sw128(smem_u32(A_lo));
+  const uint64_t dB_hi = make_smem_desc_sw128(smem_u32(B_hi)), dB_lo = make_smem_desc_sw128(smem_u32(B_lo));
   const long long total_nodes = (long long)a.B * a.N;
   const long long R = total_nodes * C;
 
@@ -200,14 +207,15 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
     const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
     const int rows_valid = nodes_valid * C;
     const long long row0 = g0 * C;
-    if (want_dQ && tid == 0) {  // stage the saved partial outputs of this tile while the prologue runs
-      const uint32_t bytes = (uint32_t)(rows_valid * p.PW * 4);
-      mbar_arrive_expect_tx(load_bar, bytes);
-      bulk_g2s(Psm, a.Psave + row0 * p.PW, bytes, load_bar);
+    if (tid == 32) {  // thread 32 owns the bulk copy and the prefetches, thread 0 only issues MMAs
+      if (want_dQ) {  // stage the saved partial outputs of this tile while the prologue runs
+        const uint32_t bytes = (uint32_t)(rows_valid * p.PW * 4);
+        mbar_arrive_expect_tx(load_bar, bytes);
+        bulk_g2s(Psm, a.Psave + row0 * p.PW, bytes, load_bar);
+      }
+      if ((a.opt & OPT_L2_PREFETCH) && tile + (int)gridDim.x < p.ntiles) dx_prefetch_tile(a, p, tile + gridDim.x, want_dQ);
     }
     STC_TRACE(0);
-    if ((a.opt & OPT_L2_PREFETCH) && tid == 32 && tile + (int)gridDim.x < p.ntiles)
-      dx_prefetch_tile(a, p, tile + gridDim.x, want_dQ);
     // ---- 1. elementwise adjoint: one float4 of hidden channels per item ----
     const int cpr = h >> 2;
     auto emit_item = [&](int row, int j, const float4& g0v, const float4& g1v, const float4& dir, bool live) {
@@ -225,39 +233,16 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
         *reinterpret_cast<float4*>(Dh + row * h + j) = dir;
       }
     };
-    if (BATCHED) {   // two items per round: all twelve 16-byte loads in flight before the first use
-      for (int it0 = tid; it0 < 128 * cpr; it0 += 2 * CV_THREADS) {
-        DxIn in[2];
-        int row[2], j[2];
-        bool live[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int it = it0 + u * CV_THREADS;
-          row[u] = it / cpr;
-          j[u] = (it - row[u] * cpr) << 2;
-          live[u] = it < 128 * cpr && row[u] < rows_valid;
-          if (live[u]) dx_load(a, (row0 + row[u]) * h + j[u], in[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (it0 + u * CV_THREADS >= 128 * cpr) continue;
-          float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
-          if (live[u]) dx_adjoint(a, in[u], g0v, g1v, dir);
-          emit_item(row[u], j[u], g0v, g1v, dir, live[u]);
-        }
+    for (int it = tid; it < 128 * cpr; it += CV_THREADS) {
+      const int row = it / cpr, j = (it - row * cpr) << 2;
+      float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
+      const bool live = row < rows_valid;
+      if (live) {
+        DxIn in;
+        dx_load(a, (row0 + row) * h + j, in);
+        dx_adjoint(a, in, g0v, g1v, dir);
       }
-    } else {
-      for (int it = tid; it < 128 * cpr; it += CV_THREADS) {
-        const int row = it / cpr, j = (it - row * cpr) << 2;
-        float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
-        const bool live = row < rows_valid;
-        if (live) {
-          DxIn in;
-          dx_load(a, (row0 + row) * h + j, in);
-          dx_adjoint(a, in, g0v, g1v, dir);
-        }
-        emit_item(row, j, g0v, g1v, dir, live);
-      }
+      emit_item(row, j, g0v, g1v, dir, live);
     }
     __syncthreads();
     STC_TRACE(1);
@@ -269,13 +254,9 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
     // ---- 2. DD atoms + MMAs ----
     bool acc_small = false;
     for (int ja = 0; ja < p.KA; ++ja) {
-      if (mma_pending) {
-        mbar_wait(mma_bar, mma_phase);
-        mma_phase ^= 1u;
-        mma_pending = false;
-      }
       const int kk = ja * ATOM_K + q * 4;
       const int c = kk / Hout, o0 = kk - c * Hout;
+      float4 vv[4];   // the atom's values are formed while the previous atom's MMAs still read the single A buffer
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -294,8 +275,15 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
               *reinterpret_cast<float4*>(a.dpre + (row0 + r0 + 32 * i) * p.Kdd + kk) = v;
           }
         }
-        store_split4(A_hi, A_lo, aoff[i], v);
+        vv[i] = v;
       }
+      if (mma_pending) {
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1u;
+        mma_pending = false;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) store_split4(A_hi, A_lo, aoff[i], vv[i]);
       fence_async_smem();
       __syncthreads();
       if (ja == 0) STC_TRACE(2);
@@ -303,10 +291,18 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
         fence_after_sync();
         const int kleft = p.Kdd - ja * ATOM_K;
         const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
-        bool acc_main = false;
-        mma_atom_3x_split(tmem_base + (uint32_t)(ja * p.Npad), d_small, smem_u32(A_hi), smem_u32(A_lo),
-                          smem_u32(B_hi + (size_t)ja * atomB), smem_u32(B_lo + (size_t)ja * atomB), ksteps, idesc,
-                          acc_main, acc_small);
+        const uint64_t bo = (uint64_t)(((uint32_t)ja * atomB) >> 4);
+        const uint32_t d_main = tmem_base + (uint32_t)((ja / DX_APM) * p.Npad);
+        uint32_t acc_main = (ja % DX_APM) != 0 ? 1u : 0u;
+#pragma unroll 4
+        for (int ks = 0; ks < ksteps; ++ks) {   // small cross terms into their own accumulator, then the main product
+          const uint64_t ko = (uint64_t)(ks * 2);
+          mma_tf32(d_small, dA_lo + ko, dB_hi + bo + ko, idesc, acc_small ? 1u : 0u);
+          mma_tf32(d_small, dA_hi + ko, dB_lo + bo + ko, idesc, 1u);
+          mma_tf32(d_main, dA_hi + ko, dB_hi + bo + ko, idesc, acc_main);
+          acc_main = 1u;
+          acc_small = true;
+        }
         mma_commit(mma_bar);
       }
       acc_small = true;
@@ -374,25 +370,99 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
     mma_pending = false;
     fence_after_sync();
     STC_TRACE(5);
-    {
-      const bool valid = erow < rows_valid;
-      const long long gr = row0 + erow;
+    const bool valid = erow < rows_valid;
+    const long long gr = row0 + erow;
+    if constexpr (FAST) {
+      // thread (erow, half) owns spatial term k = half: columns [k*KBL, k*KBL + 16) are its h-part, the next Dp its x-part
+      const int k = half;
+      const uint32_t nb = (uint32_t)(k * p.KBL);
+      {
+        uint32_t sm[16], mn[16];
+        tmem_ld16_async(tl + (uint32_t)p.Npad + nb, sm);
+        tmem_ld16_async(tl + nb, mn);
+        tmem_ld_wait();
+        tmem_ld_pin16(sm); tmem_ld_pin16(mn);
+        if (valid) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(sm[i]) + __uint_as_float(mn[i]);
+          if (k == 0 && a.phase == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 d = *reinterpret_cast<const float4*>(Dh + erow * 16 + i);
+              v[i] += d.x; v[i + 1] += d.y; v[i + 2] += d.z; v[i + 3] += d.w;
+            }
+          }
+          float* dst = (k == 0 ? a.dYh0 : a.dYh) + gr * 16;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+      float* dbase = (k == 0 ? a.dYx0 : a.dYx);
+      {
+        uint32_t sm[16], mn[16];
+        if (p.Dp == 16) {
+          tmem_ld16_async(tl + (uint32_t)p.Npad + nb + 16u, sm);
+          tmem_ld16_async(tl + nb + 16u, mn);
+          tmem_ld_wait();
+          tmem_ld_pin16(sm); tmem_ld_pin16(mn);
+        } else {   // Dp == 8
+          uint32_t s8[8], m8[8];
+          tmem_ld8_async(tl + (uint32_t)p.Npad + nb + 16u, s8);
+          tmem_ld8_async(tl + nb + 16u, m8);
+          tmem_ld_wait();
+          tmem_ld_pin8(s8); tmem_ld_pin8(m8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { sm[i] = s8[i]; mn[i] = m8[i]; sm[i + 8] = 0u; mn[i + 8] = 0u; }
+        }
+        if (valid && dbase != nullptr) {
+          float* dst = dbase + gr * Din;
+          if (p.x_vec) {   // Din % 4 == 0: 16-byte read-modify-writes, every read in flight before the first add
+            float4 o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o[i] = make_float4(__uint_as_float(sm[4 * i]) + __uint_as_float(mn[4 * i]),
+                                 __uint_as_float(sm[4 * i + 1]) + __uint_as_float(mn[4 * i + 1]),
+                                 __uint_as_float(sm[4 * i + 2]) + __uint_as_float(mn[4 * i + 2]),
+                                 __uint_as_float(sm[4 * i + 3]) + __uint_as_float(mn[4 * i + 3]));
+            if (a.accum_x) {
+              float4 pv[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (4 * i < Din) pv[i] = *reinterpret_cast<const float4*>(dst + 4 * i);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (4 * i < Din) { o[i].x += pv[i].x; o[i].y += pv[i].y; o[i].z += pv[i].z; o[i].w += pv[i].w; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (4 * i < Din) *reinterpret_cast<float4*>(dst + 4 * i) = o[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < Din) {
+                const float vi = __uint_as_float(sm[i]) + __uint_as_float(mn[i]);
+                dst[i] = a.accum_x ? dst[i] + vi : vi;
+              }
+          }
+        }
+      }
+    } else {
       int k = 0, kb = half * 8;                      // (spatial term, column within its [h | x] block) of chunk n0
       for (int n0 = half * 8; n0 < p.Npad; n0 += 16, kb += 16) {
         float v[8];
-        if (p.KA == 2) {                               // the common case: all three accumulators in flight, one wait
-          uint32_t t0[8], t1[8], t2[8];
-          tmem_ld8_async(tl + (uint32_t)(2 * p.Npad + n0), t2);
-          tmem_ld8_async(tl + (uint32_t)n0, t0);
+        if (p.nmain == 1) {                            // the common case: both accumulators in flight, one wait
+          uint32_t t0[8], t1[8];
           tmem_ld8_async(tl + (uint32_t)(p.Npad + n0), t1);
+          tmem_ld8_async(tl + (uint32_t)n0, t0);
           tmem_ld_wait();
-          tmem_ld_pin8(t0); tmem_ld_pin8(t1); tmem_ld_pin8(t2);
+          tmem_ld_pin8(t0); tmem_ld_pin8(t1);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = (__uint_as_float(t2[i]) + __uint_as_float(t0[i])) + __uint_as_float(t1[i]);
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(t1[i]) + __uint_as_float(t0[i]);
         } else {
           float t[8];
-          tmem_ld8(tl + (uint32_t)(p.KA * p.Npad + n0), v);
-          for (int m = 0; m < p.KA; ++m) {
+          tmem_ld8(tl + (uint32_t)(p.nmain * p.Npad + n0), v);
+          for (int m = 0; m < p.nmain; ++m) {
             tmem_ld8(tl + (uint32_t)(m * p.Npad + n0), t);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += t[i];
@@ -433,6 +503,7 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
     }
     STC_TRACE(6);
     fence_before_sync();
+    fence_async_smem();   // this tile's reads of Psm precede the next tile's bulk copy into it
     __syncthreads();  // Dsm / Dh / Psm are rewritten by the next tile's prologue
     STC_TRACE(7);
     ++trace_it;
@@ -483,8 +554,9 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
   p.Npad = (p.N1 + 15) & ~15;
   p.Kdd = a.Kc * a.Hout;
   p.KA = (p.Kdd + ATOM_K - 1) / ATOM_K;
+  p.nmain = (p.KA + DX_APM - 1) / DX_APM;
   p.tmem_cols = 32;
-  while (p.tmem_cols < (p.KA + 1) * p.Npad) p.tmem_cols *= 2;
+  while (p.tmem_cols < (p.nmain + 1) * p.Npad) p.tmem_cols *= 2;
   p.DP = a.Hout + 4;
   p.PW = (a.Kc - 1) * a.Hout;
   p.x_vec = (a.Din % 4 == 0) && aligned16b(a.dYx0) && aligned16b(a.dYx);
@@ -505,8 +577,8 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
     set_error("tcgen05 backward tile does not fit (%u B) although the forward ran on the tensor-core path", p.smem_bytes);
     return STC_ERR_UNSUPPORTED;
   }
-  const bool batched = (a.opt & OPT_BATCHED_PROLOGUE) != 0;
-  STC_TRY(batched ? set_smem(tc_conv_bwd_dx_kernel<true>, p.smem_bytes) : set_smem(tc_conv_bwd_dx_kernel<false>, p.smem_bytes));
+  const bool fast = a.Ks == 2 && a.h == 16 && a.Din <= 16 && p.nmain == 1 && !(a.opt & OPT_GENERIC_EPILOGUE);
+  STC_TRY(fast ? set_smem(tc_conv_bwd_dx_kernel<true>, p.smem_bytes) : set_smem(tc_conv_bwd_dx_kernel<false>, p.smem_bytes));
   int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 2) ctas_per_sm = 2;
@@ -520,7 +592,7 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
   ScopedKernelTimer _t(KK_TC_CONV_BWD_DX, st,
                        4.0 * R * ((a.phase == 0 ? 6 * a.h + a.Ks * a.Din : 3 * a.h) + a.Hout + a.Ks * L +
                                   ((a.dQ && a.Kc > 1) ? p.PW : 0)) + 4.0 * a.Ks * a.Kc * L * a.Hout);
-  if (batched)
+  if (fast)
     tc_conv_bwd_dx_kernel<true><<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
   else
     tc_conv_bwd_dx_kernel<false><<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);

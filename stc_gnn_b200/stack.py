@@ -29,15 +29,18 @@ class RecurrentStack(nn.Module):
         """X_seq [B,T,N,C,Din] -> decoder hidden states [B,horizon,N,C,h]."""
         assert X_seq.dim() == 5, "X_seq must be [B,T,N,C,Din]"
         B, T = X_seq.shape[0], X_seq.shape[1]
-        seq = X_seq
+        # Layer l > 0 consumes layer l-1's per-step outputs directly: the reference stacks them and slices the stack
+        # again (STC_GNN.py:114,111), which in backward costs one zero-filled [B,T,N,C,h] tensor plus one full-size
+        # add per timestep (select_backward) -- same values, none of that traffic.
+        seq = [X_seq[:, t] for t in range(T)]
         last = []
         for cell in self.encoder:
             Ht = cell.init_hidden(B)
             outs = []
             for t in range(T):
-                Ht = cell(Gs=Gs, Gc=Gc, Xt=seq[:, t], Ht_1=Ht)
+                Ht = cell(Gs=Gs, Gc=Gc, Xt=seq[t], Ht_1=Ht)
                 outs.append(Ht)
-            seq = torch.stack(outs, dim=1)
+            seq = outs
             last.append(Ht)
         states, x, outs = last, last[-1], []
         for _ in range(self.out_horizon):

@@ -296,3 +296,28 @@ def test_config4_knn65536_csr_forward():
         Hn = S.stc_cell_forward(csr, f(t["Gc"]), f(t["Xt"]), f(t["H"]), f(t["Wg"]), f(t["bg"]), f(t["Wc"]), f(t["bc"]), Ks, 2)
         ref = O.stc_cell(t["Gs"], t["Gc"], t["Xt"], t["H"], t["Wg"], t["bg"], t["Wc"], t["bc"], Ks, 2)
     O.assert_close(Hn.cpu(), ref, "config4 Hn")
+
+
+def test_graphed_step_replays_the_eager_step():
+    """CUDA-graph capture of a whole forward+backward roll-out (stc_gnn_b200.GraphedStep): replaying it on new
+    inputs gives the eager step's loss and gradients (atomics make parameter gradients order-dependent, so the
+    comparison is at the parity tolerance, not bit-exact)."""
+    torch.manual_seed(3)
+    stack = S.RecurrentStack(30, 5, 2, 2, 1, 16, 2, 2).to(DEV)
+    params = list(stack.parameters())
+    g = torch.Generator().manual_seed(11)
+    Gs = (torch.rand(30, 30, generator=g) / 15).to(DEV).requires_grad_(True)
+    Gc = (torch.rand(5, 5, generator=g) / 3).to(DEV).requires_grad_(True)
+    X0 = torch.randn(4, 3, 30, 5, 1, generator=g).to(DEV)
+    X1 = torch.randn(4, 3, 30, 5, 1, generator=g).to(DEV)
+    loss_fn = lambda X: stack(Gs, Gc, X).square().mean()
+    gs = S.GraphedStep(loss_fn, [X0], params + [Gs, Gc])
+    loss_g = float(gs.replay(X1).item())
+    grads_g = [p.grad.clone() for p in params + [Gs, Gc]]
+    for p in params + [Gs, Gc]:
+        p.grad = None
+    loss_e = loss_fn(X1)
+    loss_e.backward()
+    assert abs(loss_g - float(loss_e.item())) <= 1e-5 * abs(float(loss_e.item()))
+    for i, (a, b) in enumerate(zip(grads_g, [p.grad for p in params + [Gs, Gc]])):
+        O.assert_close(a.cpu(), b.double().cpu(), f"graphed grad {i}")

@@ -133,107 +133,131 @@ __device__ __forceinline__ void tc_read_acc8(uint32_t tl, const TcFwdPlan& p, in
   }
 }
 
-template <int CPT>
-__device__ __forceinline__ void tmem_ld_cols_async(uint32_t taddr, uint32_t (&r)[CPT]) {
-  static_assert(CPT == 8 || CPT == 16, "8 or 16 columns per thread");
-  if constexpr (CPT == 8) tmem_ld8_async(taddr, r); else tmem_ld16_async(taddr, r);
-}
-template <int CPT>
-__device__ __forceinline__ void tmem_ld_pin(uint32_t (&r)[CPT]) {
-  if constexpr (CPT == 8) tmem_ld_pin8(r); else tmem_ld_pin16(r);
-}
-
-// Epilogue of the common shape (Kc = 2, one main accumulator, Hout = 2 * CPT): each thread owns accumulator row
-// `erow` and CPT CONTIGUOUS output columns [half*CPT, (half+1)*CPT) -- for the gates convolution the lower four
-// warps produce u and the upper four r and r*H, with no divergence inside a warp.  One exchange of the P_1 tile
-// through shared memory (one block-wide barrier) feeds the C x C categorical mix.
-template <int CPT>
+// Epilogue of the common shape (Kc = 2, one main accumulator, Hout = 16 * NG): each thread owns accumulator row
+// `erow` and NG groups of 8 output columns, group g at column 16 g + 8 half -- for the gates convolution (NG = 2)
+// every thread produces 8 channels of u and the same 8 channels of r and r*H, so all eight warps carry the same load.
+// All TMEM loads of a stage are in flight before one wait; one exchange of the P_1 tile through shared memory (one
+// block-wide barrier) feeds the C x C categorical mix.
+template <int NG>
 __device__ __forceinline__ void tc_fwd_epilogue_fast(const ConvArgs& a, const TcFwdPlan& p, uint32_t tl, float* Pm,
                                                      const float* Qs, const float* bias_s, const float* stage_e,
                                                      int erow, int enode, int ecat, int half, bool valid,
                                                      long long gr) {
   const int h = a.h, C = a.C, Hout = a.Hout;
-  const int c0 = half * CPT;
-  uint32_t sm1[CPT], mn1[CPT];
-  tmem_ld_cols_async<CPT>(tl + (uint32_t)(p.Npad + Hout + c0), sm1);     // P_1: cross terms, then main
-  tmem_ld_cols_async<CPT>(tl + (uint32_t)(Hout + c0), mn1);
+  const int cb = half * 8;
+  uint32_t sm1[NG][8], mn1[NG][8];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {                                          // P_1: cross terms, then main
+    tmem_ld8_async(tl + (uint32_t)(p.Npad + Hout + 16 * g + cb), sm1[g]);
+    tmem_ld8_async(tl + (uint32_t)(Hout + 16 * g + cb), mn1[g]);
+  }
   tmem_ld_wait();
-  tmem_ld_pin<CPT>(sm1); tmem_ld_pin<CPT>(mn1);
-  {
-    float t[CPT];
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) t[i] = __uint_as_float(sm1[i]) + __uint_as_float(mn1[i]);
-    float* pm = Pm + erow * p.PS + c0;
+  for (int g = 0; g < NG; ++g) {
+    tmem_ld_pin8(sm1[g]); tmem_ld_pin8(mn1[g]);
+    float t[8];
 #pragma unroll
-    for (int i = 0; i < CPT; i += 4) *reinterpret_cast<float4*>(pm + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+    for (int i = 0; i < 8; ++i) t[i] = __uint_as_float(sm1[g][i]) + __uint_as_float(mn1[g][i]);
+    float* pm = Pm + erow * p.PS + 16 * g + cb;
+    *reinterpret_cast<float4*>(pm) = make_float4(t[0], t[1], t[2], t[3]);
+    *reinterpret_cast<float4*>(pm + 4) = make_float4(t[4], t[5], t[6], t[7]);
     if (a.Psave && valid) {   // backward forms dGc from these partials (no recomputation of the GEMM)
-      float* ps = a.Psave + gr * (long long)Hout + c0;
-#pragma unroll
-      for (int i = 0; i < CPT; i += 4) *reinterpret_cast<float4*>(ps + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+      float* ps = a.Psave + gr * (long long)Hout + 16 * g + cb;
+      *reinterpret_cast<float4*>(ps) = make_float4(t[0], t[1], t[2], t[3]);
+      *reinterpret_cast<float4*>(ps + 4) = make_float4(t[4], t[5], t[6], t[7]);
     }
   }
-  uint32_t sm0[CPT], mn0[CPT];
-  tmem_ld_cols_async<CPT>(tl + (uint32_t)(p.Npad + c0), sm0);            // P_0 travels under the barrier
-  tmem_ld_cols_async<CPT>(tl + (uint32_t)c0, mn0);
+  uint32_t sm0[NG][8], mn0[NG][8];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {                                          // P_0 travels under the barrier
+    tmem_ld8_async(tl + (uint32_t)(p.Npad + 16 * g + cb), sm0[g]);
+    tmem_ld8_async(tl + (uint32_t)(16 * g + cb), mn0[g]);
+  }
   __syncthreads();
   tmem_ld_wait();
-  tmem_ld_pin<CPT>(sm0); tmem_ld_pin<CPT>(mn0);
-  float v[CPT];
+  float v[NG][8];
 #pragma unroll
-  for (int i = 0; i < CPT; ++i) v[i] = __uint_as_float(sm0[i]) + __uint_as_float(mn0[i]);
+  for (int g = 0; g < NG; ++g) {
+    tmem_ld_pin8(sm0[g]); tmem_ld_pin8(mn0[g]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[g][i] = __uint_as_float(sm0[g][i]) + __uint_as_float(mn0[g][i]);
+  }
   {
-    const float* pp = Pm + (enode * C) * p.PS + c0;
+    const float* pp = Pm + (enode * C) * p.PS + cb;
     for (int cp = 0; cp < C; ++cp) {
       const float w = Qs[cp * C + ecat];
 #pragma unroll
-      for (int i = 0; i < CPT; i += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(pp + cp * p.PS + i);
-        v[i] = fmaf(w, x.x, v[i]); v[i + 1] = fmaf(w, x.y, v[i + 1]);
-        v[i + 2] = fmaf(w, x.z, v[i + 2]); v[i + 3] = fmaf(w, x.w, v[i + 3]);
+      for (int g = 0; g < NG; ++g) {
+        const float4 x0 = *reinterpret_cast<const float4*>(pp + cp * p.PS + 16 * g);
+        const float4 x1 = *reinterpret_cast<const float4*>(pp + cp * p.PS + 16 * g + 4);
+        v[g][0] = fmaf(w, x0.x, v[g][0]); v[g][1] = fmaf(w, x0.y, v[g][1]);
+        v[g][2] = fmaf(w, x0.z, v[g][2]); v[g][3] = fmaf(w, x0.w, v[g][3]);
+        v[g][4] = fmaf(w, x1.x, v[g][4]); v[g][5] = fmaf(w, x1.y, v[g][5]);
+        v[g][6] = fmaf(w, x1.z, v[g][6]); v[g][7] = fmaf(w, x1.w, v[g][7]);
       }
     }
   }
   if (!valid) return;
 #pragma unroll
-  for (int i = 0; i < CPT; i += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + i);
-    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+  for (int g = 0; g < NG; ++g) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 16 * g + cb);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 16 * g + cb + 4);
+    v[g][0] += b0.x; v[g][1] += b0.y; v[g][2] += b0.z; v[g][3] += b0.w;
+    v[g][4] += b1.x; v[g][5] += b1.y; v[g][6] += b1.z; v[g][7] += b1.w;
+    if (a.act == STC_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[g][i] = fmaxf(v[g][i], 0.f);
+    }
   }
-  if (a.act == STC_ACT_RELU) {
+  if (a.phase == 0) {   // Hout = 2h: column 16 g + cb + i is u channel (same index) while it is < h, r channel (index - h) after
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) v[i] = fmaxf(v[i], 0.f);
-  }
-  if (a.phase == 0) {   // CPT == h: half 0 -> u, half 1 -> r and r*H
+    for (int g = 0; g < NG; ++g) {
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) v[i] = sigmoidf_fast(v[i]);
-    float* dst = (half == 0 ? a.u : a.r) + gr * h;
-#pragma unroll
-    for (int i = 0; i < CPT; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    if (half != 0) {
-      float* drh = a.rH + gr * h;
-#pragma unroll
-      for (int i = 0; i < CPT; i += 4) {
-        const float4 hp = *reinterpret_cast<const float4*>(stage_e + erow * h + i);
-        *reinterpret_cast<float4*>(drh + i) = make_float4(v[i] * hp.x, v[i + 1] * hp.y, v[i + 2] * hp.z, v[i + 3] * hp.w);
+      for (int i = 0; i < 8; ++i) v[g][i] = sigmoidf_fast(v[g][i]);
+      const int col = 16 * g + cb;
+      if (col < h) {
+        float* dst = a.u + gr * h + col;
+        *reinterpret_cast<float4*>(dst) = make_float4(v[g][0], v[g][1], v[g][2], v[g][3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[g][4], v[g][5], v[g][6], v[g][7]);
+      } else {
+        const int ch = col - h;
+        const float4 h0 = *reinterpret_cast<const float4*>(stage_e + erow * h + ch);
+        const float4 h1 = *reinterpret_cast<const float4*>(stage_e + erow * h + ch + 4);
+        float* dr = a.r + gr * h + ch;
+        *reinterpret_cast<float4*>(dr) = make_float4(v[g][0], v[g][1], v[g][2], v[g][3]);
+        *reinterpret_cast<float4*>(dr + 4) = make_float4(v[g][4], v[g][5], v[g][6], v[g][7]);
+        float* drh = a.rH + gr * h + ch;
+        *reinterpret_cast<float4*>(drh) = make_float4(v[g][0] * h0.x, v[g][1] * h0.y, v[g][2] * h0.z, v[g][3] * h0.w);
+        *reinterpret_cast<float4*>(drh + 4) = make_float4(v[g][4] * h1.x, v[g][5] * h1.y, v[g][6] * h1.z, v[g][7] * h1.w);
       }
     }
-  } else {              // 2 * CPT == h: c = tanh, H' = H + u (c - H)
-    const long long o = gr * h + c0;
+  } else {              // Hout = h: c = tanh, H' = H + u (c - H)
 #pragma unroll
-    for (int i = 0; i < CPT; i += 4) {
-      const float4 uu = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + c0 + i);
-      const float4 hp = *reinterpret_cast<const float4*>(stage_e + erow * h + c0 + i);
-      const float4 cc = make_float4(tanhf_fast(v[i]), tanhf_fast(v[i + 1]), tanhf_fast(v[i + 2]), tanhf_fast(v[i + 3]));
-      *reinterpret_cast<float4*>(a.c + o + i) = cc;
-      *reinterpret_cast<float4*>(a.Hnew + o + i) =
-          make_float4(fmaf(uu.x, cc.x - hp.x, hp.x), fmaf(uu.y, cc.y - hp.y, hp.y), fmaf(uu.z, cc.z - hp.z, hp.z),
-                      fmaf(uu.w, cc.w - hp.w, hp.w));
+    for (int g = 0; g < NG; ++g) {
+      const int col = 16 * g + cb;
+      const long long o = gr * h + col;
+      float cc[8], hn[8];
+      const float4 u0 = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + col);
+      const float4 u1 = *reinterpret_cast<const float4*>(stage_e + 128 * h + erow * h + col + 4);
+      const float4 p0 = *reinterpret_cast<const float4*>(stage_e + erow * h + col);
+      const float4 p1 = *reinterpret_cast<const float4*>(stage_e + erow * h + col + 4);
+      const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      const float hp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        cc[i] = tanhf_fast(v[g][i]);
+        hn[i] = fmaf(uu[i], cc[i] - hp[i], hp[i]);
+      }
+      *reinterpret_cast<float4*>(a.c + o) = make_float4(cc[0], cc[1], cc[2], cc[3]);
+      *reinterpret_cast<float4*>(a.c + o + 4) = make_float4(cc[4], cc[5], cc[6], cc[7]);
+      *reinterpret_cast<float4*>(a.Hnew + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      *reinterpret_cast<float4*>(a.Hnew + o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
     }
   }
 }
 
-// CPT = 0: general epilogue (any Kc, any Hout % 16 == 0); CPT = 8 / 16: tc_fwd_epilogue_fast
-template <int CPT>
+// NG = 0: general epilogue (any Kc, any Hout % 16 == 0); NG = 1 / 2: tc_fwd_epilogue_fast
+template <int NG>
 __global__ void __launch_bounds__(CV_THREADS, 2)
 tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -406,7 +430,11 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
             acc_main = 1u;
             acc_small = true;
           }
+          if (ai == 0) STC_TRACE(8);
+          if (ai == p.nacc - 1) STC_TRACE(10);
           mma_commit(mma_bar);
+          if (ai == 0) STC_TRACE(9);
+          if (ai == p.nacc - 1) STC_TRACE(11);
         }
         acc_small = true;
         mma_pending = true;
@@ -424,8 +452,8 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
     STC_TRACE(6);
     const bool valid = erow < rows_valid;
     const long long gr = g0 * C + erow;
-    if constexpr (CPT != 0) {
-      tc_fwd_epilogue_fast<CPT>(a, p, tl, Pm, Qs, bias_s, stage_e, erow, enode, ecat, half, valid, gr);
+    if constexpr (NG != 0) {
+      tc_fwd_epilogue_fast<NG>(a, p, tl, Pm, Qs, bias_s, stage_e, erow, enode, ecat, half, valid, gr);
     } else {
       for (int c0 = half * 8; c0 < Hout; c0 += 16) {
         float v[8];
@@ -583,11 +611,10 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
   p.off_bar = (uint32_t)o; o += 48;
   p.smem_bytes = (uint32_t)o;
   if (p.smem_bytes > 200 * 1024) return STC_OK;  // not an SF-class shape: the FFMA path handles it
-  // contiguous-column epilogue: Kc = 2, one main accumulator, and a thread's CPT = Hout/2 columns are 8 or 16 wide
-  // (gates: CPT = h, candidate: CPT = h/2)
-  int cpt = 0;
-  if (a.Kc == 2 && p.nmain == 1 && (a.Hout == 16 || a.Hout == 32) && !(a.opt & OPT_GENERIC_EPILOGUE)) cpt = a.Hout / 2;
-  auto kern = cpt == 16 ? tc_conv_fwd_kernel<16> : (cpt == 8 ? tc_conv_fwd_kernel<8> : tc_conv_fwd_kernel<0>);
+  // batched epilogue: Kc = 2, one main accumulator, one or two 8-column groups per thread (Hout = 16 or 32)
+  int ng = 0;
+  if (a.Kc == 2 && p.nmain == 1 && (a.Hout == 16 || a.Hout == 32) && !(a.opt & OPT_GENERIC_EPILOGUE)) ng = a.Hout / 16;
+  auto kern = ng == 2 ? tc_conv_fwd_kernel<2> : (ng == 1 ? tc_conv_fwd_kernel<1> : tc_conv_fwd_kernel<0>);
   STC_TRY(set_smem(kern, p.smem_bytes));
   int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;

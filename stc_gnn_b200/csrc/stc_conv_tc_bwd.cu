@@ -303,7 +303,11 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
           acc_main = 1u;
           acc_small = true;
         }
+        if (ja == 0) STC_TRACE(8);
+        if (ja == p.KA - 1) STC_TRACE(10);
         mma_commit(mma_bar);
+        if (ja == 0) STC_TRACE(9);
+        if (ja == p.KA - 1) STC_TRACE(11);
       }
       acc_small = true;
       mma_pending = true;

@@ -25,12 +25,13 @@ constexpr int TS_THREADS = 32 * (1 + TS_PROD_WARPS + TS_EPI_WARPS);
 constexpr int TS_SLOTS = 8;                  // 16-byte chunks per producer thread per tile (Kp <= 128)
 constexpr int TS_MAX_STAGES = 4;             // X ring depth (as many as fit)
 constexpr int TS_ACC_COLS = 4 * TS_NT;       // 2 accumulator buffers x (main + cross-term)
+constexpr int TS_OLD = TS_NT + 4;            // row stride (floats) of the output staging tile: conflict-free both ways
 
 struct TcSupPlan {
   int N, Kp, W, transpose, stages;
   long long total_cols, ntiles;
   int tmem_cols;
-  uint32_t off_x, off_bar, smem_bytes, imgX;
+  uint32_t off_x, off_o, off_bar, smem_bytes, imgX;
 };
 
 __global__ void __launch_bounds__(TS_THREADS, 1)
@@ -162,35 +163,39 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
       tile += stride;
     }
   } else {
-    // =========================== epilogue: one output node per thread ===========================
+    // =========================== epilogue: TMEM -> staging tile -> coalesced rows ===========================
+    // A thread can only read its own TMEM lane (= output node m), but writing Y one node-row per thread makes every
+    // 16-byte store of a warp land in a different 128-byte line (and likewise every Z load).  So the tile goes through
+    // a padded shared-memory image [128 nodes][TS_NT + 4]: row-per-thread on the TMEM side, 16 consecutive lanes per
+    // 256-byte row segment on the global side.
     const int sp = warp & 3;                       // TMEM sub-partition this warp may read
     const int m = sp * 32 + lane;
     const bool live = m < N;
     const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
     const bool use_z = beta != 0.f;
+    float* Obuf = reinterpret_cast<float*>(smem + p.off_o);
+    const int et = tid - 32 * (1 + TS_PROD_WARPS);   // 0..127
+    const int ch = et & 15, er0 = et >> 4;           // global side: 16-byte chunk `ch` of rows er0 + 8 i
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
       const int ab = it & 1;
-      const long long cg0 = tile * TS_NT;
-      const long long b0 = cg0 / W;
-      const int j0 = (int)(cg0 - b0 * W);
-      // every Z chunk of the tile is requested before waiting for the accumulators: one exposed latency per tile
-      float4 zz[TS_NT / 4];
-      if (use_z) {
-        long long cb = b0, cg = cg0;
-        int cj = j0;
-#pragma unroll
-        for (int g = 0; g < TS_NT / 4; ++g) {
-          zz[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live && cg < p.total_cols) zz[g] = __ldg(reinterpret_cast<const float4*>(Z + cb * z_bs + (long long)m * W + cj));
-          cj += 4; cg += 4;
-          if (cj >= W) { cj = 0; ++cb; }
+      const long long cgc = tile * TS_NT + 4 * ch;   // this thread's chunk column (never straddles samples: W % 4 == 0)
+      const bool cok = cgc < p.total_cols;
+      const long long bc = cok ? cgc / W : 0;
+      const int jc = (int)(cgc - bc * W);
+      if (use_z) {   // Z tile, coalesced, while the MMAs of this tile are still running
+        const float* zsrc = Z + bc * z_bs + jc;
+#pragma unroll 4
+        for (int r = er0; r < N; r += 8) {
+          float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cok) z = *reinterpret_cast<const float4*>(zsrc + (long long)r * W);   // plain load: Y may alias Z
+          *reinterpret_cast<float4*>(Obuf + r * TS_OLD + 4 * ch) = z;
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(&accfull[ab], (uint32_t)(it >> 1) & 1u);
       fence_after_sync();
-      long long b = b0, cg = cg0;
-      int j = j0;
+      float* orow = Obuf + m * TS_OLD;
 #pragma unroll
       for (int hh = 0; hh < TS_NT / 16; ++hh) {    // 16 columns at a time
         uint32_t vm[16], vs[16];
@@ -200,27 +205,34 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
         tmem_ld_wait();
         tmem_ld_pin16(vm);
         tmem_ld_pin16(vs);
+        if (live) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (live && cg < p.total_cols) {
+          for (int g = 0; g < 4; ++g) {
             float4 o;
             o.x = alpha * (__uint_as_float(vm[4 * g + 0]) + __uint_as_float(vs[4 * g + 0]));
             o.y = alpha * (__uint_as_float(vm[4 * g + 1]) + __uint_as_float(vs[4 * g + 1]));
             o.z = alpha * (__uint_as_float(vm[4 * g + 2]) + __uint_as_float(vs[4 * g + 2]));
             o.w = alpha * (__uint_as_float(vm[4 * g + 3]) + __uint_as_float(vs[4 * g + 3]));
+            float4* slot = reinterpret_cast<float4*>(orow + hh * 16 + 4 * g);
             if (use_z) {
-              const float4 z = zz[hh * 4 + g];
+              const float4 z = *slot;
               o.x = fmaf(beta, z.x, o.x); o.y = fmaf(beta, z.y, o.y); o.z = fmaf(beta, z.z, o.z); o.w = fmaf(beta, z.w, o.w);
             }
-            *reinterpret_cast<float4*>(Y + (b * N + m) * (long long)W + j) = o;
+            *slot = o;
           }
-          j += 4; cg += 4;
-          if (j >= W) { j = 0; ++b; }
         }
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&accempty[ab]);
+      if (lane == 0) mbar_arrive(&accempty[ab]);   // the accumulators are free again while the tile is still being stored
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (cok) {
+        float* ydst = Y + bc * (long long)N * W + jc;
+#pragma unroll 4
+        for (int r = er0; r < N; r += 8)
+          *reinterpret_cast<float4*>(ydst + (long long)r * W) = *reinterpret_cast<const float4*>(Obuf + r * TS_OLD + 4 * ch);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the staging tile is rewritten by the next tile
     }
   }
   __syncthreads();
@@ -256,12 +268,14 @@ int try_launch_support_tc(const float* G, int N, int B, int width, bool transpos
   p.ntiles = (p.total_cols + TS_NT - 1) / TS_NT;
   p.imgX = (uint32_t)(TS_NT / 32) * p.Kp * ATOM_ROW_BYTES;
   p.tmem_cols = 512;   // 2 x (main + cross-term) x 64 accumulator columns + the support (2 x Kp <= 256 columns)
-  const size_t fixed = 8 * (2 * TS_MAX_STAGES + 4) + 32;
+  const size_t obytes = (size_t)128 * TS_OLD * sizeof(float);
+  const size_t fixed = 8 * (2 * TS_MAX_STAGES + 4) + 32 + obytes;
   p.stages = TS_MAX_STAGES;
   while (p.stages > 2 && 2 * (size_t)p.stages * p.imgX + fixed > 227 * 1024) --p.stages;
   size_t o = 0;
   p.off_x = (uint32_t)o; o += 2 * (size_t)p.stages * p.imgX;
   o = round_up(o, 16);
+  p.off_o = (uint32_t)o; o += obytes;
   p.off_bar = (uint32_t)o; o += 8 * (2 * TS_MAX_STAGES + 4) + 16;
   p.smem_bytes = (uint32_t)o;
   if (p.smem_bytes > 227 * 1024) return STC_OK;   // larger N: the FFMA kernel tiles it

@@ -3,7 +3,9 @@
 mkdir -p gpurun_out
 T=${1:-r1g}
 OPTS=${2:-"1 5"}
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$T.log 2>&1; tail -3 gpurun_out/pytest_$T.log
+timeout 150 python -m pytest tests/test_cell_gpu.py -m gpu -x -q -k "support_apply or sf_din16 or tiny" > gpurun_out/pytest_quick_$T.log 2>&1 || { tail -30 gpurun_out/pytest_quick_$T.log; echo QUICK TESTS FAILED; exit 1; }
+tail -1 gpurun_out/pytest_quick_$T.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$T.log 2>&1; tail -3 gpurun_out/pytest_$T.log
 for OPT in $OPTS; do
   STC_OPT=$OPT timeout 300 python bench.py --no-cpu-baseline 2> gpurun_out/bench_${T}_opt$OPT.err > gpurun_out/bench_${T}_opt$OPT.json
   tail -2 gpurun_out/bench_${T}_opt$OPT.err

@@ -315,7 +315,8 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const int warp_u = uniform_warp_index();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   const uint32_t idesc = make_idesc_tf32(128, p.Npad);
   const uint32_t d_small = tmem_base + (uint32_t)(p.nmain * p.Npad);
   const long long total_nodes = (long long)a.B * a.N;
@@ -339,15 +340,15 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   bool mma_pending = false;
   const bool tracing = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
   int trace_it = 0;
-  // thread 32 (warp 1) owns every bulk copy and prefetch; thread 0 (warp 0) only issues MMAs
-  if (tid == 32 && (int)blockIdx.x < p.ntiles) tc_issue_tile_loads(a, p, blockIdx.x, stage_h, stage_x, load_bar);
+  // one elected lane of warp 1 owns every bulk copy and prefetch; one elected lane of warp 0 only issues MMAs
+  if (warp_u == 1 && elect_one_sync() && (int)blockIdx.x < p.ntiles) tc_issue_tile_loads(a, p, blockIdx.x, stage_h, stage_x, load_bar);
 
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long g0 = (long long)tile * p.npt;
     const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
     const int rows_valid = nodes_valid * C;
     STC_TRACE(0);
-    if (tid == 32) {  // the epilogue's own operands (H, and u for the candidate) travel under the builds and the MMAs
+    if (warp_u == 1 && elect_one_sync()) {  // the epilogue's own operands (H, and u for the candidate) travel under the builds and the MMAs
       const uint32_t eb = (uint32_t)(rows_valid * h * 4);
       mbar_arrive_expect_tx(epi_bar, a.phase == 0 ? eb : 2 * eb);
       bulk_g2s(stage_e, a.Hprev + g0 * C * h, eb, epi_bar);
@@ -412,9 +413,9 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
         __syncthreads();
         if (ai == 0) STC_TRACE(2);
         // the stage is dead after the last build of this tile: fetch the next tile under the MMAs + epilogue
-        if (tid == 32 && ai == p.nacc - 1 && tile + (int)gridDim.x < p.ntiles)
+        if (warp_u == 1 && ai == p.nacc - 1 && tile + (int)gridDim.x < p.ntiles && elect_one_sync())
           tc_issue_tile_loads(a, p, tile + gridDim.x, stage_h, stage_x, load_bar);
-        if (tid == 0) {
+        if (warp_u == 0 && elect_one_sync()) {   // one lane of converged warp 0: descriptors stay in uniform registers
           fence_after_sync();
           const int kleft = p.KBL - j * ATOM_K;
           const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;

@@ -161,7 +161,8 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const int warp_u = uniform_warp_index();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   const uint32_t idesc = make_idesc_tf32(128, p.Npad);
   const uint32_t d_small = tmem_base + (uint32_t)(p.nmain * p.Npad);
   // operand descriptors are launch constants: only the 16-byte-granular address field moves (K-step: +32 B, atom: +atomB)
@@ -207,7 +208,7 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
     const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
     const int rows_valid = nodes_valid * C;
     const long long row0 = g0 * C;
-    if (tid == 32) {  // thread 32 owns the bulk copy and the prefetches, thread 0 only issues MMAs
+    if (warp_u == 1 && elect_one_sync()) {  // a lane of warp 1 owns the bulk copy and the prefetches, warp 0 only issues MMAs
       if (want_dQ) {  // stage the saved partial outputs of this tile while the prologue runs
         const uint32_t bytes = (uint32_t)(rows_valid * p.PW * 4);
         mbar_arrive_expect_tx(load_bar, bytes);
@@ -287,7 +288,7 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       fence_async_smem();
       __syncthreads();
       if (ja == 0) STC_TRACE(2);
-      if (tid == 0) {
+      if (warp_u == 0 && elect_one_sync()) {   // one lane of converged warp 0: descriptors stay in uniform registers
         fence_after_sync();
         const int kleft = p.Kdd - ja * ATOM_K;
         const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;

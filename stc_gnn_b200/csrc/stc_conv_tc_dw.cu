@@ -168,7 +168,7 @@ tc_conv_bwd_dw_kernel(const ConvArgs a, const TcDwPlan p) {
       if (i < nbs) store_split4(B_hi, B_lo, bsoff + (uint32_t)(bstep * i) * ATOM_ROW_BYTES, rb[i]);
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (uniform_warp_index() == 0 && elect_one_sync()) {   // uniform issue path, see stc_tc.cuh
       fence_after_sync();
       const uint32_t lboA = DW_TR * ATOM_ROW_BYTES, lboB = DW_TR * ATOM_ROW_BYTES;
 #pragma unroll 1
@@ -288,12 +288,13 @@ tc_conv_bwd_dw_pipe_kernel(const ConvArgs a, const TcDwPipePlan p) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const int warp_u = uniform_warp_index();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   const int my_tiles = (int)((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-  if (warp == DWP_CONS_WARPS) {
+  if (warp_u == DWP_CONS_WARPS) {
     // =========================== producer: one thread issues every bulk copy ===========================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int it = 0; it < my_tiles; ++it) {
         const long long tile = blockIdx.x + (long long)it * gridDim.x;
         const int st = it % p.stages;
@@ -326,9 +327,9 @@ tc_conv_bwd_dw_pipe_kernel(const ConvArgs a, const TcDwPipePlan p) {
         bulk_g2s(dst + p.off_d, a.dpre + row0 * p.N1, (uint32_t)(rv * p.N1 * 4), &full[st]);
       }
     }
-  } else if (warp == DWP_CONS_WARPS + 1) {
+  } else if (warp_u == DWP_CONS_WARPS + 1) {
     // =========================== MMA issuer: a warp of its own, so no worker ever waits behind the issue queue =====
-    if (lane == 0) {
+    if (elect_one_sync()) {   // one lane of the converged warp: descriptors stay in uniform registers (stc_tc.cuh)
       const uint32_t idesc = make_idesc_tf32_mn(64, p.Npad);
       const uint32_t lbo = DW_TR * ATOM_ROW_BYTES;
       for (int it = 0; it < my_tiles; ++it) {

@@ -95,9 +95,11 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
   fence_after_sync();
   const long long stride = gridDim.x;
 
-  if (warp == 0) {
-    // =========================== MMA issuer (one thread) ===========================
-    if (lane == 0) {
+  if (uniform_warp_index() == 0) {
+    // =========================== MMA issuer (one elected lane of a converged warp) ===========================
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    const uint32_t tG = tmem_base + TS_ACC_COLS;
+    if (elect_one_sync()) {
       const uint32_t idesc = make_idesc_tf32_atmem_bmn(128, TS_NT);
       int it = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
@@ -327,7 +329,8 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const int warp_u = uniform_warp_index();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   const uint32_t idesc = make_idesc_tf32(128, p.Npad);
   const uint32_t d_small = tmem_base + (uint32_t)(3 * p.Npad);
 
@@ -428,7 +431,7 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
     const int kleft = W - at * ATOM_K;
     const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
     const int mi = since_drain % 3;
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one_sync()) {   // uniform issue path, see stc_tc.cuh
       fence_after_sync();
       const uint32_t base = smem_u32(smem + (size_t)buf * bufsz);
       bool am = acc_main[mi], as = acc_small;

@@ -152,6 +152,26 @@ __device__ __forceinline__ void tmem_ld_pin16(uint32_t (&r)[16]) {
 }
 
 // ---- MMA issue (one thread) ------------------------------------------------------------------------
+// One lane of a fully converged warp.  Issuing tcgen05.mma from `if (lane == 0)` makes the compiler treat every
+// operand as lane-varying: each MMA is then wrapped in an ELECT / R2UR loop of ~25 dependent instructions (~200
+// cycles per MMA measured with clock64 -- more than the 32 cycles the MMA itself takes).  With the warp index made
+// warp-uniform (uniform_warp_index) and the lane chosen by elect.sync, descriptors stay in uniform registers and the
+// MMAs issue back to back.
+__device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ bool elect_one_sync() {   // call from warp-uniform control flow only
+  uint32_t pred;
+  __syncwarp();   // lanes may have diverged on an earlier lane-dependent branch (e.g. the trace stamps)
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(

@@ -156,8 +156,8 @@ int stc_timing_collect(double* ms_by_kind, int64_t* launches_by_kind, double* al
 const char* stc_kernel_kind_name(int32_t kind);
 
 /* Diagnostic: while dev_buf (int64 [n_slots], device memory, caller-owned) is registered, CTA 0 of the tcgen05
- * gate-convolution kernels stamps clock64() at its phase boundaries for its first n_slots/24 tiles
- * (12 stamps per tile; the gates convolution uses the first half of the buffer, the candidate convolution the
+ * gate-convolution kernels stamps clock64() at its phase boundaries for its first n_slots/32 tiles
+ * (16 stamps per tile; the gates convolution uses the first half of the buffer, the candidate convolution the
  * second; tools/trace_conv.py prints the deltas).  Pass NULL to switch it off (the default). */
 int stc_debug_trace_set(void* dev_buf, int64_t n_slots);
 

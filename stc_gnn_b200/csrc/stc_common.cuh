@@ -147,7 +147,7 @@ struct ConvArgs {
   int trace_tiles;
 };
 enum { OPT_L2_PREFETCH = 1, OPT_BATCHED_PROLOGUE = 2, OPT_GENERIC_EPILOGUE = 4 /* diagnostic: force the general epilogues */ };
-constexpr int TRACE_SLOTS = 12;
+constexpr int TRACE_SLOTS = 16;
 int conv_opt_flags();                                  // cached STC_OPT (default: OPT_L2_PREFETCH)
 void conv_trace_target(long long** buf, int* tiles);   // what stc_debug_trace_set registered (null when off)
 // fused forward cell (stc_cell_fused.cu): dense support that fits one tile, Ks = Kc = 2, h = 16

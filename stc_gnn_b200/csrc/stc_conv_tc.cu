@@ -383,20 +383,15 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
       const float* sh = stage_h + (size_t)k * 128 * h;
       const float* sx = stage_x + (size_t)k * 128 * Din;
       for (int j = 0; j < p.KB; ++j, ++ai) {
-        if (mma_pending) {  // single A buffer: the previous atom's MMAs must have read it
-          mbar_wait(mma_bar, mma_phase);
-          mma_phase ^= 1u;
-          mma_pending = false;
-          if (ai == p.nacc - 1) STC_TRACE(3);
-        }
+        // the atom's values are read and split while the previous atom's MMAs may still be reading the single A buffer
         const int kb = j * ATOM_K + q * 4;
         const bool from_h = kb < h;
+        float4 vv[4];
         if (from_h || (p.x_bulk && kb - h < Din)) {   // whole 16-byte chunks of the h-part or of an aligned x-part: one path
           const float* bp = from_h ? sh + kb : sx + (kb - h);
           const int st = from_h ? h : Din;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            store_split4(A_hi, A_lo, aoff[i], *reinterpret_cast<const float4*>(bp + (r0 + 32 * i) * st));
+          for (int i = 0; i < 4; ++i) vv[i] = *reinterpret_cast<const float4*>(bp + (r0 + 32 * i) * st);
         } else {
           const int xi = kb - h;
 #pragma unroll
@@ -406,10 +401,29 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
 #pragma unroll
             for (int t = 0; t < 4; ++t)
               if (xi + t < Din) e[t] = sp[t];
-            store_split4(A_hi, A_lo, aoff[i], make_float4(e[0], e[1], e[2], e[3]));
+            vv[i] = make_float4(e[0], e[1], e[2], e[3]);
           }
         }
+        float4 vh[4], vl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          split_tf32(vv[i].x, vh[i].x, vl[i].x); split_tf32(vv[i].y, vh[i].y, vl[i].y);
+          split_tf32(vv[i].z, vh[i].z, vl[i].z); split_tf32(vv[i].w, vh[i].w, vl[i].w);
+        }
+        if (mma_pending) {
+          mbar_wait(mma_bar, mma_phase);
+          mma_phase ^= 1u;
+          mma_pending = false;
+          if (ai == p.nacc - 1) STC_TRACE(3);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<float4*>(A_hi + aoff[i]) = vh[i];
+          *reinterpret_cast<float4*>(A_lo + aoff[i]) = vl[i];
+        }
+        if (ai == 0) STC_TRACE(12);
         fence_async_smem();
+        if (ai == 0) STC_TRACE(13);
         __syncthreads();
         if (ai == 0) STC_TRACE(2);
         // the stage is dead after the last build of this tile: fetch the next tile under the MMAs + epilogue

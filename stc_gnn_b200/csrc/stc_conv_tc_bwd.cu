@@ -106,7 +106,8 @@ __device__ __forceinline__ void dx_prefetch_tile(const ConvArgs& a, const TcDxPl
 }
 
 // FAST: contiguous-column epilogue of the common shape (Ks = 2, h = 16, Din <= 16, one main accumulator)
-template <bool FAST>
+// BATCHED: the elementwise adjoint issues the loads of two items before the first use (12 x 16 bytes in flight per thread)
+template <bool FAST, bool BATCHED>
 __global__ void __launch_bounds__(CV_THREADS, 2)
 tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -234,16 +235,39 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
         *reinterpret_cast<float4*>(Dh + row * h + j) = dir;
       }
     };
-    for (int it = tid; it < 128 * cpr; it += CV_THREADS) {
-      const int row = it / cpr, j = (it - row * cpr) << 2;
-      float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
-      const bool live = row < rows_valid;
-      if (live) {
-        DxIn in;
-        dx_load(a, (row0 + row) * h + j, in);
-        dx_adjoint(a, in, g0v, g1v, dir);
+    if constexpr (BATCHED) {
+      for (int it0 = tid; it0 < 128 * cpr; it0 += 2 * CV_THREADS) {
+        DxIn in[2];
+        int row[2], j[2];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int it = it0 + u * CV_THREADS;
+          row[u] = it / cpr;
+          j[u] = (it - row[u] * cpr) << 2;
+          live[u] = it < 128 * cpr && row[u] < rows_valid;
+          if (live[u]) dx_load(a, (row0 + row[u]) * h + j[u], in[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (it0 + u * CV_THREADS >= 128 * cpr) continue;
+          float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
+          if (live[u]) dx_adjoint(a, in[u], g0v, g1v, dir);
+          emit_item(row[u], j[u], g0v, g1v, dir, live[u]);
+        }
       }
-      emit_item(row, j, g0v, g1v, dir, live);
+    } else {
+      for (int it = tid; it < 128 * cpr; it += CV_THREADS) {
+        const int row = it / cpr, j = (it - row * cpr) << 2;
+        float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
+        const bool live = row < rows_valid;
+        if (live) {
+          DxIn in;
+          dx_load(a, (row0 + row) * h + j, in);
+          dx_adjoint(a, in, g0v, g1v, dir);
+        }
+        emit_item(row, j, g0v, g1v, dir, live);
+      }
     }
     __syncthreads();
     STC_TRACE(1);
@@ -285,7 +309,9 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) store_split4(A_hi, A_lo, aoff[i], vv[i]);
+      if (ja == 0) STC_TRACE(12);
       fence_async_smem();
+      if (ja == 0) STC_TRACE(13);
       __syncthreads();
       if (ja == 0) STC_TRACE(2);
       if (warp_u == 0 && elect_one_sync()) {   // one lane of converged warp 0: descriptors stay in uniform registers
@@ -583,7 +609,10 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
     return STC_ERR_UNSUPPORTED;
   }
   const bool fast = a.Ks == 2 && a.h == 16 && a.Din <= 16 && p.nmain == 1 && !(a.opt & OPT_GENERIC_EPILOGUE);
-  STC_TRY(fast ? set_smem(tc_conv_bwd_dx_kernel<true>, p.smem_bytes) : set_smem(tc_conv_bwd_dx_kernel<false>, p.smem_bytes));
+  const bool batched = (a.opt & OPT_BATCHED_PROLOGUE) != 0;
+  auto kern = fast ? (batched ? tc_conv_bwd_dx_kernel<true, true> : tc_conv_bwd_dx_kernel<true, false>)
+                   : (batched ? tc_conv_bwd_dx_kernel<false, true> : tc_conv_bwd_dx_kernel<false, false>);
+  STC_TRY(set_smem(kern, p.smem_bytes));
   int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 2) ctas_per_sm = 2;
@@ -597,10 +626,7 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
   ScopedKernelTimer _t(KK_TC_CONV_BWD_DX, st,
                        4.0 * R * ((a.phase == 0 ? 6 * a.h + a.Ks * a.Din : 3 * a.h) + a.Hout + a.Ks * L +
                                   ((a.dQ && a.Kc > 1) ? p.PW : 0)) + 4.0 * a.Ks * a.Kc * L * a.Hout);
-  if (fast)
-    tc_conv_bwd_dx_kernel<true><<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
-  else
-    tc_conv_bwd_dx_kernel<false><<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
+  kern<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p);
   STC_LAUNCH_OK("tc_conv_bwd_dx_kernel");
   *handled = true;
   return STC_OK;

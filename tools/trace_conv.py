@@ -24,7 +24,7 @@ DX = ["tile start -> elementwise adjoint done", "-> first atom built", "-> last 
 
 
 def report(name, buf, tiles, labels):
-    t = buf.view(tiles, 12).cpu().double()
+    t = buf.view(tiles, 16).cpu().double()
     t = t[(t[:, :8] > 0).all(dim=1)]
     if t.shape[0] < 4:
         print(f"{name}: only {t.shape[0]} traced tiles")
@@ -37,7 +37,10 @@ def report(name, buf, tiles, labels):
     for i in range(7):
         print(f"   {d[:, i].mean().item():8.0f}  {labels[i]}")
     print(f"   {nxt.mean().item():8.0f}  {labels[7]}")
-    if (t[:, 8:] > 0).all():
+    if (t[:, 12:14] > 0).all():
+        print(f"   first atom (thread 0): values + stores {(t[:, 12] - t[:, 1]).mean().item():.0f}, proxy fence {(t[:, 13] - t[:, 12]).mean().item():.0f}, "
+              f"barrier {(t[:, 2] - t[:, 13]).mean().item():.0f}")
+    if (t[:, 8:12] > 0).all():
         print(f"   MMA issue (thread 0): first atom {(t[:, 8] - t[:, 2]).mean().item():.0f} cycles after its build barrier, "
               f"commit +{(t[:, 9] - t[:, 8]).mean().item():.0f}; last atom issue done {(t[:, 10] - t[:, 9]).mean().item():.0f} "
               f"after the first commit, commit +{(t[:, 11] - t[:, 10]).mean().item():.0f}")
@@ -49,7 +52,7 @@ def main():
     dev = torch.device("cuda:0")
     lib = _lib.load()
     tiles = 40
-    buf = torch.zeros(2 * tiles * 12, dtype=torch.int64, device=dev)
+    buf = torch.zeros(2 * tiles * 16, dtype=torch.int64, device=dev)
     Gs, Gc = sf_supports()
     Gs, Gc = Gs.to(dev).requires_grad_(True), Gc.to(dev).requires_grad_(True)
     cell = S.STC_Cell(100, 5, 2, 2, Din, 16).to(dev)
@@ -62,13 +65,13 @@ def main():
     _lib.check(lib.stc_debug_trace_set(buf.data_ptr(), buf.numel()), "trace_set")
     out = cell(Gs=Gs, Gc=Gc, Xt=X, Ht_1=H)
     torch.cuda.synchronize()
-    report("conv_fwd gates", buf[: tiles * 12].clone(), tiles, FWD)
-    report("conv_fwd candidate", buf[tiles * 12:].clone(), tiles, FWD)
+    report("conv_fwd gates", buf[: tiles * 16].clone(), tiles, FWD)
+    report("conv_fwd candidate", buf[tiles * 16:].clone(), tiles, FWD)
     buf.zero_()
     out.sum().backward()
     torch.cuda.synchronize()
-    report("conv_bwd_dx gates", buf[: tiles * 12].clone(), tiles, DX)
-    report("conv_bwd_dx candidate", buf[tiles * 12:].clone(), tiles, DX)
+    report("conv_bwd_dx gates", buf[: tiles * 16].clone(), tiles, DX)
+    report("conv_bwd_dx candidate", buf[tiles * 16:].clone(), tiles, DX)
     lib.stc_debug_trace_set(None, 0)
 
 

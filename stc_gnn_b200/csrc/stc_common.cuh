@@ -146,7 +146,7 @@ struct ConvArgs {
   long long* trace;    // [trace_tiles][TRACE_SLOTS] clock64 stamps of CTA 0's first tiles, or null
   int trace_tiles;
 };
-enum { OPT_L2_PREFETCH = 1, OPT_BATCHED_PROLOGUE = 2, OPT_GENERIC_EPILOGUE = 4 /* diagnostic: force the general epilogues */ };
+enum { OPT_L2_PREFETCH = 1, OPT_GENERIC_EPILOGUE = 4 /* diagnostic: force the general epilogues */ };
 constexpr int TRACE_SLOTS = 16;
 int conv_opt_flags();                                  // cached STC_OPT (default: OPT_L2_PREFETCH)
 void conv_trace_target(long long** buf, int* tiles);   // what stc_debug_trace_set registered (null when off)

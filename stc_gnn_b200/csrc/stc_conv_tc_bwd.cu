@@ -106,8 +106,7 @@ __device__ __forceinline__ void dx_prefetch_tile(const ConvArgs& a, const TcDxPl
 }
 
 // FAST: contiguous-column epilogue of the common shape (Ks = 2, h = 16, Din <= 16, one main accumulator)
-// BATCHED: the elementwise adjoint issues the loads of two items before the first use (12 x 16 bytes in flight per thread)
-template <bool FAST, bool BATCHED>
+template <bool FAST>
 __global__ void __launch_bounds__(CV_THREADS, 2)
 tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -235,39 +234,18 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
         *reinterpret_cast<float4*>(Dh + row * h + j) = dir;
       }
     };
-    if constexpr (BATCHED) {
-      for (int it0 = tid; it0 < 128 * cpr; it0 += 2 * CV_THREADS) {
-        DxIn in[2];
-        int row[2], j[2];
-        bool live[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int it = it0 + u * CV_THREADS;
-          row[u] = it / cpr;
-          j[u] = (it - row[u] * cpr) << 2;
-          live[u] = it < 128 * cpr && row[u] < rows_valid;
-          if (live[u]) dx_load(a, (row0 + row[u]) * h + j[u], in[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (it0 + u * CV_THREADS >= 128 * cpr) continue;
-          float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
-          if (live[u]) dx_adjoint(a, in[u], g0v, g1v, dir);
-          emit_item(row[u], j[u], g0v, g1v, dir, live[u]);
-        }
+    // (issuing both rounds' loads before the first use was measured: shorter prologue, slower kernel -- the extra
+    //  48 live registers spill)
+    for (int it = tid; it < 128 * cpr; it += CV_THREADS) {
+      const int row = it / cpr, j = (it - row * cpr) << 2;
+      float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
+      const bool live = row < rows_valid;
+      if (live) {
+        DxIn in;
+        dx_load(a, (row0 + row) * h + j, in);
+        dx_adjoint(a, in, g0v, g1v, dir);
       }
-    } else {
-      for (int it = tid; it < 128 * cpr; it += CV_THREADS) {
-        const int row = it / cpr, j = (it - row * cpr) << 2;
-        float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v, dir = g0v;
-        const bool live = row < rows_valid;
-        if (live) {
-          DxIn in;
-          dx_load(a, (row0 + row) * h + j, in);
-          dx_adjoint(a, in, g0v, g1v, dir);
-        }
-        emit_item(row, j, g0v, g1v, dir, live);
-      }
+      emit_item(row, j, g0v, g1v, dir, live);
     }
     __syncthreads();
     STC_TRACE(1);
@@ -609,9 +587,7 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
     return STC_ERR_UNSUPPORTED;
   }
   const bool fast = a.Ks == 2 && a.h == 16 && a.Din <= 16 && p.nmain == 1 && !(a.opt & OPT_GENERIC_EPILOGUE);
-  const bool batched = (a.opt & OPT_BATCHED_PROLOGUE) != 0;
-  auto kern = fast ? (batched ? tc_conv_bwd_dx_kernel<true, true> : tc_conv_bwd_dx_kernel<true, false>)
-                   : (batched ? tc_conv_bwd_dx_kernel<false, true> : tc_conv_bwd_dx_kernel<false, false>);
+  auto kern = fast ? tc_conv_bwd_dx_kernel<true> : tc_conv_bwd_dx_kernel<false>;
   STC_TRY(set_smem(kern, p.smem_bytes));
   int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;

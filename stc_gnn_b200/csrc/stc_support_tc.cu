@@ -178,6 +178,23 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
     float* Obuf = reinterpret_cast<float*>(smem + p.off_o);
     const int et = tid - 32 * (1 + TS_PROD_WARPS);   // 0..127
     const int ch = et & 15, er0 = et >> 4;           // global side: 16-byte chunk `ch` of rows er0 + 8 i
+    // Z travels one tile ahead in registers (same coalesced chunk pattern as the Y stores): its latency is covered by
+    // the previous tile's drain instead of being exposed once per tile
+    constexpr int ZR = 16;                           // rows er0 + 8 i, i < ZR  (N <= 128)
+    float4 zreg[ZR];
+    auto fetch_z = [&](long long tile) {
+      const long long cg = tile * TS_NT + 4 * ch;
+      const bool ok = tile < p.ntiles && cg < p.total_cols;
+      const long long b = ok ? cg / W : 0;
+      const float* zsrc = Z + b * z_bs + (cg - b * W);
+#pragma unroll
+      for (int i = 0; i < ZR; ++i) {
+        const int r = er0 + 8 * i;
+        zreg[i] = (ok && r < N) ? *reinterpret_cast<const float4*>(zsrc + (long long)r * W)   // plain load: Y may alias Z
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (use_z) fetch_z(blockIdx.x);
     int it = 0;
     for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
       const int ab = it & 1;
@@ -185,15 +202,14 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
       const bool cok = cgc < p.total_cols;
       const long long bc = cok ? cgc / W : 0;
       const int jc = (int)(cgc - bc * W);
-      if (use_z) {   // Z tile, coalesced, while the MMAs of this tile are still running
-        const float* zsrc = Z + bc * z_bs + jc;
-#pragma unroll 4
-        for (int r = er0; r < N; r += 8) {
-          float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (cok) z = *reinterpret_cast<const float4*>(zsrc + (long long)r * W);   // plain load: Y may alias Z
-          *reinterpret_cast<float4*>(Obuf + r * TS_OLD + 4 * ch) = z;
+      if (use_z) {
+#pragma unroll
+        for (int i = 0; i < ZR; ++i) {
+          const int r = er0 + 8 * i;
+          if (r < N) *reinterpret_cast<float4*>(Obuf + r * TS_OLD + 4 * ch) = zreg[i];
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        fetch_z(tile + stride);
       }
       mbar_wait(&accfull[ab], (uint32_t)(it >> 1) & 1u);
       fence_after_sync();
@@ -339,8 +355,10 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
   uint32_t soff[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) soff[i] = atom_chunk_offset(r0 + 32 * i, q);
-  float4 ra[4], rb[4];
-  auto fetch = [&](int s, int at) {   // s-th sample of this CTA, atom `at` within the sample
+  // two register sets: the operands of atom seq + 2 are requested right after atom seq has been staged, so two atoms
+  // (2 x 25 KB per SM) are always in flight -- one was not enough to cover the HBM latency (Little's law)
+  float4 ra0[4], rb0[4], ra1[4], rb1[4];
+  auto fetch = [&](int s, int at, float4 (&ra)[4], float4 (&rb)[4]) {   // s-th sample of this CTA, atom `at` within the sample
     const long long b = blockIdx.x + s * (long long)gridDim.x;
     const int j = at * ATOM_K + q * 4;
     const bool ok = j < W;               // W % 4 == 0
@@ -354,7 +372,7 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
       rb[i] = live ? __ldg(reinterpret_cast<const float4*>(pb + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  auto stage = [&](int buf) {
+  auto stage = [&](int buf, const float4 (&ra)[4], const float4 (&rb)[4]) {
     uint8_t* base = smem + (size_t)buf * bufsz;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -416,16 +434,24 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
     since_drain = 0;
   };
 
-  if (natoms > 0) fetch(0, 0);
-  int cur_s = 0, at = 0;               // (sample, atom) of `seq`, advanced without divisions
-  for (long long seq = 0; seq < natoms; ++seq) {
+  int at = 0;                           // atom of `seq` within its sample
+  int pf_s = 0, pf_at = 0;              // (sample, atom) the next fetch targets: runs two atoms ahead, no divisions
+  auto advance_pf = [&]() {
+    if (++pf_at == p.atoms_per_sample) {
+      pf_at = 0;
+      ++pf_s;
+    }
+  };
+  auto step = [&](long long seq, float4 (&ra)[4], float4 (&rb)[4]) {
     const int buf = (int)(seq & 1);
     if (pend[buf]) {   // the MMAs that read this buffer two atoms ago
       mbar_wait(&bars[buf], ph[buf]);
       ph[buf] ^= 1u;
       pend[buf] = false;
     }
-    stage(buf);
+    stage(buf, ra, rb);
+    if (seq + 2 < natoms) fetch(pf_s, pf_at, ra, rb);
+    advance_pf();
     fence_async_smem();
     __syncthreads();
     const int kleft = W - at * ATOM_K;
@@ -443,12 +469,16 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
     acc_small = true;
     pend[buf] = true;
     ++since_drain;
-    if (++at == p.atoms_per_sample) {
-      at = 0;
-      ++cur_s;
-    }
-    if (seq + 1 < natoms) fetch(cur_s, at);
+    if (++at == p.atoms_per_sample) at = 0;
     if (since_drain >= TO_DRAIN) drain();
+  };
+  if (natoms > 0) fetch(pf_s, pf_at, ra0, rb0);
+  advance_pf();
+  if (natoms > 1) fetch(pf_s, pf_at, ra1, rb1);
+  advance_pf();
+  for (long long seq = 0; seq < natoms; seq += 2) {
+    step(seq, ra0, rb0);
+    if (seq + 1 < natoms) step(seq + 1, ra1, rb1);
   }
   if (since_drain > 0) drain();
 

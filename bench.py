@@ -42,7 +42,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--batch", type=int, default=4096, help="windows per GPU per step (weak scaling)")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--cpu-batch", type=int, default=32, help="windows per CPU-baseline step (bounded sample)")
+    p.add_argument("--cpu-batch", type=int, default=128, help="windows per CPU-baseline step (bounded sample)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true", help="skip the instrumented per-kernel pass")
     p.add_argument("--cuda-graph", action="store_true",

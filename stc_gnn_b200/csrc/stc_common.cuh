@@ -146,7 +146,8 @@ struct ConvArgs {
   long long* trace;    // [trace_tiles][TRACE_SLOTS] clock64 stamps of CTA 0's first tiles, or null
   int trace_tiles;
 };
-enum { OPT_L2_PREFETCH = 1, OPT_GENERIC_EPILOGUE = 4 /* diagnostic: force the general epilogues */ };
+enum { OPT_L2_PREFETCH = 1, OPT_GENERIC_EPILOGUE = 4 /* diagnostic: force the general epilogues */,
+       OPT_SMEM_A = 8 /* diagnostic: forward convolution with the A operand staged in shared memory */ };
 constexpr int TRACE_SLOTS = 16;
 int conv_opt_flags();                                  // cached STC_OPT (default: OPT_L2_PREFETCH)
 void conv_trace_target(long long** buf, int* tiles);   // what stc_debug_trace_set registered (null when off)

@@ -551,6 +551,294 @@ tc_conv_fwd_kernel(const ConvArgs a, const TcFwdPlan p) {
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// =================================================================================================
+// A-in-TMEM forward kernel for the common shape (Ks = 2, Kc = 2, h = 16, Din <= 16; SF: N=100, C=5).
+//
+// Measured on the kernel above (profiles/r1k_phase_trace.txt): the tensor core's own operand fetch dominates the
+// shared-memory traffic of a tile (every K-step re-reads A_hi twice and A_lo once: 12 KB for 2 KB of B), the single
+// A buffer forces an MMA round trip in the middle of the tile, and each A build costs a proxy fence + block barrier.
+// Here the data rows never touch shared memory: thread (row, half) loads the 32 K-values of spatial term k = half
+// of its own row straight from global memory, splits them and writes hi / lo into TENSOR MEMORY columns of its
+// accumulator lane (tcgen05.st); the MMAs take A from TMEM (tcgen05.mma with a TMEM A operand) and only the resident
+// weight atoms from shared memory.  One block barrier per tile before the (24) MMAs, no mid-tile wait, no staging
+// buffers.  TMEM columns: [0, Npad) main accumulator, [Npad, 2 Npad) cross terms, then A_hi (64) and A_lo (64).
+template <int NG>
+__device__ __forceinline__ void tc_fwd_epilogue_regs(const ConvArgs& a, const TcFwdPlan& p, uint32_t tl, float* Pm,
+                                                     const float* Qs, const float* bias_s, const float4 (&hp)[2],
+                                                     const float4 (&uu)[2], int erow, int enode, int ecat, int half,
+                                                     bool valid, long long gr) {
+  const int h = a.h, C = a.C, Hout = a.Hout;
+  const int cb = half * 8;
+  uint32_t sm1[NG][8], mn1[NG][8];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {                                          // P_1: cross terms, then main
+    tmem_ld8_async(tl + (uint32_t)(p.Npad + Hout + 16 * g + cb), sm1[g]);
+    tmem_ld8_async(tl + (uint32_t)(Hout + 16 * g + cb), mn1[g]);
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    tmem_ld_pin8(sm1[g]); tmem_ld_pin8(mn1[g]);
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = __uint_as_float(sm1[g][i]) + __uint_as_float(mn1[g][i]);
+    float* pm = Pm + erow * p.PS + 16 * g + cb;
+    *reinterpret_cast<float4*>(pm) = make_float4(t[0], t[1], t[2], t[3]);
+    *reinterpret_cast<float4*>(pm + 4) = make_float4(t[4], t[5], t[6], t[7]);
+    if (a.Psave && valid) {   // backward forms dGc from these partials (no recomputation of the GEMM)
+      float* ps = a.Psave + gr * (long long)Hout + 16 * g + cb;
+      *reinterpret_cast<float4*>(ps) = make_float4(t[0], t[1], t[2], t[3]);
+      *reinterpret_cast<float4*>(ps + 4) = make_float4(t[4], t[5], t[6], t[7]);
+    }
+  }
+  uint32_t sm0[NG][8], mn0[NG][8];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {                                          // P_0 travels under the barrier
+    tmem_ld8_async(tl + (uint32_t)(p.Npad + 16 * g + cb), sm0[g]);
+    tmem_ld8_async(tl + (uint32_t)(16 * g + cb), mn0[g]);
+  }
+  __syncthreads();
+  tmem_ld_wait();
+  float v[NG][8];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    tmem_ld_pin8(sm0[g]); tmem_ld_pin8(mn0[g]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[g][i] = __uint_as_float(sm0[g][i]) + __uint_as_float(mn0[g][i]);
+  }
+  {
+    const float* pp = Pm + (enode * C) * p.PS + cb;
+    for (int cp = 0; cp < C; ++cp) {
+      const float w = Qs[cp * C + ecat];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float4 x0 = *reinterpret_cast<const float4*>(pp + cp * p.PS + 16 * g);
+        const float4 x1 = *reinterpret_cast<const float4*>(pp + cp * p.PS + 16 * g + 4);
+        v[g][0] = fmaf(w, x0.x, v[g][0]); v[g][1] = fmaf(w, x0.y, v[g][1]);
+        v[g][2] = fmaf(w, x0.z, v[g][2]); v[g][3] = fmaf(w, x0.w, v[g][3]);
+        v[g][4] = fmaf(w, x1.x, v[g][4]); v[g][5] = fmaf(w, x1.y, v[g][5]);
+        v[g][6] = fmaf(w, x1.z, v[g][6]); v[g][7] = fmaf(w, x1.w, v[g][7]);
+      }
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 16 * g + cb);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 16 * g + cb + 4);
+    v[g][0] += b0.x; v[g][1] += b0.y; v[g][2] += b0.z; v[g][3] += b0.w;
+    v[g][4] += b1.x; v[g][5] += b1.y; v[g][6] += b1.z; v[g][7] += b1.w;
+    if (a.act == STC_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[g][i] = fmaxf(v[g][i], 0.f);
+    }
+  }
+  const float hpv[8] = {hp[0].x, hp[0].y, hp[0].z, hp[0].w, hp[1].x, hp[1].y, hp[1].z, hp[1].w};
+  if (a.phase == 0) {   // h = 16, Hout = 32: group 0 = u channels cb.., group 1 = r channels cb..
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[g][i] = sigmoidf_fast(v[g][i]);
+      const int col = 16 * g + cb;
+      if (col < h) {
+        float* dst = a.u + gr * h + col;
+        *reinterpret_cast<float4*>(dst) = make_float4(v[g][0], v[g][1], v[g][2], v[g][3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[g][4], v[g][5], v[g][6], v[g][7]);
+      } else {
+        const int ch = col - h;   // == cb
+        float* dr = a.r + gr * h + ch;
+        *reinterpret_cast<float4*>(dr) = make_float4(v[g][0], v[g][1], v[g][2], v[g][3]);
+        *reinterpret_cast<float4*>(dr + 4) = make_float4(v[g][4], v[g][5], v[g][6], v[g][7]);
+        float* drh = a.rH + gr * h + ch;
+        *reinterpret_cast<float4*>(drh) = make_float4(v[g][0] * hpv[0], v[g][1] * hpv[1], v[g][2] * hpv[2], v[g][3] * hpv[3]);
+        *reinterpret_cast<float4*>(drh + 4) = make_float4(v[g][4] * hpv[4], v[g][5] * hpv[5], v[g][6] * hpv[6], v[g][7] * hpv[7]);
+      }
+    }
+  } else {              // Hout = h = 16: one group, channels cb..: c = tanh, H' = H + u (c - H)
+    const float uuv[8] = {uu[0].x, uu[0].y, uu[0].z, uu[0].w, uu[1].x, uu[1].y, uu[1].z, uu[1].w};
+    const long long o = gr * h + cb;
+    float cc[8], hn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      cc[i] = tanhf_fast(v[0][i]);
+      hn[i] = fmaf(uuv[i], cc[i] - hpv[i], hpv[i]);
+    }
+    *reinterpret_cast<float4*>(a.c + o) = make_float4(cc[0], cc[1], cc[2], cc[3]);
+    *reinterpret_cast<float4*>(a.c + o + 4) = make_float4(cc[4], cc[5], cc[6], cc[7]);
+    *reinterpret_cast<float4*>(a.Hnew + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    *reinterpret_cast<float4*>(a.Hnew + o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+  }
+}
+
+template <int NG>
+__global__ void __launch_bounds__(CV_THREADS, 2)
+tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, L = a.Din + a.h, Din = a.Din, Hout = a.Hout;
+  constexpr int h = 16;
+  const uint32_t atomB = (uint32_t)p.Npad * ATOM_ROW_BYTES;
+  float* Pm = reinterpret_cast<float*>(smem + p.off_a);          // [128][PS] exchange buffer of the categorical mix
+  uint8_t* B_hi = smem + p.off_b;                                // [2][atomB] resident weight atoms (spatial term 0, 1)
+  uint8_t* B_lo = B_hi + (size_t)2 * atomB;
+  float* Qs = reinterpret_cast<float*>(smem + p.off_q);
+  float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  for (int i = tid; i < C * C; i += CV_THREADS) Qs[i] = a.Q[C * C + i];
+  for (int i = tid; i < Hout; i += CV_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
+  for (int k = 0; k < 2; ++k) {   // Bt[(c,o)][kb] = W[((k*Kc + c)*L + l(kb))*Hout + o], K order [h-part | x-part | zero pad]
+    uint8_t* bh = B_hi + (size_t)k * atomB;
+    uint8_t* bl = B_lo + (size_t)k * atomB;
+    for (int it = tid; it < p.Npad * 8; it += CV_THREADS) {
+      const int n = it >> 3, qq = it & 7;
+      const int c = n / Hout, o = n - c * Hout;
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kb = qq * 4 + i;
+        const int l = kb < h ? Din + kb : (kb - h < Din ? kb - h : -1);
+        v[i] = (n < p.Ntot && l >= 0) ? a.W[((size_t)(k * 2 + c) * L + l) * Hout + o] : 0.f;
+      }
+      store_split4(bh, bl, atom_chunk_offset(n, qq), make_float4(v[0], v[1], v[2], v[3]));
+    }
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const int warp_u = uniform_warp_index();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  const uint32_t idesc = make_idesc_tf32(128, p.Npad);
+  const uint32_t d_main = tmem_base, d_small = tmem_base + (uint32_t)p.Npad;
+  const uint32_t colA = (uint32_t)(2 * p.Npad);              // A_hi columns [colA, colA+64), A_lo [colA+64, colA+128)
+  const uint64_t dB_hi = make_smem_desc_sw128(smem_u32(B_hi)), dB_lo = make_smem_desc_sw128(smem_u32(B_lo));
+  const int ksteps = p.KBL >> 3;                             // 3 (Din <= 8) or 4 K-steps per spatial term
+  const long long total_nodes = (long long)a.B * a.N;
+  const long long R = total_nodes * C;
+
+  const int sp = warp & 3, half = warp >> 2;
+  const int erow = sp * 32 + lane;                           // accumulator lane = tile row
+  const int enode = erow / C, ecat = erow - enode * C;
+  const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
+  const uint32_t tA = tl + colA + (uint32_t)(half * 32);     // this thread writes term k = half of its row
+  const bool xvec = p.x_bulk != 0;
+  uint32_t mma_phase = 0;
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
+  int trace_it = 0;
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long g0 = (long long)tile * p.npt;
+    const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
+    const int rows_valid = nodes_valid * C;
+    const bool valid = erow < rows_valid;
+    const long long gr = g0 * C + erow;
+    STC_TRACE(0);
+    if ((a.opt & OPT_L2_PREFETCH) && warp_u == 1 && tile + (int)gridDim.x < p.ntiles && elect_one_sync())
+      tc_prefetch_tile(a, p, tile + gridDim.x);
+    // ---- my row's K-values of spatial term k = half: [h-part (16) | x-part (Din) | zeros] ----
+    float4 xv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const float* hs = (half == 0 ? a.h0 : a.yh) + gr * h;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(hs + 4 * i);
+      const float* xs;
+      if (half == 0) {
+        const long long g = g0 + enode;
+        const long long b = g / a.N;
+        xs = a.x0 + b * a.x0_bs + ((g - b * a.N) * C + ecat) * Din;
+      } else {
+        xs = a.yx + gr * Din;
+      }
+      if (xvec) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (4 * i < Din) xv[4 + i] = *reinterpret_cast<const float4*>(xs + 4 * i);
+      } else {
+        float e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = i < Din ? xs[i] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[4 + i] = make_float4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
+      }
+    }
+    STC_TRACE(1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // 8 columns at a time: hi into A_hi, lo into A_lo
+      float hi[8], lo[8];
+      split_tf32(xv[2 * i].x, hi[0], lo[0]); split_tf32(xv[2 * i].y, hi[1], lo[1]);
+      split_tf32(xv[2 * i].z, hi[2], lo[2]); split_tf32(xv[2 * i].w, hi[3], lo[3]);
+      split_tf32(xv[2 * i + 1].x, hi[4], lo[4]); split_tf32(xv[2 * i + 1].y, hi[5], lo[5]);
+      split_tf32(xv[2 * i + 1].z, hi[6], lo[6]); split_tf32(xv[2 * i + 1].w, hi[7], lo[7]);
+      tmem_st8(tA + (uint32_t)(8 * i), hi);
+      tmem_st8(tA + 64u + (uint32_t)(8 * i), lo);
+    }
+    tmem_st_wait();
+    STC_TRACE(12);
+    fence_before_sync();
+    STC_TRACE(13);
+    __syncthreads();
+    STC_TRACE(2);
+    STC_TRACE(3);
+    if (warp_u == 0 && elect_one_sync()) {
+      fence_after_sync();
+      uint32_t acc = 0u;
+#pragma unroll
+      for (int ai = 0; ai < 2; ++ai) {
+        const uint64_t bo = (uint64_t)(((uint32_t)ai * atomB) >> 4);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t ko = (uint64_t)(ks * 2);
+          const uint32_t ah = tmem_base + colA + (uint32_t)(ai * 32 + ks * 8), al = ah + 64u;
+          mma_tf32_atmem(d_small, al, dB_hi + bo + ko, idesc, acc);
+          mma_tf32_atmem(d_small, ah, dB_lo + bo + ko, idesc, 1u);
+          mma_tf32_atmem(d_main, ah, dB_hi + bo + ko, idesc, acc);
+          acc = 1u;
+        }
+      }
+      STC_TRACE(8);
+      STC_TRACE(10);
+      mma_commit(mma_bar);
+      STC_TRACE(9);
+      STC_TRACE(11);
+    }
+    // ---- the epilogue's own operands travel under the MMAs: H (and u for the candidate), 8 channels of my row ----
+    float4 hp[2], uu[2];
+    hp[0] = hp[1] = uu[0] = uu[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const float* hsrc = a.Hprev + gr * h + half * 8;
+      hp[0] = *reinterpret_cast<const float4*>(hsrc);
+      hp[1] = *reinterpret_cast<const float4*>(hsrc + 4);
+      if (a.phase != 0) {
+        const float* usrc = a.u + gr * h + half * 8;
+        uu[0] = *reinterpret_cast<const float4*>(usrc);
+        uu[1] = *reinterpret_cast<const float4*>(usrc + 4);
+      }
+    }
+    STC_TRACE(4);
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1u;
+    fence_after_sync();
+    STC_TRACE(5);
+    STC_TRACE(6);
+    tc_fwd_epilogue_regs<NG>(a, p, tl, Pm, Qs, bias_s, hp, uu, erow, enode, ecat, half, valid, gr);
+    STC_TRACE(7);
+    ++trace_it;
+    fence_before_sync();   // TMEM reads precede the next tile's TMEM stores and MMAs; Pm is free for the next exchange
+    __syncthreads();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 static bool tc_disabled() {
   static int cached = -1;
   if (cached < 0) {
@@ -630,6 +918,19 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
   int ng = 0;
   if (a.Kc == 2 && p.nmain == 1 && (a.Hout == 16 || a.Hout == 32) && !(a.opt & OPT_GENERIC_EPILOGUE)) ng = a.Hout / 16;
   auto kern = ng == 2 ? tc_conv_fwd_kernel<2> : (ng == 1 ? tc_conv_fwd_kernel<1> : tc_conv_fwd_kernel<0>);
+  // A-in-TMEM variant: additionally Ks = 2, h = 16, one atom per spatial term (Din <= 16)
+  const bool at = ng != 0 && a.Ks == 2 && a.h == 16 && p.KB == 1 && !(a.opt & OPT_SMEM_A);
+  if (at) {
+    kern = ng == 2 ? tc_conv_fwd_at_kernel<2> : tc_conv_fwd_at_kernel<1>;
+    size_t q = 0;
+    p.off_a = (uint32_t)q; q += round_up((size_t)128 * p.PS * sizeof(float), 1024);   // exchange buffer
+    p.off_b = (uint32_t)q; q += 2 * (size_t)2 * atomB;                               // resident W atoms hi/lo
+    p.off_q = (uint32_t)q; q += round_up((size_t)a.C * a.C * sizeof(float), 16);
+    p.off_bias = (uint32_t)q; q += round_up((size_t)a.Hout * sizeof(float), 16);
+    p.off_bar = (uint32_t)q; q += 32;
+    p.smem_bytes = (uint32_t)q;
+    p.tmem_cols = 256;   // 2 Npad accumulator columns + 128 A columns
+  }
   STC_TRY(set_smem(kern, p.smem_bytes));
   int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;

@@ -106,7 +106,10 @@ __device__ __forceinline__ void dx_prefetch_tile(const ConvArgs& a, const TcDxPl
 }
 
 // FAST: contiguous-column epilogue of the common shape (Ks = 2, h = 16, Din <= 16, one main accumulator)
-template <bool FAST>
+// AT (implies FAST, Kc = 2): the A operand [Ds | Dm_1] goes from registers straight into TENSOR MEMORY (tcgen05.st) and
+//     the MMAs read it from there -- no A atoms in shared memory, no proxy fence, no MMA round trip between atoms
+//     (see tc_conv_fwd_at_kernel in stc_conv_tc.cu for the measurements behind this)
+template <bool FAST, bool AT>
 __global__ void __launch_bounds__(CV_THREADS, 2)
 tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -254,68 +257,139 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       for (int row = db_grp; row < rows_valid; row += db_groups) s += Dsm[row * DP + db_col];
       db_acc += s;
     }
-    // ---- 2. DD atoms + MMAs ----
-    bool acc_small = false;
-    for (int ja = 0; ja < p.KA; ++ja) {
-      const int kk = ja * ATOM_K + q * 4;
-      const int c = kk / Hout, o0 = kk - c * Hout;
-      float4 vv[4];   // the atom's values are formed while the previous atom's MMAs still read the single A buffer
+    if constexpr (AT) {
+      // ---- 2'. my row's share of the A operand: Ds columns [cw*half, +cw) and the same columns of Dm_1 ----
+      const int cw = Hout >> 1;                        // 8 (candidate) or 16 (gates)
+      const int cbase = cw * half;
+      const int enode = erow / C, ecat = erow - enode * C;
+      const float* qrow = Qs + ecat * C;               // Dm_1[(node,c')][o] = sum_d Q_1[c'][d] Ds[(node,d)][o]
+      const uint32_t tA = tl + (uint32_t)(2 * p.Npad);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kk < p.Kdd) {
-          if (c == 0) {
-            v = *reinterpret_cast<const float4*>(Dsm + (r0 + 32 * i) * DP + o0);
-          } else {  // Dm_c[(node,c')][o] = sum_d Q_c[c'][d] Ds[(node,d)][o]
-            const float* Qc = Qs + (size_t)(c - 1) * C * C + rcat[i] * C;
-            const float* sp = Dsm + rnode[i] * C * DP + o0;
-            for (int d = 0; d < C; ++d) {
-              const float w = Qc[d];
-              const float4 x = *reinterpret_cast<const float4*>(sp + d * DP);
-              v.x = fmaf(w, x.x, v.x); v.y = fmaf(w, x.y, v.y); v.z = fmaf(w, x.z, v.z); v.w = fmaf(w, x.w, v.w);
-            }
-            if (r0 + 32 * i < rows_valid)   // the dW kernel contracts Y_k^T with [Ds | Dm_1 | ...] straight from HBM
-              *reinterpret_cast<float4*>(a.dpre + (row0 + r0 + 32 * i) * p.Kdd + kk) = v;
+      for (int part = 0; part < 2; ++part) {           // 8 columns at a time (cw == 8: one part)
+        if (part * 8 < cw) {
+          const int col = cbase + part * 8;
+          float ds[8], dm[8];
+          {
+            const float4 x0 = *reinterpret_cast<const float4*>(Dsm + erow * DP + col);
+            const float4 x1 = *reinterpret_cast<const float4*>(Dsm + erow * DP + col + 4);
+            ds[0] = x0.x; ds[1] = x0.y; ds[2] = x0.z; ds[3] = x0.w; ds[4] = x1.x; ds[5] = x1.y; ds[6] = x1.z; ds[7] = x1.w;
           }
-        }
-        vv[i] = v;
-      }
-      if (mma_pending) {
-        mbar_wait(mma_bar, mma_phase);
-        mma_phase ^= 1u;
-        mma_pending = false;
-      }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) store_split4(A_hi, A_lo, aoff[i], vv[i]);
-      if (ja == 0) STC_TRACE(12);
-      fence_async_smem();
-      if (ja == 0) STC_TRACE(13);
-      __syncthreads();
-      if (ja == 0) STC_TRACE(2);
-      if (warp_u == 0 && elect_one_sync()) {   // one lane of converged warp 0: descriptors stay in uniform registers
-        fence_after_sync();
-        const int kleft = p.Kdd - ja * ATOM_K;
-        const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
-        const uint64_t bo = (uint64_t)(((uint32_t)ja * atomB) >> 4);
-        const uint32_t d_main = tmem_base + (uint32_t)((ja / DX_APM) * p.Npad);
-        uint32_t acc_main = (ja % DX_APM) != 0 ? 1u : 0u;
-#pragma unroll 4
-        for (int ks = 0; ks < ksteps; ++ks) {   // small cross terms into their own accumulator, then the main product
-          const uint64_t ko = (uint64_t)(ks * 2);
-          mma_tf32(d_small, dA_lo + ko, dB_hi + bo + ko, idesc, acc_small ? 1u : 0u);
-          mma_tf32(d_small, dA_hi + ko, dB_lo + bo + ko, idesc, 1u);
-          mma_tf32(d_main, dA_hi + ko, dB_hi + bo + ko, idesc, acc_main);
-          acc_main = 1u;
-          acc_small = true;
+          for (int i = 0; i < 8; ++i) dm[i] = 0.f;
+          const float* sp = Dsm + (enode * C) * DP + col;
+          for (int d = 0; d < C; ++d) {
+            const float w = qrow[d];
+            const float4 x0 = *reinterpret_cast<const float4*>(sp + d * DP);
+            const float4 x1 = *reinterpret_cast<const float4*>(sp + d * DP + 4);
+            dm[0] = fmaf(w, x0.x, dm[0]); dm[1] = fmaf(w, x0.y, dm[1]); dm[2] = fmaf(w, x0.z, dm[2]); dm[3] = fmaf(w, x0.w, dm[3]);
+            dm[4] = fmaf(w, x1.x, dm[4]); dm[5] = fmaf(w, x1.y, dm[5]); dm[6] = fmaf(w, x1.z, dm[6]); dm[7] = fmaf(w, x1.w, dm[7]);
+          }
+          if (erow < rows_valid) {   // the dW kernel contracts Y_k^T with [Ds | Dm_1] straight from HBM
+            float* dp = a.dpre + (row0 + erow) * p.Kdd + Hout + col;
+            *reinterpret_cast<float4*>(dp) = make_float4(dm[0], dm[1], dm[2], dm[3]);
+            *reinterpret_cast<float4*>(dp + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
+          }
+          float hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_tf32(ds[i], hi[i], lo[i]);
+          tmem_st8(tA + (uint32_t)col, hi);
+          tmem_st8(tA + 64u + (uint32_t)col, lo);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_tf32(dm[i], hi[i], lo[i]);
+          tmem_st8(tA + (uint32_t)(Hout + col), hi);
+          tmem_st8(tA + 64u + (uint32_t)(Hout + col), lo);
         }
-        if (ja == 0) STC_TRACE(8);
-        if (ja == p.KA - 1) STC_TRACE(10);
-        mma_commit(mma_bar);
-        if (ja == 0) STC_TRACE(9);
-        if (ja == p.KA - 1) STC_TRACE(11);
       }
-      acc_small = true;
+      tmem_st_wait();
+      STC_TRACE(12);
+      fence_before_sync();
+      STC_TRACE(13);
+      __syncthreads();
+      STC_TRACE(2);
+      if (warp_u == 0 && elect_one_sync()) {
+        fence_after_sync();
+        const uint32_t a0 = tmem_base + (uint32_t)(2 * p.Npad);
+        uint32_t acc = 0u;
+        const int nks = p.Kdd >> 3;
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint64_t bo = (uint64_t)((((uint32_t)(ks >> 2)) * atomB) >> 4) + (uint64_t)((ks & 3) * 2);
+          const uint32_t ah = a0 + (uint32_t)(ks * 8), al = ah + 64u;
+          mma_tf32_atmem(d_small, al, dB_hi + bo, idesc, acc);
+          mma_tf32_atmem(d_small, ah, dB_lo + bo, idesc, 1u);
+          mma_tf32_atmem(tmem_base, ah, dB_hi + bo, idesc, acc);
+          acc = 1u;
+        }
+        STC_TRACE(8);
+        STC_TRACE(10);
+        mma_commit(mma_bar);
+        STC_TRACE(9);
+        STC_TRACE(11);
+      }
       mma_pending = true;
+    } else {
+      // ---- 2. DD atoms + MMAs ----
+      bool acc_small = false;
+      for (int ja = 0; ja < p.KA; ++ja) {
+        const int kk = ja * ATOM_K + q * 4;
+        const int c = kk / Hout, o0 = kk - c * Hout;
+        float4 vv[4];   // the atom's values are formed while the previous atom's MMAs still read the single A buffer
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kk < p.Kdd) {
+            if (c == 0) {
+              v = *reinterpret_cast<const float4*>(Dsm + (r0 + 32 * i) * DP + o0);
+            } else {  // Dm_c[(node,c')][o] = sum_d Q_c[c'][d] Ds[(node,d)][o]
+              const float* Qc = Qs + (size_t)(c - 1) * C * C + rcat[i] * C;
+              const float* sp = Dsm + rnode[i] * C * DP + o0;
+              for (int d = 0; d < C; ++d) {
+                const float w = Qc[d];
+                const float4 x = *reinterpret_cast<const float4*>(sp + d * DP);
+                v.x = fmaf(w, x.x, v.x); v.y = fmaf(w, x.y, v.y); v.z = fmaf(w, x.z, v.z); v.w = fmaf(w, x.w, v.w);
+              }
+              if (r0 + 32 * i < rows_valid)   // the dW kernel contracts Y_k^T with [Ds | Dm_1 | ...] straight from HBM
+                *reinterpret_cast<float4*>(a.dpre + (row0 + r0 + 32 * i) * p.Kdd + kk) = v;
+            }
+          }
+          vv[i] = v;
+        }
+        if (mma_pending) {
+          mbar_wait(mma_bar, mma_phase);
+          mma_phase ^= 1u;
+          mma_pending = false;
+        }
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) store_split4(A_hi, A_lo, aoff[i], vv[i]);
+        if (ja == 0) STC_TRACE(12);
+        fence_async_smem();
+        if (ja == 0) STC_TRACE(13);
+        __syncthreads();
+        if (ja == 0) STC_TRACE(2);
+        if (warp_u == 0 && elect_one_sync()) {   // one lane of converged warp 0: descriptors stay in uniform registers
+          fence_after_sync();
+          const int kleft = p.Kdd - ja * ATOM_K;
+          const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
+          const uint64_t bo = (uint64_t)(((uint32_t)ja * atomB) >> 4);
+          const uint32_t d_main = tmem_base + (uint32_t)((ja / DX_APM) * p.Npad);
+          uint32_t acc_main = (ja % DX_APM) != 0 ? 1u : 0u;
+  #pragma unroll 4
+          for (int ks = 0; ks < ksteps; ++ks) {   // small cross terms into their own accumulator, then the main product
+            const uint64_t ko = (uint64_t)(ks * 2);
+            mma_tf32(d_small, dA_lo + ko, dB_hi + bo + ko, idesc, acc_small ? 1u : 0u);
+            mma_tf32(d_small, dA_hi + ko, dB_lo + bo + ko, idesc, 1u);
+            mma_tf32(d_main, dA_hi + ko, dB_hi + bo + ko, idesc, acc_main);
+            acc_main = 1u;
+            acc_small = true;
+          }
+          if (ja == 0) STC_TRACE(8);
+          if (ja == p.KA - 1) STC_TRACE(10);
+          mma_commit(mma_bar);
+          if (ja == 0) STC_TRACE(9);
+          if (ja == p.KA - 1) STC_TRACE(11);
+        }
+        acc_small = true;
+        mma_pending = true;
+      }
     }
     STC_TRACE(3);
     // ---- 4 (overlaps the MMAs). dQ_c[c'][d] += sum_{node,o} P_c[(node,c')][o] * Ds[(node,d)][o] ----
@@ -587,7 +661,10 @@ int try_launch_conv_bwd_dx_tc(const ConvArgs& a, cudaStream_t st, bool* handled)
     return STC_ERR_UNSUPPORTED;
   }
   const bool fast = a.Ks == 2 && a.h == 16 && a.Din <= 16 && p.nmain == 1 && !(a.opt & OPT_GENERIC_EPILOGUE);
-  auto kern = fast ? tc_conv_bwd_dx_kernel<true> : tc_conv_bwd_dx_kernel<false>;
+  const bool at = fast && a.Kc == 2 && p.Kdd <= 64 && (a.Hout == 16 || a.Hout == 32) && !(a.opt & OPT_SMEM_A);
+  auto kern = at ? tc_conv_bwd_dx_kernel<true, true>
+                 : (fast ? tc_conv_bwd_dx_kernel<true, false> : tc_conv_bwd_dx_kernel<false, false>);
+  if (at) p.tmem_cols = 256;   // 2 Npad accumulator columns + 64 A_hi + 64 A_lo
   STC_TRY(set_smem(kern, p.smem_bytes));
   int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;

@@ -680,8 +680,10 @@ tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
   constexpr int h = 16;
   const uint32_t atomB = (uint32_t)p.Npad * ATOM_ROW_BYTES;
   float* Pm = reinterpret_cast<float*>(smem + p.off_a);          // [128][PS] exchange buffer of the categorical mix
-  uint8_t* B_hi = smem + p.off_b;                                // [2][atomB] resident weight atoms (spatial term 0, 1)
-  uint8_t* B_lo = B_hi + (size_t)2 * atomB;
+  // resident weight atoms, per spatial term [hi (Npad rows) | lo (Npad rows)]: one descriptor over both is the
+  // N = 2 Npad operand [W_hi ; W_lo], so A_hi x [W_hi ; W_lo] fills the main AND the cross-term accumulator in one MMA
+  uint8_t* B_hi = smem + p.off_b;
+  uint8_t* B_lo = B_hi + atomB;
   float* Qs = reinterpret_cast<float*>(smem + p.off_q);
   float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
@@ -699,8 +701,8 @@ tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
   if (use_pf)
     for (int i = 0; i < 8; ++i) pf[i * CV_THREADS + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < 2; ++k) {   // Bt[(c,o)][kb] = W[((k*Kc + c)*L + l(kb))*Hout + o], K order [h-part | x-part | zero pad]
-    uint8_t* bh = B_hi + (size_t)k * atomB;
-    uint8_t* bl = B_lo + (size_t)k * atomB;
+    uint8_t* bh = B_hi + (size_t)k * 2 * atomB;
+    uint8_t* bl = B_lo + (size_t)k * 2 * atomB;
     for (int it = tid; it < p.Npad * 8; it += CV_THREADS) {
       const int n = it >> 3, qq = it & 7;
       const int c = n / Hout, o = n - c * Hout;
@@ -720,10 +722,10 @@ tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
   fence_after_sync();
   const int warp_u = uniform_warp_index();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
-  const uint32_t idesc = make_idesc_tf32(128, p.Npad);
+  const uint32_t idesc = make_idesc_tf32(128, p.Npad), idesc2 = make_idesc_tf32(128, 2 * p.Npad);
   const uint32_t d_main = tmem_base, d_small = tmem_base + (uint32_t)p.Npad;
   const uint32_t colA = (uint32_t)(2 * p.Npad);              // A_hi columns [colA, colA+64), A_lo [colA+64, colA+128)
-  const uint64_t dB_hi = make_smem_desc_sw128(smem_u32(B_hi)), dB_lo = make_smem_desc_sw128(smem_u32(B_lo));
+  const uint64_t dB_hi = make_smem_desc_sw128(smem_u32(B_hi));
   const int ksteps = p.KBL >> 3;                             // 3 (Din <= 8) or 4 K-steps per spatial term
   const long long total_nodes = (long long)a.B * a.N;
   const long long R = total_nodes * C;
@@ -835,13 +837,12 @@ tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
       uint32_t acc = 0u;
 #pragma unroll
       for (int ai = 0; ai < 2; ++ai) {
-        const uint64_t bo = (uint64_t)(((uint32_t)ai * atomB) >> 4);
+        const uint64_t bo = (uint64_t)(((uint32_t)ai * 2u * atomB) >> 4);
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t ko = (uint64_t)(ks * 2);
           const uint32_t ah = tmem_base + colA + (uint32_t)(ai * 32 + ks * 8), al = ah + 64u;
-          mma_tf32_atmem(d_small, al, dB_hi + bo + ko, idesc, acc);
-          mma_tf32_atmem(d_small, ah, dB_lo + bo + ko, idesc, 1u);
-          mma_tf32_atmem(d_main, ah, dB_hi + bo + ko, idesc, acc);
+          mma_tf32_atmem(d_main, ah, dB_hi + bo + ko, idesc2, acc);    // [main | cross] (+)= A_hi x [W_hi ; W_lo]
+          mma_tf32_atmem(d_small, al, dB_hi + bo + ko, idesc, 1u);     // cross += A_lo x W_hi
           acc = 1u;
         }
       }

@@ -121,8 +121,11 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   const uint32_t atomB = (uint32_t)p.Npad * ATOM_ROW_BYTES;
   uint8_t* A_hi = smem + p.off_a;
   uint8_t* A_lo = A_hi + atomA;
-  uint8_t* B_hi = smem + p.off_b;                               // [KA][atomB]
-  uint8_t* B_lo = B_hi + (size_t)p.KA * atomB;
+  // resident weight atoms: [KA][hi] then [KA][lo]; AT: per atom [hi | lo] so that one descriptor over both is the
+  // N = 2 Npad operand [W_hi ; W_lo] (A_hi x [W_hi ; W_lo] fills the main and the cross-term accumulator in one MMA)
+  uint8_t* B_hi = smem + p.off_b;
+  uint8_t* B_lo = B_hi + (AT ? (size_t)atomB : (size_t)p.KA * atomB);
+  const size_t bstride = AT ? 2 * (size_t)atomB : (size_t)atomB;   // distance between consecutive atoms
   float* Dsm = reinterpret_cast<float*>(smem + p.off_ds);       // [128][DP]  plain Ds
   float* Dh = reinterpret_cast<float*>(smem + p.off_dh);        // [128][h]   direct dH terms (gates)
   float* Psm = reinterpret_cast<float*>(smem + p.off_ps);       // [128][PW]  saved P_c tile (bulk copied)
@@ -144,8 +147,8 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   }
   // resident B atoms:  Bt[(k,kb)][(c,o)] = W[((k*Kc + c)*L + l(kb))*Hout + o]
   for (int ja = 0; ja < p.KA; ++ja) {
-    uint8_t* bh = B_hi + (size_t)ja * atomB;
-    uint8_t* bl = B_lo + (size_t)ja * atomB;
+    uint8_t* bh = B_hi + (size_t)ja * bstride;
+    uint8_t* bl = B_lo + (size_t)ja * bstride;
     for (int it = tid; it < p.Npad * 8; it += CV_THREADS) {
       const int n = it >> 3, qq = it & 7;
       const int k = n / p.KBL, kb = n - k * p.KBL;
@@ -166,7 +169,7 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   fence_after_sync();
   const int warp_u = uniform_warp_index();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
-  const uint32_t idesc = make_idesc_tf32(128, p.Npad);
+  const uint32_t idesc = make_idesc_tf32(128, p.Npad), idesc2 = make_idesc_tf32(128, 2 * p.Npad);
   const uint32_t d_small = tmem_base + (uint32_t)(p.nmain * p.Npad);
   // operand descriptors are launch constants: only the 16-byte-granular address field moves (K-step: +32 B, atom: +atomB)
   const uint64_t dA_hi = make_smem_desc_sw128(smem_u32(A_hi)), dA_lo = make_smem_desc_sw128(smem_u32(A_lo));
@@ -312,11 +315,10 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
         uint32_t acc = 0u;
         const int nks = p.Kdd >> 3;
         for (int ks = 0; ks < nks; ++ks) {
-          const uint64_t bo = (uint64_t)((((uint32_t)(ks >> 2)) * atomB) >> 4) + (uint64_t)((ks & 3) * 2);
+          const uint64_t bo = (uint64_t)((((uint32_t)(ks >> 2)) * 2u * atomB) >> 4) + (uint64_t)((ks & 3) * 2);
           const uint32_t ah = a0 + (uint32_t)(ks * 8), al = ah + 64u;
-          mma_tf32_atmem(d_small, al, dB_hi + bo, idesc, acc);
-          mma_tf32_atmem(d_small, ah, dB_lo + bo, idesc, 1u);
-          mma_tf32_atmem(tmem_base, ah, dB_hi + bo, idesc, acc);
+          mma_tf32_atmem(tmem_base, ah, dB_hi + bo, idesc2, acc);   // [main | cross] (+)= A_hi x [W_hi ; W_lo]
+          mma_tf32_atmem(d_small, al, dB_hi + bo, idesc, 1u);       // cross += A_lo x W_hi
           acc = 1u;
         }
         STC_TRACE(8);

@@ -50,6 +50,20 @@ def parse():
     return p.parse_args()
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/profile_summary.py traffic); None when that kernel was not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        d = json.load(f)
+    e = d.get("kernels", {}).get(kernel)
+    if not e:
+        return None, None
+    return e["dram_bytes_per_launch"], f"{d.get('source', 'profiles/traffic.json')}: mean of {e['launches']} captured launches at batch {d.get('batch')}"
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -323,13 +337,14 @@ def run_b200(args):
         top = max(kinds.items(), key=lambda kv: kv[1][0])
         name, (kms, kn, kbytes) = top
         achieved = kbytes / (kms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(name)
         roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "avg_launch_us": 1e3 * kms / kn, "alg_bytes_per_launch": kbytes / kn,
                     "share_of_kernel_time": kms / tot_ms,
                     "note": "achieved = this kernel's own compulsory bytes (inputs it must read + outputs it must write, "
-                            "formula beside its launcher) / its mean launch time; 3xTF32 tcgen05 kernel, latency- and "
-                            "issue-bound rather than HBM-bound at this size (see DESIGN.md section 4)"}
+                            "formula beside its launcher) / its mean launch time over every launch of the step (both "
+                            "convolutions, Din = 1 and Din = 16 cells); 3xTF32 tcgen05 kernel (see DESIGN.md section 4)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -147,8 +147,7 @@ struct ConvArgs {
   int trace_tiles;
 };
 enum { OPT_L2_PREFETCH = 1, OPT_GENERIC_EPILOGUE = 4 /* diagnostic: force the general epilogues */,
-       OPT_SMEM_A = 8 /* diagnostic: convolutions with the A operand staged in shared memory */,
-       OPT_NO_ROW_PREFETCH = 16 /* diagnostic: A-in-TMEM forward without the cp.async row prefetch */ };
+       OPT_SMEM_A = 8 /* diagnostic: convolutions with the A operand staged in shared memory */ };
 constexpr int TRACE_SLOTS = 16;
 int conv_opt_flags();                                  // cached STC_OPT (default: OPT_L2_PREFETCH)
 void conv_trace_target(long long** buf, int* tiles);   // what stc_debug_trace_set registered (null when off)

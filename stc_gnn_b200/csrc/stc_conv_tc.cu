@@ -688,8 +688,6 @@ tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
   float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
-  float4* pf = reinterpret_cast<float4*>(smem + p.off_sh);       // [8][CV_THREADS] row prefetch slots (own slots only)
-  const bool use_pf = (a.opt & OPT_NO_ROW_PREFETCH) == 0;
 
   if (tid == 0) {
     mbar_init(mma_bar, 1);
@@ -698,8 +696,6 @@ tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   for (int i = tid; i < C * C; i += CV_THREADS) Qs[i] = a.Q[C * C + i];
   for (int i = tid; i < Hout; i += CV_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
-  if (use_pf)
-    for (int i = 0; i < 8; ++i) pf[i * CV_THREADS + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < 2; ++k) {   // Bt[(c,o)][kb] = W[((k*Kc + c)*L + l(kb))*Hout + o], K order [h-part | x-part | zero pad]
     uint8_t* bh = B_hi + (size_t)k * 2 * atomB;
     uint8_t* bl = B_lo + (size_t)k * 2 * atomB;
@@ -739,40 +735,8 @@ tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
   uint32_t mma_phase = 0;
   const bool tracing = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
   int trace_it = 0;
-  // the 32 K-values of (row erow, spatial term half) of tile t, as per-thread asynchronous copies into the thread's own
-  // slots: issued one tile ahead (right after the MMAs of the current tile are issued), they cost no registers
-  auto prefetch_row = [&](int t) {
-    const long long g0 = (long long)t * p.npt;
-    const int nv = (int)min((long long)p.npt, total_nodes - g0);
-    const long long gr = g0 * C + erow;
-    if (erow < nv * C) {
-      const float* hs = (half == 0 ? a.h0 : a.yh) + gr * h;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cp_async16(&pf[i * CV_THREADS + tid], hs + 4 * i);
-      const float* xs;
-      if (half == 0) {
-        const long long g = g0 + enode;
-        const long long b = g / a.N;
-        xs = a.x0 + b * a.x0_bs + ((g - b * a.N) * C + ecat) * Din;
-      } else {
-        xs = a.yx + gr * Din;
-      }
-      if (xvec) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (4 * i < Din) cp_async16(&pf[(4 + i) * CV_THREADS + tid], xs + 4 * i);
-      } else {
-        for (int i = 0; i < Din; ++i)   // unaligned x-part (e.g. Din = 1): 4-byte copies; the rest of the slots stays zero
-          cp_async4(reinterpret_cast<float*>(&pf[(4 + (i >> 2)) * CV_THREADS + tid]) + (i & 3), xs + i);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pf[i * CV_THREADS + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    cp_async_commit();
-  };
-  if (use_pf && (int)blockIdx.x < p.ntiles) prefetch_row(blockIdx.x);
-
+  // (a cp.async prefetch of the rows one tile ahead was measured: the load phase shrinks but the tile time does not --
+  //  the two resident CTAs already cover each other's load latency)
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long g0 = (long long)tile * p.npt;
     const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
@@ -786,11 +750,7 @@ tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
     float4 xv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (use_pf) {
-      cp_async_wait_all();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = pf[i * CV_THREADS + tid];
-    } else if (valid) {
+    if (valid) {
       const float* hs = (half == 0 ? a.h0 : a.yh) + gr * h;
 #pragma unroll
       for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(hs + 4 * i);
@@ -852,7 +812,6 @@ tc_conv_fwd_at_kernel(const ConvArgs a, const TcFwdPlan p) {
       STC_TRACE(9);
       STC_TRACE(11);
     }
-    if (use_pf && tile + (int)gridDim.x < p.ntiles) prefetch_row(tile + gridDim.x);   // my slots were read above
     // ---- the epilogue's own operands travel under the MMAs: H (and u for the candidate), 8 channels of my row ----
     float4 hp[2], uu[2];
     hp[0] = hp[1] = uu[0] = uu[1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -971,7 +930,6 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
     p.off_q = (uint32_t)q; q += round_up((size_t)a.C * a.C * sizeof(float), 16);
     p.off_bias = (uint32_t)q; q += round_up((size_t)a.Hout * sizeof(float), 16);
     p.off_bar = (uint32_t)q; q += 32;
-    p.off_sh = (uint32_t)q; q += (size_t)8 * CV_THREADS * sizeof(float4);             // row prefetch slots
     p.smem_bytes = (uint32_t)q;
     p.tmem_cols = 256;   // 2 Npad accumulator columns + 128 A columns
   }

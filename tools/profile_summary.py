@@ -63,5 +63,34 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst, batch="4096"):
+    """profiles/traffic.json: mean dram bytes (read + write) per launch of each captured kernel kind."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    kinds = {"tc_conv_bwd_dx_kernel": "tc_conv_bwd_dx", "tc_conv_fwd": "tc_conv_fwd", "tc_conv_bwd_dw": "tc_conv_bwd_dw",
+             "tc_support_kernel": "tc_support", "tc_outer_kernel": "tc_outer"}
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for r in data:
+        name = r[idx["Kernel Name"]]
+        kind = next((v for k, v in kinds.items() if k in name), None)
+        if kind is None:
+            continue
+        b = sum(float(r[idx[m]].replace(",", "")) * scale[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        t = float(r[idx["gpu__time_duration.sum"]].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}[units[idx["gpu__time_duration.sum"]]]
+        agg[kind][0] += 1
+        agg[kind][1] += b
+        agg[kind][2] += t
+    d = {"source": "ncu --set full --clock-control none capture " + src.split("/")[-1], "batch": int(batch),
+         "kernels": {k: {"launches": v[0], "dram_bytes_per_launch": v[1] / v[0], "mean_us_under_ncu": v[2] / v[0]}
+                     for k, v in agg.items()}}
+    with open(dst, "w") as f:
+        json.dump(d, f, indent=1)
+    print(json.dumps(d, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -16,11 +16,15 @@ import stc_gnn_b200 as S  # noqa: E402
 from stc_gnn_b200 import _lib  # noqa: E402
 from stc_gnn_b200.synth import sf_supports  # noqa: E402
 
-FWD = ["tile start -> stage landed", "-> first atom built", "-> MMA of first atom done (single A buffer)",
-       "-> last atom built + MMAs issued", "-> last MMA done", "-> epilogue operands landed", "-> epilogue done",
-       "-> tile sync (next tile start)"]
-DX = ["tile start -> elementwise adjoint done", "-> first atom built", "-> last atom built + MMAs issued",
-      "-> dQ partial sums done", "-> last MMA done", "-> epilogue done", "-> tile sync", "-> next tile start"]
+# smem-A kernels (STC_OPT=9) stamp every phase; the A-in-TMEM kernels (default) have no second build / mid-tile wait,
+# so their stamps 2 -> 3 coincide
+FWD = ["tile start -> row loads issued (smem-A: stage landed)", "-> A operand written + barrier (smem-A: first atom built)",
+       "-> (smem-A only: MMA of first atom done, single A buffer)",
+       "-> MMAs issued, epilogue operands requested (smem-A: last atom built + MMAs issued)", "-> last MMA done",
+       "-> epilogue operands landed", "-> epilogue done", "-> tile sync (next tile start)"]
+DX = ["tile start -> elementwise adjoint done", "-> A operand [Ds | Dm] written + barrier (smem-A: first atom built)",
+      "-> MMAs issued (smem-A: last atom built + MMAs issued)", "-> dQ partial sums done", "-> last MMA done",
+      "-> epilogue done", "-> tile sync", "-> next tile start"]
 
 
 def report(name, buf, tiles, labels):
@@ -38,7 +42,7 @@ def report(name, buf, tiles, labels):
         print(f"   {d[:, i].mean().item():8.0f}  {labels[i]}")
     print(f"   {nxt.mean().item():8.0f}  {labels[7]}")
     if (t[:, 12:14] > 0).all():
-        print(f"   first atom (thread 0): values + stores {(t[:, 12] - t[:, 1]).mean().item():.0f}, proxy fence {(t[:, 13] - t[:, 12]).mean().item():.0f}, "
+        print(f"   A operand (thread 0): values + stores {(t[:, 12] - t[:, 1]).mean().item():.0f}, proxy fence {(t[:, 13] - t[:, 12]).mean().item():.0f}, "
               f"barrier {(t[:, 2] - t[:, 13]).mean().item():.0f}")
     if (t[:, 8:12] > 0).all():
         print(f"   MMA issue (thread 0): first atom {(t[:, 8] - t[:, 2]).mean().item():.0f} cycles after its build barrier, "

@@ -184,6 +184,7 @@ __device__ __forceinline__ void tc_fwd_epilogue_fast(const ConvArgs& a, const Tc
   }
   {
     const float* pp = Pm + (enode * C) * p.PS + cb;
+#pragma unroll 5
     for (int cp = 0; cp < C; ++cp) {
       const float w = Qs[cp * C + ecat];
 #pragma unroll
@@ -608,6 +609,7 @@ __device__ __forceinline__ void tc_fwd_epilogue_regs(const ConvArgs& a, const Tc
   }
   {
     const float* pp = Pm + (enode * C) * p.PS + cb;
+#pragma unroll 5
     for (int cp = 0; cp < C; ++cp) {
       const float w = Qs[cp * C + ecat];
 #pragma unroll

@@ -267,38 +267,53 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       const int enode = erow / C, ecat = erow - enode * C;
       const float* qrow = Qs + ecat * C;               // Dm_1[(node,c')][o] = sum_d Q_1[c'][d] Ds[(node,d)][o]
       const uint32_t tA = tl + (uint32_t)(2 * p.Npad);
+      // both 8-column parts of a 16-column share (gates) advance through the category loop together: twice the
+      // independent FMA chains and loads in flight per thread
+      const bool two = cw == 16;
+      float dm[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dm[i] = 0.f;
+      {
+        const float* sp = Dsm + (enode * C) * DP + cbase;
+#pragma unroll 5
+        for (int d = 0; d < C; ++d) {
+          const float w = qrow[d];
+          const float4 x0 = *reinterpret_cast<const float4*>(sp + d * DP);
+          const float4 x1 = *reinterpret_cast<const float4*>(sp + d * DP + 4);
+          dm[0] = fmaf(w, x0.x, dm[0]); dm[1] = fmaf(w, x0.y, dm[1]); dm[2] = fmaf(w, x0.z, dm[2]); dm[3] = fmaf(w, x0.w, dm[3]);
+          dm[4] = fmaf(w, x1.x, dm[4]); dm[5] = fmaf(w, x1.y, dm[5]); dm[6] = fmaf(w, x1.z, dm[6]); dm[7] = fmaf(w, x1.w, dm[7]);
+          if (two) {
+            const float4 x2 = *reinterpret_cast<const float4*>(sp + d * DP + 8);
+            const float4 x3 = *reinterpret_cast<const float4*>(sp + d * DP + 12);
+            dm[8] = fmaf(w, x2.x, dm[8]); dm[9] = fmaf(w, x2.y, dm[9]); dm[10] = fmaf(w, x2.z, dm[10]); dm[11] = fmaf(w, x2.w, dm[11]);
+            dm[12] = fmaf(w, x3.x, dm[12]); dm[13] = fmaf(w, x3.y, dm[13]); dm[14] = fmaf(w, x3.z, dm[14]); dm[15] = fmaf(w, x3.w, dm[15]);
+          }
+        }
+      }
+      if (erow < rows_valid) {   // the dW kernel contracts Y_k^T with [Ds | Dm_1] straight from HBM
+        float* dp = a.dpre + (row0 + erow) * p.Kdd + Hout + cbase;
+        *reinterpret_cast<float4*>(dp) = make_float4(dm[0], dm[1], dm[2], dm[3]);
+        *reinterpret_cast<float4*>(dp + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
+        if (two) {
+          *reinterpret_cast<float4*>(dp + 8) = make_float4(dm[8], dm[9], dm[10], dm[11]);
+          *reinterpret_cast<float4*>(dp + 12) = make_float4(dm[12], dm[13], dm[14], dm[15]);
+        }
+      }
 #pragma unroll
       for (int part = 0; part < 2; ++part) {           // 8 columns at a time (cw == 8: one part)
         if (part * 8 < cw) {
           const int col = cbase + part * 8;
-          float ds[8], dm[8];
+          float hi[8], lo[8];
           {
             const float4 x0 = *reinterpret_cast<const float4*>(Dsm + erow * DP + col);
             const float4 x1 = *reinterpret_cast<const float4*>(Dsm + erow * DP + col + 4);
-            ds[0] = x0.x; ds[1] = x0.y; ds[2] = x0.z; ds[3] = x0.w; ds[4] = x1.x; ds[5] = x1.y; ds[6] = x1.z; ds[7] = x1.w;
+            split_tf32(x0.x, hi[0], lo[0]); split_tf32(x0.y, hi[1], lo[1]); split_tf32(x0.z, hi[2], lo[2]); split_tf32(x0.w, hi[3], lo[3]);
+            split_tf32(x1.x, hi[4], lo[4]); split_tf32(x1.y, hi[5], lo[5]); split_tf32(x1.z, hi[6], lo[6]); split_tf32(x1.w, hi[7], lo[7]);
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dm[i] = 0.f;
-          const float* sp = Dsm + (enode * C) * DP + col;
-          for (int d = 0; d < C; ++d) {
-            const float w = qrow[d];
-            const float4 x0 = *reinterpret_cast<const float4*>(sp + d * DP);
-            const float4 x1 = *reinterpret_cast<const float4*>(sp + d * DP + 4);
-            dm[0] = fmaf(w, x0.x, dm[0]); dm[1] = fmaf(w, x0.y, dm[1]); dm[2] = fmaf(w, x0.z, dm[2]); dm[3] = fmaf(w, x0.w, dm[3]);
-            dm[4] = fmaf(w, x1.x, dm[4]); dm[5] = fmaf(w, x1.y, dm[5]); dm[6] = fmaf(w, x1.z, dm[6]); dm[7] = fmaf(w, x1.w, dm[7]);
-          }
-          if (erow < rows_valid) {   // the dW kernel contracts Y_k^T with [Ds | Dm_1] straight from HBM
-            float* dp = a.dpre + (row0 + erow) * p.Kdd + Hout + col;
-            *reinterpret_cast<float4*>(dp) = make_float4(dm[0], dm[1], dm[2], dm[3]);
-            *reinterpret_cast<float4*>(dp + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
-          }
-          float hi[8], lo[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) split_tf32(ds[i], hi[i], lo[i]);
           tmem_st8(tA + (uint32_t)col, hi);
           tmem_st8(tA + 64u + (uint32_t)col, lo);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split_tf32(dm[i], hi[i], lo[i]);
+          for (int i = 0; i < 8; ++i) split_tf32(dm[part * 8 + i], hi[i], lo[i]);
           tmem_st8(tA + (uint32_t)(Hout + col), hi);
           tmem_st8(tA + 64u + (uint32_t)(Hout + col), lo);
         }

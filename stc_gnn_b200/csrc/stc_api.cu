@@ -121,6 +121,17 @@ WsLayout make_layout(const StcDims& d) {
   const size_t kcm1 = d.Kc > 1 ? (size_t)(d.Kc - 1) : 0;
   w.Pg = take(w.R * kcm1 * 2 * d.h);
   w.Pc = take(w.R * kcm1 * d.h);
+  {  // weight images of the wide-hidden-state forward: only for shapes the SF-class tensor-core kernels do not take
+    ConvArgs t;
+    memset(&t, 0, sizeof(t));
+    t.B = d.B; t.N = d.N; t.C = d.C; t.Din = d.Din; t.h = d.h; t.Ks = d.Ks; t.Kc = d.Kc;
+    t.Hout = 2 * d.h;
+    const bool small_g = conv_tc_eligible(t);
+    t.Hout = d.h;
+    const bool small_c = conv_tc_eligible(t);
+    w.Wimg_g = take(small_g ? 0 : conv_big_img_floats(d.C, d.Din, d.h, d.Ks, d.Kc, 2 * d.h));
+    w.Wimg_c = take(small_c ? 0 : conv_big_img_floats(d.C, d.Din, d.h, d.Ks, d.Kc, d.h));
+  }
   w.saved_total = o;
   o = 0;
   w.dpre = take(w.R * 2 * d.h * d.Kc);   // tcgen05 path keeps the Kc unmixed copies side by side
@@ -305,6 +316,7 @@ static int fwd_gates(const FwdCtx& f, const float* Wg, const float* bg) {
   a.r = ws + w.r;
   a.rH = ws + w.Yr;
   a.Psave = ws + w.Pg;
+  a.Wimg = (w.Wimg_c > w.Wimg_g) ? ws + w.Wimg_g : nullptr;   // region is empty when the shape is not eligible
   return launch_conv_fwd(a, f.st);
 }
 
@@ -341,6 +353,7 @@ static int fwd_candi(const FwdCtx& f, const float* Wc, const float* bc, float* h
   a.c = ws + w.c;
   a.Hnew = h_out;
   a.Psave = ws + w.Pc;
+  a.Wimg = (w.saved_total > w.Wimg_c) ? ws + w.Wimg_c : nullptr;
   return launch_conv_fwd(a, f.st);
 }
 

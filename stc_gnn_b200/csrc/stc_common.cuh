@@ -83,7 +83,7 @@ int check_arch();        // STC_OK when the current device is compute capability
 struct WsLayout {
   size_t R;  // B*N*C rows
   // `saved` buffer (written by forward, read by backward)
-  size_t u, r, c, Yr, Yx, Yh, Q, Pg, Pc, saved_total;
+  size_t u, r, c, Yr, Yx, Yh, Q, Pg, Pc, Wimg_g, Wimg_c, saved_total;
   // backward `scratch` buffer
   size_t dpre, dYx0, dYx, dYh, dYr, dQ, scratch_total;
 };
@@ -127,6 +127,7 @@ struct ConvArgs {
   float* c;
   float* Hnew;
   float* Psave;        // [R][(Kc-1)*Hout]: pre-mix partial outputs P_c, c >= 1 (tcgen05 path, for dGc)
+  float* Wimg;         // wide-hidden-state forward (stc_conv_tc_big.cu): scratch for the split, pre-swizzled weights
   // backward inputs / outputs
   const float* dHn;
   const float* drH;    // gates phase: adjoint of r*H
@@ -158,6 +159,10 @@ int launch_cell_fwd_fused(const StcDims& d, const StcSupport& gs, const float* Q
                           float* h_out, float* ws, const WsLayout& w, cudaStream_t st);
 int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, cudaStream_t st);
 int launch_conv_fwd(const ConvArgs& a, cudaStream_t st);
+// wide hidden states (h >= 32, Kc = 2): streamed-weight tcgen05 forward (stc_conv_tc_big.cu)
+bool conv_big_shape_ok(int C, int Din, int h, int Ks, int Kc, int Hout);
+size_t conv_big_img_floats(int C, int Din, int h, int Ks, int Kc, int Hout);   // 0 when the shape is not eligible
+int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled);
 bool conv_tc_eligible(const ConvArgs& a);  // shape-only test shared by forward and backward
 bool conv_tc_dw_shape_ok(const ConvArgs& a);  // additionally: the tensor-core dW kernel tiles this shape
 int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st);

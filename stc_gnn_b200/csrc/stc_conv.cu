@@ -164,6 +164,8 @@ int launch_conv_fwd(const ConvArgs& a, cudaStream_t st) {
   bool handled = false;
   STC_TRY(try_launch_conv_fwd_tc(a, st, &handled));
   if (handled) return STC_OK;
+  STC_TRY(try_launch_conv_fwd_big(a, st, &handled));
+  if (handled) return STC_OK;
   ConvTile t; size_t smem; int ni;
   STC_TRY(pick_rows_fwd(a, &t, &smem, &ni));
   long long total_nodes = (long long)a.B * a.N;

@@ -1,0 +1,376 @@
+// tcgen05 / TMEM forward gate / candidate convolution for WIDE hidden states (h = 32 ... 128, e.g. F = 64 of the
+// synthetic grid and kNN configurations): the reference's 'bmdk,kh->bmdh' (/root/reference/framework/STC_GNN.py:42)
+// with K = Ks * (h + Din) up to 512 and N = Kc * Hout up to 256 -- the one shape where the contraction is a real GEMM.
+//
+// Differences from the SF-class kernels (stc_conv_tc.cu):
+//   * the split weights (hi | lo) do not fit in shared memory (512 KB at F = 64): a preparation kernel writes them
+//     once per launch as ready-to-use K-major SW128 atoms into a scratch image, and the main kernel streams one
+//     32-wide K chunk at a time through a 3-stage TMA (1-D bulk copy) ring;
+//   * the data rows are the TMEM A operand (tcgen05.st), double-buffered per K chunk;
+//   * N is processed per categorical block (c = 1 first, then c = 0): accumulators main0 | main1 | cross terms
+//     = 3 Hout <= 384 TMEM columns, A buffers in columns [384, 512); chunks alternate between the two main
+//     accumulators so that no chain exceeds K/2 (accumulate-truncation, profiles/r1_tc_precision.txt);
+//   * the categorical mix is applied to the GEMM output as in the SF kernels: P_1 goes to shared memory, the c = 0
+//     epilogue adds T_1(Gc)^T-mix(P_1), bias, activation, sigmoid / tanh and the GRU blend (STC_GNN.py:44-46, 71-78).
+// Forward only: backward for these shapes runs on the general path (stc_conv.cu), which saves nothing extra.
+#include "stc_conv_common.cuh"
+#include "stc_tc.cuh"
+
+#include <stdlib.h>
+
+namespace stc {
+
+using namespace tc;
+
+constexpr int BG_STAGES = 3;
+constexpr int BG_ACOL = 384;   // first TMEM column of the A buffers: buffer b = [hi 32 | lo 32] at BG_ACOL + 64 b
+
+struct BigPlan {
+  int npt, Dp, KBL;
+  int nchk;       // 32-wide K chunks per spatial term
+  int nch;        // chunks per categorical block = Ks * nchk
+  int ntiles;
+  int PS;         // row stride (floats) of the P_1 exchange tile
+  int x_vec;
+  uint32_t stage_bytes;   // one weight chunk: [hi: Hout rows x 128 B | lo: Hout rows x 128 B]
+  uint32_t off_b, off_pm, off_q, off_bias, off_bar, smem_bytes;
+};
+
+// img[(cb, ch)][hi | lo][o][kb]  <-  W[((k*Kc + cb)*L + l(kb))*Hout + o],  k = ch / nchk, kb = 32 (ch % nchk) + ...
+__global__ void tc_big_prep_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int Din, int h, int Ks, int Kc,
+                                   int Hout, int KBL, int nchk) {
+  const int L = Din + h, nch = Ks * nchk;
+  const long long total = (long long)Kc * nch * Hout * 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx & 7);
+    long long r = idx >> 3;
+    const int o = (int)(r % Hout);
+    r /= Hout;
+    const int ch = (int)(r % nch), cb = (int)(r / nch);
+    const int k = ch / nchk, j = ch - k * nchk;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kb = 32 * j + 4 * q + i;
+      const int l = kb >= KBL ? -1 : (kb < h ? Din + kb : (kb - h < Din ? kb - h : -1));
+      v[i] = l >= 0 ? W[((size_t)(k * Kc + cb) * L + l) * Hout + o] : 0.f;
+    }
+    uint8_t* base = img + (size_t)(cb * nch + ch) * 2 * Hout * ATOM_ROW_BYTES;
+    store_split4(base, base + (size_t)Hout * ATOM_ROW_BYTES, atom_chunk_offset(o, q), make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restrict__ img) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, h = a.h, Din = a.Din, Hout = a.Hout;
+  uint8_t* Bring = smem + p.off_b;
+  float* Pm = reinterpret_cast<float*>(smem + p.off_pm);        // [128 + C][PS]  P_1 tile (rows past 128 stay zero)
+  float* Qs = reinterpret_cast<float*>(smem + p.off_q);         // [C][C] = T_1(Gc)
+  float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* b_free = b_full + BG_STAGES;
+  uint64_t* a_free = b_free + BG_STAGES;
+  uint64_t* acc_full = a_free + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  if (tid == 0) {
+    for (int i = 0; i < BG_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_free[i], 1);
+    }
+    mbar_init(&a_free[0], 1);
+    mbar_init(&a_free[1], 1);
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512u);
+  for (int i = tid; i < C * C; i += CV_THREADS) Qs[i] = a.Q[C * C + i];
+  for (int i = tid; i < Hout; i += CV_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
+  for (int i = tid; i < (128 + C) * p.PS; i += CV_THREADS) Pm[i] = 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const int warp_u = uniform_warp_index();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  const uint32_t idesc = make_idesc_tf32(128, Hout);
+  const uint32_t d_small = tmem_base + (uint32_t)(2 * Hout);
+  const long long total_nodes = (long long)a.B * a.N;
+  const long long R = total_nodes * C;
+
+  const int sp = warp & 3, half = warp >> 2;
+  const int erow = sp * 32 + lane;                     // accumulator lane = tile row
+  const int enode = erow / C, ecat = erow - enode * C;
+  const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
+  const int hcols = Hout >> 1;                         // epilogue: this thread's columns [half*hcols, +hcols)
+  const bool xvec = p.x_vec != 0;
+
+  const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t total_chunks = (uint32_t)my_tiles * 2u * (uint32_t)p.nch;
+  auto img_of = [&](uint32_t g) {                      // chunk g of this CTA -> its weight image (periodic in the tile)
+    const uint32_t w = g % (2u * (uint32_t)p.nch);
+    const uint32_t cbi = w / (uint32_t)p.nch, ch = w - cbi * (uint32_t)p.nch;
+    return img + (size_t)((1u - cbi) * (uint32_t)p.nch + ch) * p.stage_bytes;   // c = 1 first, then c = 0
+  };
+  if (warp_u == 1 && elect_one_sync()) {               // ring prologue: the first BG_STAGES - 1 chunks
+    for (uint32_t g = 0; g < (uint32_t)(BG_STAGES - 1) && g < total_chunks; ++g) {
+      mbar_arrive_expect_tx(&b_full[g], p.stage_bytes);
+      bulk_g2s(Bring + (size_t)g * p.stage_bytes, img_of(g), p.stage_bytes, &b_full[g]);
+    }
+  }
+
+  uint32_t g = 0;                                      // running chunk counter of this CTA
+  uint32_t acc_phase = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long g0 = (long long)tile * p.npt;
+    const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
+    const int rows_valid = nodes_valid * C;
+    const bool valid = erow < rows_valid;
+    const long long gr = g0 * C + erow;
+    // x-part source of my row for spatial term 0 (Xt carries a batch stride)
+    const float* xs0 = a.x0;
+    if (valid) {
+      const long long gn = g0 + enode;
+      const long long b = gn / a.N;
+      xs0 = a.x0 + b * a.x0_bs + ((gn - b * a.N) * C + ecat) * Din;
+    }
+    // my 16 K-values of chunk ch: K range [32 j + 16 half, +16) of spatial term k
+    auto load_chunk = [&](int ch, float4 (&v)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!valid) return;
+      const int k = ch / p.nchk, j = ch - k * p.nchk;
+      const int kb0 = 32 * j + 16 * half;
+      if (kb0 < h) {        // h % 16 == 0: the run lies entirely in the h-part
+        const float* hs = (k == 0 ? a.h0 : a.yh + (size_t)(k - 1) * R * h) + gr * h + kb0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(hs + 4 * i);
+      } else {
+        const int xi = kb0 - h;
+        const float* xs = (k == 0 ? xs0 : a.yx + (size_t)(k - 1) * R * Din + gr * Din);
+        if (xvec) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (xi + 4 * i < Din) v[i] = *reinterpret_cast<const float4*>(xs + xi + 4 * i);
+        } else {
+          float e[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) e[i] = (xi + i < Din) ? xs[xi + i] : 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = make_float4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
+        }
+      }
+    };
+
+    for (int cbi = 0; cbi < 2; ++cbi) {                // categorical block c = 1, then c = 0
+      const int cb = 1 - cbi;
+      float4 cur[4], nxt[4];
+      load_chunk(0, cur);
+      for (int ch = 0; ch < p.nch; ++ch, ++g) {
+        if (ch + 1 < p.nch) load_chunk(ch + 1, nxt);   // next chunk's loads travel under this chunk's work
+        const int buf = (int)(g & 1u);
+        const uint32_t ua = g >> 1;
+        if (ua >= 1u) {                                // the MMAs that read this A buffer two chunks ago are done
+          mbar_wait(&a_free[buf], (ua - 1u) & 1u);
+          fence_after_sync();
+        }
+        const uint32_t tA = tl + (uint32_t)(BG_ACOL + 64 * buf + 16 * half);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                  // 8 columns at a time: hi, then lo 32 columns further
+          float hi[8], lo[8];
+          split_tf32(cur[2 * i].x, hi[0], lo[0]); split_tf32(cur[2 * i].y, hi[1], lo[1]);
+          split_tf32(cur[2 * i].z, hi[2], lo[2]); split_tf32(cur[2 * i].w, hi[3], lo[3]);
+          split_tf32(cur[2 * i + 1].x, hi[4], lo[4]); split_tf32(cur[2 * i + 1].y, hi[5], lo[5]);
+          split_tf32(cur[2 * i + 1].z, hi[6], lo[6]); split_tf32(cur[2 * i + 1].w, hi[7], lo[7]);
+          tmem_st8(tA + (uint32_t)(8 * i), hi);
+          tmem_st8(tA + 32u + (uint32_t)(8 * i), lo);
+        }
+        tmem_st_wait();
+        fence_before_sync();
+        __syncthreads();
+        const int st = (int)(g % (uint32_t)BG_STAGES);
+        if (warp_u == 0 && elect_one_sync()) {
+          mbar_wait(&b_full[st], (g / (uint32_t)BG_STAGES) & 1u);
+          fence_after_sync();
+          const int j = ch % p.nchk;
+          const int kleft = p.KBL - 32 * j;
+          const int ksteps = kleft >= 32 ? 4 : (kleft + 7) / 8;
+          const uint32_t d_main = tmem_base + (uint32_t)((ch & 1) * Hout);
+          const uint32_t a_hi0 = tmem_base + (uint32_t)(BG_ACOL + 64 * buf);
+          const uint64_t dBh = make_smem_desc_sw128(smem_u32(Bring + (size_t)st * p.stage_bytes));
+          const uint64_t dBl = dBh + (uint64_t)(((uint32_t)Hout * ATOM_ROW_BYTES) >> 4);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ko = (uint64_t)(ks * 2);
+            const uint32_t ah = a_hi0 + (uint32_t)(ks * 8), al = ah + 32u;
+            mma_tf32_atmem(d_small, al, dBh + ko, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+            mma_tf32_atmem(d_small, ah, dBl + ko, idesc, 1u);
+            mma_tf32_atmem(d_main, ah, dBh + ko, idesc, (ch >= 2 || ks > 0) ? 1u : 0u);
+          }
+          mma_commit(&a_free[buf]);                     // A buffer and weight stage are free once these MMAs have read them
+          mma_commit(&b_free[st]);
+          if (ch == p.nch - 1) mma_commit(acc_full);    // ... and the block's accumulators are complete
+        }
+        if (warp_u == 1 && elect_one_sync()) {          // refill the ring BG_STAGES - 1 chunks ahead
+          const uint32_t t = g + (uint32_t)(BG_STAGES - 1);
+          if (t < total_chunks) {
+            const uint32_t ts = t % (uint32_t)BG_STAGES, tu = t / (uint32_t)BG_STAGES;
+            if (tu >= 1u) mbar_wait(&b_free[ts], (tu - 1u) & 1u);
+            mbar_arrive_expect_tx(&b_full[ts], p.stage_bytes);
+            bulk_g2s(Bring + (size_t)ts * p.stage_bytes, img_of(t), p.stage_bytes, &b_full[ts]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+      }
+      // ---- epilogue of this categorical block ----
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1u;
+      fence_after_sync();
+      for (int c0 = half * hcols; c0 < (half + 1) * hcols; c0 += 8) {
+        float v[8];
+        {
+          uint32_t t0[8], t1[8], t2[8];
+          tmem_ld8_async(tl + (uint32_t)(2 * Hout + c0), t2);
+          tmem_ld8_async(tl + (uint32_t)c0, t0);
+          tmem_ld8_async(tl + (uint32_t)(Hout + c0), t1);
+          tmem_ld_wait();
+          tmem_ld_pin8(t0); tmem_ld_pin8(t1); tmem_ld_pin8(t2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = (__uint_as_float(t2[i]) + __uint_as_float(t0[i])) + __uint_as_float(t1[i]);
+        }
+        if (cb == 1) {                                   // P_1: parked in shared memory for the mix
+          *reinterpret_cast<float4*>(Pm + erow * p.PS + c0) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(Pm + erow * p.PS + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          continue;
+        }
+        {                                                // P_0 + T_1(Gc)^T-mix of P_1 over the node's categories
+          const float* pp = Pm + (enode * C) * p.PS + c0;
+          for (int cp = 0; cp < C; ++cp) {
+            const float w = Qs[cp * C + ecat];
+            const float4 x0 = *reinterpret_cast<const float4*>(pp + cp * p.PS);
+            const float4 x1 = *reinterpret_cast<const float4*>(pp + cp * p.PS + 4);
+            v[0] = fmaf(w, x0.x, v[0]); v[1] = fmaf(w, x0.y, v[1]); v[2] = fmaf(w, x0.z, v[2]); v[3] = fmaf(w, x0.w, v[3]);
+            v[4] = fmaf(w, x1.x, v[4]); v[5] = fmaf(w, x1.y, v[5]); v[6] = fmaf(w, x1.z, v[6]); v[7] = fmaf(w, x1.w, v[7]);
+          }
+        }
+        if (!valid) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float pre = v[i] + bias_s[c0 + i];
+          if (a.act == STC_ACT_RELU) pre = fmaxf(pre, 0.f);
+          v[i] = pre;
+        }
+        if (a.phase == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = sigmoidf_fast(v[i]);
+          if (c0 < h) {
+            float4* dst = reinterpret_cast<float4*>(a.u + gr * h + c0);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            const long long o = gr * h + (c0 - h);
+            const float4 h0 = *reinterpret_cast<const float4*>(a.Hprev + o);
+            const float4 h1 = *reinterpret_cast<const float4*>(a.Hprev + o + 4);
+            float4* dr = reinterpret_cast<float4*>(a.r + o);
+            dr[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dr[1] = make_float4(v[4], v[5], v[6], v[7]);
+            float4* drh = reinterpret_cast<float4*>(a.rH + o);
+            drh[0] = make_float4(v[0] * h0.x, v[1] * h0.y, v[2] * h0.z, v[3] * h0.w);
+            drh[1] = make_float4(v[4] * h1.x, v[5] * h1.y, v[6] * h1.z, v[7] * h1.w);
+          }
+        } else {
+          const long long o = gr * h + c0;
+          const float4 u0 = *reinterpret_cast<const float4*>(a.u + o), u1 = *reinterpret_cast<const float4*>(a.u + o + 4);
+          const float4 p0 = *reinterpret_cast<const float4*>(a.Hprev + o), p1 = *reinterpret_cast<const float4*>(a.Hprev + o + 4);
+          const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+          const float hp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          float cc[8], hn[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            cc[i] = tanhf_fast(v[i]);
+            hn[i] = fmaf(uu[i], cc[i] - hp[i], hp[i]);
+          }
+          float4* dc = reinterpret_cast<float4*>(a.c + o);
+          dc[0] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+          dc[1] = make_float4(cc[4], cc[5], cc[6], cc[7]);
+          float4* dh = reinterpret_cast<float4*>(a.Hnew + o);
+          dh[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          dh[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        }
+      }
+      fence_before_sync();   // accumulator reads precede the next block's overwriting MMAs; P_1 is complete / consumed
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512u);
+}
+
+static bool aligned16g(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// shape-only test (also sizes the weight image inside the `saved` buffer, so it must not depend on pointers)
+bool conv_big_shape_ok(int C, int Din, int h, int Ks, int Kc, int Hout) {
+  const char* e = getenv("STC_DISABLE_TC");
+  if (e && e[0] && e[0] != '0') return false;
+  if (Kc != 2 || h % 16 != 0 || h < 32 || Hout % 16 != 0 || Hout > 128 || C > 128 || Ks < 1) return false;
+  const int Dp = (Din + 7) & ~7, KBL = h + Dp, nchk = (KBL + 31) / 32;
+  if (Ks * nchk < 2) return false;
+  const size_t smem = (size_t)BG_STAGES * 2 * Hout * ATOM_ROW_BYTES + (size_t)(128 + C) * (Hout + 4) * sizeof(float) +
+                      (size_t)C * C * sizeof(float) + (size_t)Hout * sizeof(float) + 2048;
+  return smem <= 220 * 1024;
+}
+
+size_t conv_big_img_floats(int C, int Din, int h, int Ks, int Kc, int Hout) {
+  if (!conv_big_shape_ok(C, Din, h, Ks, Kc, Hout)) return 0;
+  const int Dp = (Din + 7) & ~7, KBL = h + Dp, nchk = (KBL + 31) / 32;
+  return (size_t)Kc * Ks * nchk * 2 * Hout * (ATOM_ROW_BYTES / sizeof(float));
+}
+
+int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (a.Wimg == nullptr || !conv_big_shape_ok(a.C, a.Din, a.h, a.Ks, a.Kc, a.Hout)) return STC_OK;
+  if (!aligned16g(a.u) || !aligned16g(a.Hprev) || !aligned16g(a.r) || !aligned16g(a.rH) || !aligned16g(a.c) ||
+      !aligned16g(a.Hnew) || !aligned16g(a.h0) || !aligned16g(a.yh) || ((reinterpret_cast<uintptr_t>(a.Wimg) & 127) != 0))
+    return STC_OK;   // the general path takes unaligned state tensors
+  BigPlan p;
+  p.npt = 128 / a.C;
+  p.Dp = (a.Din + 7) & ~7;
+  p.KBL = a.h + p.Dp;
+  p.nchk = (p.KBL + 31) / 32;
+  p.nch = a.Ks * p.nchk;
+  p.PS = a.Hout + 4;
+  p.x_vec = (a.Din % 4 == 0) && (a.x0_bs % 4 == 0) && aligned16g(a.x0) && aligned16g(a.yx);
+  const long long total_nodes = (long long)a.B * a.N;
+  p.ntiles = ceil_div(total_nodes, p.npt);
+  p.stage_bytes = (uint32_t)(2 * a.Hout * ATOM_ROW_BYTES);
+  size_t o = 0;
+  p.off_b = (uint32_t)o; o += (size_t)BG_STAGES * p.stage_bytes;
+  p.off_pm = (uint32_t)o; o += round_up((size_t)(128 + a.C) * p.PS * sizeof(float), 16);
+  p.off_q = (uint32_t)o; o += round_up((size_t)a.C * a.C * sizeof(float), 16);
+  p.off_bias = (uint32_t)o; o += round_up((size_t)a.Hout * sizeof(float), 16);
+  p.off_bar = (uint32_t)o; o += 8 * (2 * BG_STAGES + 3) + 16;
+  p.smem_bytes = (uint32_t)o;
+  if (p.smem_bytes > 226 * 1024) return STC_OK;
+  {
+    const long long items = (long long)a.Kc * p.nch * a.Hout * 8;
+    tc_big_prep_kernel<<<(int)min((items + 255) / 256, (long long)1024), 256, 0, st>>>(
+        a.W, reinterpret_cast<uint8_t*>(a.Wimg), a.Din, a.h, a.Ks, a.Kc, a.Hout, p.KBL, p.nchk);
+    STC_LAUNCH_OK("tc_big_prep_kernel");
+  }
+  STC_TRY(set_smem(tc_conv_fwd_big_kernel, p.smem_bytes));
+  int grid = device_sm_count();
+  if (grid > p.ntiles) grid = p.ntiles;
+  const int L = a.Din + a.h, P = a.Ks * a.Kc;
+  const double R = (double)total_nodes * a.C;
+  ScopedKernelTimer _t(KK_TC_CONV_FWD, st,
+                       4.0 * R * (a.Ks * L + (a.phase == 0 ? 3 * a.h : 4 * a.h)) + 4.0 * P * L * a.Hout);
+  tc_conv_fwd_big_kernel<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
+  STC_LAUNCH_OK("tc_conv_fwd_big_kernel");
+  *handled = true;
+  return STC_OK;
+}
+
+}  // namespace stc

@@ -66,6 +66,8 @@ SHAPES = [
     (1, 20, 64, 8, 16, 2, 2),     # wide category axis (LongC-like)
     (2, 24, 16, 64, 64, 2, 2),    # F = 64 (G4096-like feature widths)
     (5, 12, 8, 64, 64, 4, 2),     # Ks = 4 (kNN64K-like)
+    (3, 40, 8, 1, 32, 2, 2),      # wide-state forward kernel: Din = 1 (partial last K chunk), h = 32
+    (2, 21, 5, 20, 48, 3, 2),     # ... h = 48 (Hout 96 / 48), 3 spatial terms, ragged last tile
     (2, 9, 2, 3, 4, 1, 3),
     (4, 1, 1, 1, 1, 2, 2),        # degenerate sizes
 ]

@@ -23,6 +23,7 @@ namespace stc {
 using namespace tc;
 
 constexpr int BG_STAGES = 3;
+constexpr int BG_THREADS = 512;   // 16 warps: four threads per tile row (one per 8 K-values of a chunk / per quarter of the output columns)
 constexpr int BG_ACOL = 384;   // first TMEM column of the A buffers: buffer b = [hi 32 | lo 32] at BG_ACOL + 64 b
 
 struct BigPlan {
@@ -61,7 +62,7 @@ __global__ void tc_big_prep_kernel(const float* __restrict__ W, uint8_t* __restr
   }
 }
 
-__global__ void __launch_bounds__(CV_THREADS, 1)
+__global__ void __launch_bounds__(BG_THREADS, 1)
 tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restrict__ img) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -88,9 +89,9 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512u);
-  for (int i = tid; i < C * C; i += CV_THREADS) Qs[i] = a.Q[C * C + i];
-  for (int i = tid; i < Hout; i += CV_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
-  for (int i = tid; i < (128 + C) * p.PS; i += CV_THREADS) Pm[i] = 0.f;
+  for (int i = tid; i < C * C; i += BG_THREADS) Qs[i] = a.Q[C * C + i];
+  for (int i = tid; i < Hout; i += BG_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
+  for (int i = tid; i < (128 + C) * p.PS; i += BG_THREADS) Pm[i] = 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -101,11 +102,10 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
   const long long total_nodes = (long long)a.B * a.N;
   const long long R = total_nodes * C;
 
-  const int sp = warp & 3, half = warp >> 2;
+  const int sp = warp & 3, qtr = warp >> 2;            // TMEM lane quarter / which of the row's four threads
   const int erow = sp * 32 + lane;                     // accumulator lane = tile row
   const int enode = erow / C, ecat = erow - enode * C;
   const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
-  const int hcols = Hout >> 1;                         // epilogue: this thread's columns [half*hcols, +hcols)
   const bool xvec = p.x_vec != 0;
 
   const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -137,37 +137,35 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
       const long long b = gn / a.N;
       xs0 = a.x0 + b * a.x0_bs + ((gn - b * a.N) * C + ecat) * Din;
     }
-    // my 16 K-values of chunk ch: K range [32 j + 16 half, +16) of spatial term k
-    auto load_chunk = [&](int ch, float4 (&v)[4]) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // my 8 K-values of chunk ch: K range [32 j + 8 qtr, +8) of spatial term k
+    auto load_chunk = [&](int ch, float4 (&v)[2]) {
+      v[0] = v[1] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (!valid) return;
       const int k = ch / p.nchk, j = ch - k * p.nchk;
-      const int kb0 = 32 * j + 16 * half;
+      const int kb0 = 32 * j + 8 * qtr;
       if (kb0 < h) {        // h % 16 == 0: the run lies entirely in the h-part
         const float* hs = (k == 0 ? a.h0 : a.yh + (size_t)(k - 1) * R * h) + gr * h + kb0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(hs + 4 * i);
+        v[0] = *reinterpret_cast<const float4*>(hs);
+        v[1] = *reinterpret_cast<const float4*>(hs + 4);
       } else {
         const int xi = kb0 - h;
         const float* xs = (k == 0 ? xs0 : a.yx + (size_t)(k - 1) * R * Din + gr * Din);
         if (xvec) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (xi + 4 * i < Din) v[i] = *reinterpret_cast<const float4*>(xs + xi + 4 * i);
+          if (xi < Din) v[0] = *reinterpret_cast<const float4*>(xs + xi);
+          if (xi + 4 < Din) v[1] = *reinterpret_cast<const float4*>(xs + xi + 4);
         } else {
-          float e[16];
+          float e[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) e[i] = (xi + i < Din) ? xs[xi + i] : 0.f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = make_float4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) e[i] = (xi + i < Din) ? xs[xi + i] : 0.f;
+          v[0] = make_float4(e[0], e[1], e[2], e[3]);
+          v[1] = make_float4(e[4], e[5], e[6], e[7]);
         }
       }
     };
 
     for (int cbi = 0; cbi < 2; ++cbi) {                // categorical block c = 1, then c = 0
       const int cb = 1 - cbi;
-      float4 cur[4], nxt[4];
+      float4 cur[2], nxt[2];
       load_chunk(0, cur);
       for (int ch = 0; ch < p.nch; ++ch, ++g) {
         if (ch + 1 < p.nch) load_chunk(ch + 1, nxt);   // next chunk's loads travel under this chunk's work
@@ -177,16 +175,15 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
           mbar_wait(&a_free[buf], (ua - 1u) & 1u);
           fence_after_sync();
         }
-        const uint32_t tA = tl + (uint32_t)(BG_ACOL + 64 * buf + 16 * half);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {                  // 8 columns at a time: hi, then lo 32 columns further
+        const uint32_t tA = tl + (uint32_t)(BG_ACOL + 64 * buf + 8 * qtr);
+        {                                              // my 8 columns: hi, and lo 32 columns further
           float hi[8], lo[8];
-          split_tf32(cur[2 * i].x, hi[0], lo[0]); split_tf32(cur[2 * i].y, hi[1], lo[1]);
-          split_tf32(cur[2 * i].z, hi[2], lo[2]); split_tf32(cur[2 * i].w, hi[3], lo[3]);
-          split_tf32(cur[2 * i + 1].x, hi[4], lo[4]); split_tf32(cur[2 * i + 1].y, hi[5], lo[5]);
-          split_tf32(cur[2 * i + 1].z, hi[6], lo[6]); split_tf32(cur[2 * i + 1].w, hi[7], lo[7]);
-          tmem_st8(tA + (uint32_t)(8 * i), hi);
-          tmem_st8(tA + 32u + (uint32_t)(8 * i), lo);
+          split_tf32(cur[0].x, hi[0], lo[0]); split_tf32(cur[0].y, hi[1], lo[1]);
+          split_tf32(cur[0].z, hi[2], lo[2]); split_tf32(cur[0].w, hi[3], lo[3]);
+          split_tf32(cur[1].x, hi[4], lo[4]); split_tf32(cur[1].y, hi[5], lo[5]);
+          split_tf32(cur[1].z, hi[6], lo[6]); split_tf32(cur[1].w, hi[7], lo[7]);
+          tmem_st8(tA, hi);
+          tmem_st8(tA + 32u, lo);
         }
         tmem_st_wait();
         fence_before_sync();
@@ -222,14 +219,14 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
             bulk_g2s(Bring + (size_t)ts * p.stage_bytes, img_of(t), p.stage_bytes, &b_full[ts]);
           }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+        cur[0] = nxt[0];
+        cur[1] = nxt[1];
       }
       // ---- epilogue of this categorical block ----
       mbar_wait(acc_full, acc_phase);
       acc_phase ^= 1u;
       fence_after_sync();
-      for (int c0 = half * hcols; c0 < (half + 1) * hcols; c0 += 8) {
+      for (int c0 = 8 * qtr; c0 < Hout; c0 += 32) {   // this thread's 8-column groups: qtr, qtr + 4, ...
         float v[8];
         {
           uint32_t t0[8], t1[8], t2[8];
@@ -367,7 +364,7 @@ int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled) {
   const double R = (double)total_nodes * a.C;
   ScopedKernelTimer _t(KK_TC_CONV_FWD, st,
                        4.0 * R * (a.Ks * L + (a.phase == 0 ? 3 * a.h : 4 * a.h)) + 4.0 * P * L * a.Hout);
-  tc_conv_fwd_big_kernel<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
+  tc_conv_fwd_big_kernel<<<grid, BG_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
   STC_LAUNCH_OK("tc_conv_fwd_big_kernel");
   *handled = true;
   return STC_OK;

@@ -195,16 +195,18 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
           const int j = ch % p.nchk;
           const int kleft = p.KBL - 32 * j;
           const int ksteps = kleft >= 32 ? 4 : (kleft + 7) / 8;
-          const uint32_t d_main = tmem_base + (uint32_t)((ch & 1) * Hout);
           const uint32_t a_hi0 = tmem_base + (uint32_t)(BG_ACOL + 64 * buf);
           const uint64_t dBh = make_smem_desc_sw128(smem_u32(Bring + (size_t)st * p.stage_bytes));
           const uint64_t dBl = dBh + (uint64_t)(((uint32_t)Hout * ATOM_ROW_BYTES) >> 4);
+          // consecutive MMAs never touch the same accumulator twice in a row: the main product alternates between the
+          // two main accumulators per K-step and sits between the two cross-term products
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t ko = (uint64_t)(ks * 2);
             const uint32_t ah = a_hi0 + (uint32_t)(ks * 8), al = ah + 32u;
+            const uint32_t d_main = tmem_base + (uint32_t)((ks & 1) * Hout);
             mma_tf32_atmem(d_small, al, dBh + ko, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+            mma_tf32_atmem(d_main, ah, dBh + ko, idesc, (ch > 0 || ks >= 2) ? 1u : 0u);
             mma_tf32_atmem(d_small, ah, dBl + ko, idesc, 1u);
-            mma_tf32_atmem(d_main, ah, dBh + ko, idesc, (ch >= 2 || ks > 0) ? 1u : 0u);
           }
           mma_commit(&a_free[buf]);                     // A buffer and weight stage are free once these MMAs have read them
           mma_commit(&b_free[st]);

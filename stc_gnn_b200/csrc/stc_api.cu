@@ -140,6 +140,11 @@ WsLayout make_layout(const StcDims& d) {
   w.dYh = take(km1 * Rh);
   w.dYr = take((size_t)d.Ks * Rh);
   w.dQ = take((size_t)d.Kc * d.C * d.C);
+  {  // weight image of the wide-state backward dx (candidate pass, then gates pass: stream-ordered reuse)
+    const size_t ig = w.Wimg_c > w.Wimg_g ? conv_big_dx_img_floats(d.C, d.Din, d.h, d.Ks, d.Kc, 2 * d.h) : 0;
+    const size_t ic = w.saved_total > w.Wimg_c ? conv_big_dx_img_floats(d.C, d.Din, d.h, d.Ks, d.Kc, d.h) : 0;
+    w.Wimg_dx = take(ig > ic ? ig : ic);
+  }
   w.scratch_total = o;
   return w;
 }
@@ -526,6 +531,7 @@ int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
     a.dQ = want_dGc ? sc + w.dQ : nullptr;
     a.dW = dWc;
     a.Psave = sv + w.Pc;
+    a.Wimg = (w.saved_total > w.Wimg_c && w.scratch_total > w.Wimg_dx) ? sc + w.Wimg_dx : nullptr;   // wide forward ran
     STC_TRY(launch_conv_bwd_dx(a, st));
     STC_TRY(launch_conv_bwd_dw(a, st));
   }
@@ -553,6 +559,7 @@ int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
     a.dQ = want_dGc ? sc + w.dQ : nullptr;
     a.dW = dWg;
     a.Psave = sv + w.Pg;
+    a.Wimg = (w.Wimg_c > w.Wimg_g && w.scratch_total > w.Wimg_dx) ? sc + w.Wimg_dx : nullptr;   // wide forward ran
     STC_TRY(launch_conv_bwd_dx(a, st));
     STC_TRY(launch_conv_bwd_dw(a, st));
   }

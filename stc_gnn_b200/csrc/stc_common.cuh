@@ -85,7 +85,7 @@ struct WsLayout {
   // `saved` buffer (written by forward, read by backward)
   size_t u, r, c, Yr, Yx, Yh, Q, Pg, Pc, Wimg_g, Wimg_c, saved_total;
   // backward `scratch` buffer
-  size_t dpre, dYx0, dYx, dYh, dYr, dQ, scratch_total;
+  size_t dpre, dYx0, dYx, dYh, dYr, dQ, Wimg_dx, scratch_total;
 };
 WsLayout make_layout(const StcDims& d);
 
@@ -148,7 +148,8 @@ struct ConvArgs {
   int trace_tiles;
 };
 enum { OPT_L2_PREFETCH = 1, OPT_GENERIC_EPILOGUE = 4 /* diagnostic: force the general epilogues */,
-       OPT_SMEM_A = 8 /* diagnostic: convolutions with the A operand staged in shared memory */ };
+       OPT_SMEM_A = 8 /* diagnostic: convolutions with the A operand staged in shared memory */,
+       OPT_WIDE_DX_FFMA = 32 /* diagnostic: wide-state backward dx on the general path */ };
 constexpr int TRACE_SLOTS = 16;
 int conv_opt_flags();                                  // cached STC_OPT (default: OPT_L2_PREFETCH)
 void conv_trace_target(long long** buf, int* tiles);   // what stc_debug_trace_set registered (null when off)
@@ -163,6 +164,8 @@ int launch_conv_fwd(const ConvArgs& a, cudaStream_t st);
 bool conv_big_shape_ok(int C, int Din, int h, int Ks, int Kc, int Hout);
 size_t conv_big_img_floats(int C, int Din, int h, int Ks, int Kc, int Hout);   // 0 when the shape is not eligible
 int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled);
+size_t conv_big_dx_img_floats(int C, int Din, int h, int Ks, int Kc, int Hout);
+int try_launch_conv_bwd_dx_big(const ConvArgs& a, cudaStream_t st, bool* handled);
 bool conv_tc_eligible(const ConvArgs& a);  // shape-only test shared by forward and backward
 bool conv_tc_dw_shape_ok(const ConvArgs& a);  // additionally: the tensor-core dW kernel tiles this shape
 int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st);

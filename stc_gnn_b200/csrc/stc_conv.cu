@@ -346,6 +346,8 @@ int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st) {
     bool handled = false;
     STC_TRY(try_launch_conv_bwd_dx_tc(a, st, &handled));
     if (handled) return STC_OK;
+    STC_TRY(try_launch_conv_bwd_dx_big(a, st, &handled));
+    if (handled) return STC_OK;
   }
   const int L = a.Din + a.h;
   const int CGL = ((L + 3) & ~3) / 4;

@@ -17,6 +17,7 @@
 #include "stc_tc.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace stc {
 
@@ -243,6 +244,11 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
         if (cb == 1) {                                   // P_1: parked in shared memory for the mix
           *reinterpret_cast<float4*>(Pm + erow * p.PS + c0) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(Pm + erow * p.PS + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          if (a.Psave && valid) {                        // the wide-state dx kernel forms dGc from these partials
+            float4* ps = reinterpret_cast<float4*>(a.Psave + gr * (long long)Hout + c0);
+            ps[0] = make_float4(v[0], v[1], v[2], v[3]);
+            ps[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
           continue;
         }
         {                                                // P_0 + T_1(Gc)^T-mix of P_1 over the node's categories
@@ -332,8 +338,12 @@ int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled) {
   *handled = false;
   if (a.Wimg == nullptr || !conv_big_shape_ok(a.C, a.Din, a.h, a.Ks, a.Kc, a.Hout)) return STC_OK;
   if (!aligned16g(a.u) || !aligned16g(a.Hprev) || !aligned16g(a.r) || !aligned16g(a.rH) || !aligned16g(a.c) ||
-      !aligned16g(a.Hnew) || !aligned16g(a.h0) || !aligned16g(a.yh) || ((reinterpret_cast<uintptr_t>(a.Wimg) & 127) != 0))
-    return STC_OK;   // the general path takes unaligned state tensors
+      !aligned16g(a.Hnew) || !aligned16g(a.h0) || !aligned16g(a.yh) || !aligned16g(a.Psave) ||
+      ((reinterpret_cast<uintptr_t>(a.Wimg) & 127) != 0)) {
+    // forward and backward must take the same path for a shape (backward reads what this kernel saves)
+    set_error("tcgen05 wide-state path needs 16-byte aligned state / workspace tensors");
+    return STC_ERR_BAD_ARG;
+  }
   BigPlan p;
   p.npt = 128 / a.C;
   p.Dp = (a.Din + 7) & ~7;
@@ -368,6 +378,388 @@ int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled) {
                        4.0 * R * (a.Ks * L + (a.phase == 0 ? 3 * a.h : 4 * a.h)) + 4.0 * P * L * a.Hout);
   tc_conv_fwd_big_kernel<<<grid, BG_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
   STC_LAUNCH_OK("tc_conv_fwd_big_kernel");
+  *handled = true;
+  return STC_OK;
+}
+
+// =================================================================================================
+// backward dx for wide hidden states: the adjoint of the kernel above.
+//   dY_k = [Ds | Dm_1] x [W_{k,0}^T ; W_{k,1}^T]      (K = 2 Hout, one N block of KBLp columns per spatial term k)
+// Prologue (GRU / activation adjoint -> Ds tile in shared memory, dpre for the dW kernel, direct dH terms, bias
+// column sums), dT_1(Gc) from the forward's saved P_1, then per spatial term the same streamed-weight mainloop as
+// the forward with A = my row's 8 columns of [Ds | Dm_1] (Dm_1 mixed on the fly from the Ds tile) and an epilogue
+// that writes the h-part / x-part adjoints (x-part accumulated across the two convolutions).
+// =================================================================================================
+struct BigDxPlan {
+  int npt, Dp, KBL, KBLp;   // KBLp = KBL rounded up to 16: GEMM N per spatial term
+  int nkc;                  // 32-wide K chunks = 2 Hout / 32
+  int ntiles, DP, x_vec;
+  uint32_t stage_bytes;     // [hi: KBLp rows x 128 B | lo]
+  uint32_t off_b, off_ds, off_q, off_qacc, off_bar, smem_bytes;
+};
+
+// img[(k, kc)][hi | lo][n = kb][kk]  <-  W[((k*Kc + c)*L + l(kb))*Hout + o],  32 kc + kk = c*Hout + o
+__global__ void tc_big_dx_prep_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int Din, int h, int Ks,
+                                      int Kc, int Hout, int KBL, int KBLp, int nkc) {
+  const int L = Din + h;
+  const long long total = (long long)Ks * nkc * KBLp * 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx & 7);
+    long long r = idx >> 3;
+    const int n = (int)(r % KBLp);
+    r /= KBLp;
+    const int kc = (int)(r % nkc), k = (int)(r / nkc);
+    const int l = n >= KBL ? -1 : (n < h ? Din + n : (n - h < Din ? n - h : -1));
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = 32 * kc + 4 * q + i;
+      const int c = kk / Hout, o = kk - c * Hout;
+      v[i] = (l >= 0 && c < Kc) ? W[((size_t)(k * Kc + c) * L + l) * Hout + o] : 0.f;
+    }
+    uint8_t* base = img + (size_t)(k * nkc + kc) * 2 * KBLp * ATOM_ROW_BYTES;
+    store_split4(base, base + (size_t)KBLp * ATOM_ROW_BYTES, atom_chunk_offset(n, q), make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+__global__ void __launch_bounds__(BG_THREADS, 1)
+tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __restrict__ img) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, h = a.h, Din = a.Din, Hout = a.Hout, DP = p.DP;
+  const bool want_dQ = a.dQ != nullptr;
+  uint8_t* Bring = smem + p.off_b;
+  float* Dsm = reinterpret_cast<float*>(smem + p.off_ds);       // [128 + C][DP]  Ds tile (rows past 128 stay zero)
+  float* Qs = reinterpret_cast<float*>(smem + p.off_q);         // [C][C] = T_1(Gc)
+  float* dQacc = reinterpret_cast<float*>(smem + p.off_qacc);   // [C][C] per-CTA partial sums of dT_1(Gc)
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* b_free = b_full + BG_STAGES;
+  uint64_t* a_free = b_free + BG_STAGES;
+  uint64_t* acc_full = a_free + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  if (tid == 0) {
+    for (int i = 0; i < BG_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_free[i], 1);
+    }
+    mbar_init(&a_free[0], 1);
+    mbar_init(&a_free[1], 1);
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512u);
+  for (int i = tid; i < C * C; i += BG_THREADS) {
+    Qs[i] = a.Q[C * C + i];
+    dQacc[i] = 0.f;
+  }
+  for (int i = tid; i < (128 + C) * DP; i += BG_THREADS) Dsm[i] = 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const int warp_u = uniform_warp_index();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  const int Nb = p.KBLp;
+  const uint32_t idesc = make_idesc_tf32(128, Nb);
+  const uint32_t d_small = tmem_base + (uint32_t)(2 * Nb);
+  const long long total_nodes = (long long)a.B * a.N;
+  const long long R = total_nodes * C;
+
+  const int sp = warp & 3, qtr = warp >> 2;
+  const int erow = sp * 32 + lane;
+  const int enode = erow / C, ecat = erow - enode * C;
+  const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
+  const float* qrow = Qs + ecat * C;                    // Dm_1[(node,c')][o] = sum_d Q_1[c'][d] Ds[(node,d)][o]
+  const bool xvec = p.x_vec != 0;
+  float db_acc = 0.f;                                   // thread j < Hout owns bias-gradient column j
+
+  const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t per_tile = (uint32_t)(a.Ks * p.nkc);
+  const uint32_t total_chunks = (uint32_t)my_tiles * per_tile;
+  auto img_of = [&](uint32_t g) { return img + (size_t)(g % per_tile) * p.stage_bytes; };   // (k, kc) order = issue order
+  if (warp_u == 1 && elect_one_sync()) {
+    for (uint32_t g = 0; g < (uint32_t)(BG_STAGES - 1) && g < total_chunks; ++g) {
+      mbar_arrive_expect_tx(&b_full[g], p.stage_bytes);
+      bulk_g2s(Bring + (size_t)g * p.stage_bytes, img_of(g), p.stage_bytes, &b_full[g]);
+    }
+  }
+
+  uint32_t g = 0;
+  uint32_t acc_phase = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long g0 = (long long)tile * p.npt;
+    const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
+    const int rows_valid = nodes_valid * C;
+    const long long row0 = g0 * C;
+    const bool valid = erow < rows_valid;
+    const long long gr = row0 + erow;
+    // ---- 1. elementwise adjoint: one float4 of hidden channels per item ----
+    const int cpr = h >> 2;
+    for (int it = tid; it < 128 * cpr; it += BG_THREADS) {
+      const int row = it / cpr, j = (it - row * cpr) << 2;
+      float4 g0v = make_float4(0.f, 0.f, 0.f, 0.f), g1v = g0v;
+      if (row < rows_valid) {
+        const long long o = (row0 + row) * h + j;
+        const float4 dhn = *reinterpret_cast<const float4*>(a.dHn + o);
+        const float4 uu = *reinterpret_cast<const float4*>(a.u + o);
+        const float4 cc = *reinterpret_cast<const float4*>(a.c + o);
+        if (a.phase == 1) {
+          g0v = make_float4(dhn.x * uu.x * (1.f - cc.x * cc.x), dhn.y * uu.y * (1.f - cc.y * cc.y),
+                            dhn.z * uu.z * (1.f - cc.z * cc.z), dhn.w * uu.w * (1.f - cc.w * cc.w));
+          if (a.act == STC_ACT_RELU) {
+            if (!(cc.x > 0.f)) g0v.x = 0.f;
+            if (!(cc.y > 0.f)) g0v.y = 0.f;
+            if (!(cc.z > 0.f)) g0v.z = 0.f;
+            if (!(cc.w > 0.f)) g0v.w = 0.f;
+          }
+          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * a.dpre_ld + j) = g0v;
+        } else {
+          const float4 hp = *reinterpret_cast<const float4*>(a.Hprev + o);
+          const float4 rr = *reinterpret_cast<const float4*>(a.r + o);
+          const float4 drh = *reinterpret_cast<const float4*>(a.drH + o);
+          g0v = make_float4(dhn.x * (cc.x - hp.x) * uu.x * (1.f - uu.x), dhn.y * (cc.y - hp.y) * uu.y * (1.f - uu.y),
+                            dhn.z * (cc.z - hp.z) * uu.z * (1.f - uu.z), dhn.w * (cc.w - hp.w) * uu.w * (1.f - uu.w));
+          g1v = make_float4(drh.x * hp.x * rr.x * (1.f - rr.x), drh.y * hp.y * rr.y * (1.f - rr.y),
+                            drh.z * hp.z * rr.z * (1.f - rr.z), drh.w * hp.w * rr.w * (1.f - rr.w));
+          if (a.act == STC_ACT_RELU) {
+            if (!(uu.x > 0.5f)) g0v.x = 0.f;
+            if (!(uu.y > 0.5f)) g0v.y = 0.f;
+            if (!(uu.z > 0.5f)) g0v.z = 0.f;
+            if (!(uu.w > 0.5f)) g0v.w = 0.f;
+            if (!(rr.x > 0.5f)) g1v.x = 0.f;
+            if (!(rr.y > 0.5f)) g1v.y = 0.f;
+            if (!(rr.z > 0.5f)) g1v.z = 0.f;
+            if (!(rr.w > 0.5f)) g1v.w = 0.f;
+          }
+          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * a.dpre_ld + j) = g0v;
+          *reinterpret_cast<float4*>(a.dpre + (row0 + row) * a.dpre_ld + h + j) = g1v;
+          // direct terms of dH; the k = 0 epilogue adds the convolution adjoint (after the block barrier below)
+          *reinterpret_cast<float4*>(a.dYh0 + o) =
+              make_float4(dhn.x * (1.f - uu.x) + drh.x * rr.x, dhn.y * (1.f - uu.y) + drh.y * rr.y,
+                          dhn.z * (1.f - uu.z) + drh.z * rr.z, dhn.w * (1.f - uu.w) + drh.w * rr.w);
+        }
+      }
+      *reinterpret_cast<float4*>(Dsm + row * DP + j) = g0v;
+      if (a.phase == 0) *reinterpret_cast<float4*>(Dsm + row * DP + h + j) = g1v;
+    }
+    __syncthreads();
+    if (a.dbias && tid < Hout) {
+      float sacc = 0.f;
+      for (int row = 0; row < rows_valid; ++row) sacc += Dsm[row * DP + tid];
+      db_acc += sacc;
+    }
+    // ---- 2. dT_1(Gc)[c'][d] += sum_{node,o} P_1[(node,c')][o] * Ds[(node,d)][o]  (P_1 saved by the forward kernel) ----
+    if (want_dQ) {
+      for (int pr = tid; pr < C * C; pr += BG_THREADS) {
+        const int cp = pr / C, d = pr - cp * C;
+        float sacc = 0.f;
+        for (int node = 0; node < nodes_valid; ++node) {
+          const float* pp = a.Psave + (row0 + node * C + cp) * (long long)Hout;
+          const float* dd = Dsm + (node * C + d) * DP;
+          for (int o = 0; o < Hout; o += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(pp + o);
+            const float4 y = *reinterpret_cast<const float4*>(dd + o);
+            sacc = fmaf(x.x, y.x, sacc); sacc = fmaf(x.y, y.y, sacc); sacc = fmaf(x.z, y.z, sacc); sacc = fmaf(x.w, y.w, sacc);
+          }
+        }
+        dQacc[pr] += sacc;   // pair pr is only ever touched by this thread
+      }
+    }
+    // ---- 3. per spatial term: streamed-weight GEMM + epilogue ----
+    for (int k = 0; k < a.Ks; ++k) {
+      for (int kc = 0; kc < p.nkc; ++kc, ++g) {
+        // my 8 columns of [Ds | Dm_1]: K range [32 kc + 8 qtr, +8)
+        const int kk0 = 32 * kc + 8 * qtr;
+        float av[8];
+        if (kk0 < Hout) {
+          const float4 x0 = *reinterpret_cast<const float4*>(Dsm + erow * DP + kk0);
+          const float4 x1 = *reinterpret_cast<const float4*>(Dsm + erow * DP + kk0 + 4);
+          av[0] = x0.x; av[1] = x0.y; av[2] = x0.z; av[3] = x0.w; av[4] = x1.x; av[5] = x1.y; av[6] = x1.z; av[7] = x1.w;
+        } else {
+          const float* spm = Dsm + (enode * C) * DP + (kk0 - Hout);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) av[i] = 0.f;
+#pragma unroll 4
+          for (int d = 0; d < C; ++d) {
+            const float w = qrow[d];
+            const float4 x0 = *reinterpret_cast<const float4*>(spm + d * DP);
+            const float4 x1 = *reinterpret_cast<const float4*>(spm + d * DP + 4);
+            av[0] = fmaf(w, x0.x, av[0]); av[1] = fmaf(w, x0.y, av[1]); av[2] = fmaf(w, x0.z, av[2]); av[3] = fmaf(w, x0.w, av[3]);
+            av[4] = fmaf(w, x1.x, av[4]); av[5] = fmaf(w, x1.y, av[5]); av[6] = fmaf(w, x1.z, av[6]); av[7] = fmaf(w, x1.w, av[7]);
+          }
+        }
+        const int buf = (int)(g & 1u);
+        const uint32_t ua = g >> 1;
+        if (ua >= 1u) {
+          mbar_wait(&a_free[buf], (ua - 1u) & 1u);
+          fence_after_sync();
+        }
+        {
+          const uint32_t tA = tl + (uint32_t)(BG_ACOL + 64 * buf + 8 * qtr);
+          float hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_tf32(av[i], hi[i], lo[i]);
+          tmem_st8(tA, hi);
+          tmem_st8(tA + 32u, lo);
+        }
+        tmem_st_wait();
+        fence_before_sync();
+        __syncthreads();
+        const int st = (int)(g % (uint32_t)BG_STAGES);
+        if (warp_u == 0 && elect_one_sync()) {
+          mbar_wait(&b_full[st], (g / (uint32_t)BG_STAGES) & 1u);
+          fence_after_sync();
+          const uint32_t a_hi0 = tmem_base + (uint32_t)(BG_ACOL + 64 * buf);
+          const uint64_t dBh = make_smem_desc_sw128(smem_u32(Bring + (size_t)st * p.stage_bytes));
+          const uint64_t dBl = dBh + (uint64_t)(((uint32_t)Nb * ATOM_ROW_BYTES) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ko = (uint64_t)(ks * 2);
+            const uint32_t ah = a_hi0 + (uint32_t)(ks * 8), al = ah + 32u;
+            const uint32_t d_main = tmem_base + (uint32_t)((ks & 1) * Nb);
+            mma_tf32_atmem(d_small, al, dBh + ko, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            mma_tf32_atmem(d_main, ah, dBh + ko, idesc, (kc > 0 || ks >= 2) ? 1u : 0u);
+            mma_tf32_atmem(d_small, ah, dBl + ko, idesc, 1u);
+          }
+          mma_commit(&a_free[buf]);
+          mma_commit(&b_free[st]);
+          if (kc == p.nkc - 1) mma_commit(acc_full);
+        }
+        if (warp_u == 1 && elect_one_sync()) {
+          const uint32_t t = g + (uint32_t)(BG_STAGES - 1);
+          if (t < total_chunks) {
+            const uint32_t ts = t % (uint32_t)BG_STAGES, tu = t / (uint32_t)BG_STAGES;
+            if (tu >= 1u) mbar_wait(&b_free[ts], (tu - 1u) & 1u);
+            mbar_arrive_expect_tx(&b_full[ts], p.stage_bytes);
+            bulk_g2s(Bring + (size_t)ts * p.stage_bytes, img_of(t), p.stage_bytes, &b_full[ts]);
+          }
+        }
+      }
+      // ---- epilogue of spatial term k: columns [0,h) -> h-part adjoint, [h, h+Din) -> x-part adjoint ----
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1u;
+      fence_after_sync();
+      for (int c0 = 8 * qtr; c0 < Nb; c0 += 32) {
+        float v[8];
+        {
+          uint32_t t0[8], t1[8], t2[8];
+          tmem_ld8_async(tl + (uint32_t)(2 * Nb + c0), t2);
+          tmem_ld8_async(tl + (uint32_t)c0, t0);
+          tmem_ld8_async(tl + (uint32_t)(Nb + c0), t1);
+          tmem_ld_wait();
+          tmem_ld_pin8(t0); tmem_ld_pin8(t1); tmem_ld_pin8(t2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = (__uint_as_float(t2[i]) + __uint_as_float(t0[i])) + __uint_as_float(t1[i]);
+        }
+        if (!valid) continue;
+        if (c0 < h) {
+          float* dst = (k == 0 ? a.dYh0 : a.dYh + (size_t)(k - 1) * R * h) + gr * h + c0;
+          float4 o0 = make_float4(v[0], v[1], v[2], v[3]), o1 = make_float4(v[4], v[5], v[6], v[7]);
+          if (k == 0 && a.phase == 0) {   // the prologue left the direct dH terms there
+            const float4 p0 = reinterpret_cast<const float4*>(dst)[0], p1 = reinterpret_cast<const float4*>(dst)[1];
+            o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+            o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+          }
+          reinterpret_cast<float4*>(dst)[0] = o0;
+          reinterpret_cast<float4*>(dst)[1] = o1;
+        } else {
+          const int xi = c0 - h;
+          if (xi >= Din) continue;
+          float* dst = (k == 0 ? a.dYx0 : a.dYx + (size_t)(k - 1) * R * Din) + gr * Din + xi;
+          if (xvec) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (xi + 4 * i < Din) {
+                float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                if (a.accum_x) {
+                  const float4 pv = reinterpret_cast<const float4*>(dst)[i];
+                  o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+                }
+                reinterpret_cast<float4*>(dst)[i] = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (xi + i < Din) dst[i] = a.accum_x ? dst[i] + v[i] : v[i];
+          }
+        }
+      }
+      fence_before_sync();
+      __syncthreads();
+    }
+  }
+  if (a.dbias && tid < Hout) atomicAdd(&a.dbias[tid], db_acc);
+  if (want_dQ)
+    for (int i = tid; i < C * C; i += BG_THREADS) atomicAdd(&a.dQ[C * C + i], dQacc[i]);
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512u);
+}
+
+static bool big_dx_shape_ok(const ConvArgs& a) {
+  if (!conv_big_shape_ok(a.C, a.Din, a.h, a.Ks, a.Kc, a.Hout)) return false;
+  const int KBLp = (a.h + ((a.Din + 7) & ~7) + 15) & ~15;
+  if (KBLp > 128) return false;
+  const size_t smem = (size_t)BG_STAGES * 2 * KBLp * ATOM_ROW_BYTES + (size_t)(128 + a.C) * (a.Hout + 4) * sizeof(float) +
+                      2 * (size_t)a.C * a.C * sizeof(float) + 2048;
+  return smem <= 220 * 1024;
+}
+
+size_t conv_big_dx_img_floats(int C, int Din, int h, int Ks, int Kc, int Hout) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.C = C; a.Din = Din; a.h = h; a.Ks = Ks; a.Kc = Kc; a.Hout = Hout;
+  if (!big_dx_shape_ok(a)) return 0;
+  const int KBLp = (h + ((Din + 7) & ~7) + 15) & ~15;
+  return (size_t)Ks * (2 * Hout / 32) * 2 * KBLp * (ATOM_ROW_BYTES / sizeof(float));
+}
+
+int try_launch_conv_bwd_dx_big(const ConvArgs& a, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (a.Wimg == nullptr || !big_dx_shape_ok(a) || (a.opt & OPT_WIDE_DX_FFMA)) return STC_OK;
+  if (!aligned16g(a.dHn) || !aligned16g(a.u) || !aligned16g(a.c) || !aligned16g(a.Hprev) || !aligned16g(a.dpre) ||
+      !aligned16g(a.dYh0) || !aligned16g(a.dYh) || !aligned16g(a.Psave) || (a.dpre_ld % 4) != 0 ||
+      (a.phase == 0 && (!aligned16g(a.r) || !aligned16g(a.drH))) || ((reinterpret_cast<uintptr_t>(a.Wimg) & 127) != 0)) {
+    set_error("tcgen05 wide-state backward needs 16-byte aligned gradient / workspace tensors");
+    return STC_ERR_BAD_ARG;
+  }
+  BigDxPlan p;
+  p.npt = 128 / a.C;
+  p.Dp = (a.Din + 7) & ~7;
+  p.KBL = a.h + p.Dp;
+  p.KBLp = (p.KBL + 15) & ~15;
+  p.nkc = 2 * a.Hout / 32;
+  p.DP = a.Hout + 4;
+  p.x_vec = (a.Din % 4 == 0) && aligned16g(a.dYx0) && aligned16g(a.dYx);
+  const long long total_nodes = (long long)a.B * a.N;
+  p.ntiles = ceil_div(total_nodes, p.npt);
+  p.stage_bytes = (uint32_t)(2 * p.KBLp * ATOM_ROW_BYTES);
+  size_t o = 0;
+  p.off_b = (uint32_t)o; o += (size_t)BG_STAGES * p.stage_bytes;
+  p.off_ds = (uint32_t)o; o += round_up((size_t)(128 + a.C) * p.DP * sizeof(float), 16);
+  p.off_q = (uint32_t)o; o += round_up((size_t)a.C * a.C * sizeof(float), 16);
+  p.off_qacc = (uint32_t)o; o += round_up((size_t)a.C * a.C * sizeof(float), 16);
+  p.off_bar = (uint32_t)o; o += 8 * (2 * BG_STAGES + 3) + 16;
+  p.smem_bytes = (uint32_t)o;
+  if (p.smem_bytes > 226 * 1024) return STC_OK;
+  {
+    const long long items = (long long)a.Ks * p.nkc * p.KBLp * 8;
+    tc_big_dx_prep_kernel<<<(int)min((items + 255) / 256, (long long)1024), 256, 0, st>>>(
+        a.W, reinterpret_cast<uint8_t*>(a.Wimg), a.Din, a.h, a.Ks, a.Kc, a.Hout, p.KBL, p.KBLp, p.nkc);
+    STC_LAUNCH_OK("tc_big_dx_prep_kernel");
+  }
+  STC_TRY(set_smem(tc_conv_bwd_dx_big_kernel, p.smem_bytes));
+  int grid = device_sm_count();
+  if (grid > p.ntiles) grid = p.ntiles;
+  const int L = a.Din + a.h;
+  const double R = (double)total_nodes * a.C;
+  ScopedKernelTimer _t(KK_TC_CONV_BWD_DX, st,
+                       4.0 * R * ((a.phase == 0 ? 6 * a.h + a.Ks * a.Din : 3 * a.h) + a.Hout + a.Ks * L +
+                                  (a.dQ ? a.Hout : 0)) + 4.0 * a.Ks * a.Kc * L * a.Hout);
+  tc_conv_bwd_dx_big_kernel<<<grid, BG_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
+  STC_LAUNCH_OK("tc_conv_bwd_dx_big_kernel");
   *handled = true;
   return STC_OK;
 }

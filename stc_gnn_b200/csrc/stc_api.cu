@@ -182,8 +182,10 @@ static ConvArgs base_args(const StcDims& d, const float* xt, int64_t xt_bs, cons
   a.yx = ws + w.Yx;
   a.W = W;
   a.Q = Q;
-  a.dpre_ld = conv_tc_eligible(a) ? a.Kc * a.Hout : a.Hout;
+  // dx leaves [Ds | Dm_1 ...] side by side for the tensor-core dW kernels; the general path only the plain Ds
   a.opt = conv_opt_flags();
+  const bool wide_bwd = !(a.opt & OPT_WIDE_DX_FFMA) && conv_big_bwd_shape_ok(a.C, a.Din, a.h, a.Ks, a.Kc, a.Hout);
+  a.dpre_ld = (conv_tc_eligible(a) || wide_bwd) ? a.Kc * a.Hout : a.Hout;
   conv_trace_target(&a.trace, &a.trace_tiles);
   if (a.trace) a.trace += (size_t)phase * a.trace_tiles * TRACE_SLOTS;   // gates stamps first, candidate stamps after them
   return a;

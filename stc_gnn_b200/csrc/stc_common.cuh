@@ -166,6 +166,8 @@ size_t conv_big_img_floats(int C, int Din, int h, int Ks, int Kc, int Hout);   /
 int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled);
 size_t conv_big_dx_img_floats(int C, int Din, int h, int Ks, int Kc, int Hout);
 int try_launch_conv_bwd_dx_big(const ConvArgs& a, cudaStream_t st, bool* handled);
+bool conv_big_bwd_shape_ok(int C, int Din, int h, int Ks, int Kc, int Hout);   // wide-state dx + dW kernels tile this shape
+int try_launch_conv_bwd_dw_big(const ConvArgs& a, cudaStream_t st, bool* handled);
 bool conv_tc_eligible(const ConvArgs& a);  // shape-only test shared by forward and backward
 bool conv_tc_dw_shape_ok(const ConvArgs& a);  // additionally: the tensor-core dW kernel tiles this shape
 int launch_conv_bwd_dx(const ConvArgs& a, cudaStream_t st);

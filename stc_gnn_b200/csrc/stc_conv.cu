@@ -503,6 +503,8 @@ int launch_conv_bwd_dw(const ConvArgs& a, cudaStream_t st) {
     bool handled = false;
     STC_TRY(try_launch_conv_bwd_dw_tc(a, st, &handled));
     if (handled) return STC_OK;
+    STC_TRY(try_launch_conv_bwd_dw_big(a, st, &handled));
+    if (handled) return STC_OK;
   }
   const int L = a.Din + a.h;
   const int LP4 = (L + 3) & ~3;

@@ -590,6 +590,11 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
             av[4] = fmaf(w, x1.x, av[4]); av[5] = fmaf(w, x1.y, av[5]); av[6] = fmaf(w, x1.z, av[6]); av[7] = fmaf(w, x1.w, av[7]);
           }
         }
+        if (k == 0 && kk0 >= Hout && valid && a.dpre_ld >= 2 * Hout) {   // the wide dW kernel contracts Y_k^T with [Ds | Dm_1]
+          float4* dp = reinterpret_cast<float4*>(a.dpre + gr * a.dpre_ld + kk0);
+          dp[0] = make_float4(av[0], av[1], av[2], av[3]);
+          dp[1] = make_float4(av[4], av[5], av[6], av[7]);
+        }
         const int buf = (int)(g & 1u);
         const uint32_t ua = g >> 1;
         if (ua >= 1u) {
@@ -760,6 +765,246 @@ int try_launch_conv_bwd_dx_big(const ConvArgs& a, cudaStream_t st, bool* handled
                                   (a.dQ ? a.Hout : 0)) + 4.0 * a.Ks * a.Kc * L * a.Hout);
   tc_conv_bwd_dx_big_kernel<<<grid, BG_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
   STC_LAUNCH_OK("tc_conv_bwd_dx_big_kernel");
+  *handled = true;
+  return STC_OK;
+}
+
+// =================================================================================================
+// weight gradient for wide hidden states:  dW_{k,c} = Y_k^T x DD_c,  DD = [Ds | Dm_1] as left in `dpre` by the kernel
+// above ([R][2 Hout]).  The contraction runs over rows, so both operands change with every chunk: each CTA owns one
+// 128 x 128 output tile (spatial term k x a 128-column slice of [Ds | Dm_1]) and a contiguous range of rows; per
+// 32-row chunk every thread loads two 16-byte pieces of each operand (next chunk's loads in flight), splits them and
+// stores them MN-major (rows = K, SWIZZLE_128B_BASE32B, as tc_conv_bwd_dw_pipe_kernel) into one of two image buffers;
+// 12 MMAs per chunk into main0 / main1 / cross accumulators, drained into fp32 registers every BG_DW_DRAIN chunks
+// (bounded accumulation chains), one atomicAdd per element at the end.
+// =================================================================================================
+constexpr int BG_DW_CR = 32;       // rows per chunk (K extent of one image)
+constexpr int BG_DW_DRAIN = 32;    // chunks per accumulation chain: 64 K-steps into each main accumulator
+
+struct BigDwPlan {
+  int Dp, KBL, N1, NH;             // N1 = 2 Hout, NH = 128-column slices of it
+  int nsplit;                      // row ranges per output tile
+  long long rows_per;              // rows per range (multiple of BG_DW_CR)
+  int x_vec;
+  uint32_t img_bytes;              // one buffer: [A_hi | A_lo | B_hi | B_lo], 16 KB each
+  uint32_t off_img, off_bar, smem_bytes;
+};
+
+__global__ void __launch_bounds__(BG_THREADS, 1)
+tc_conv_bwd_dw_big_kernel(const ConvArgs a, const BigDwPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, h = a.h, Din = a.Din, Hout = a.Hout, L = a.Din + a.h;
+  constexpr uint32_t IMG1 = 4u * BG_DW_CR * ATOM_ROW_BYTES;          // one hi or lo image: 4 column blocks x 32 rows
+  uint8_t* img = smem + p.off_img;
+  uint64_t* img_free = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [2] MMAs that read an image buffer are done
+  uint64_t* acc_full = img_free + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  if (tid == 0) {
+    mbar_init(&img_free[0], 1);
+    mbar_init(&img_free[1], 1);
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512u);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const int warp_u = uniform_warp_index();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  const uint32_t idesc = make_idesc_tf32_mn(128, 128);
+  const uint32_t d_small = tmem_base + 256u;
+  const long long total_nodes = (long long)a.B * a.N;
+  const long long R = total_nodes * C;
+
+  // which output tile / row range
+  const int T = a.Ks * p.NH;
+  const int tile = (int)blockIdx.x % T, split = (int)blockIdx.x / T;
+  const int k = tile / p.NH, nh = tile - k * p.NH;
+  const long long rbeg = (long long)split * p.rows_per;
+  const long long rend = min(R, rbeg + p.rows_per);
+  const int nchunks = rbeg < rend ? (int)((rend - rbeg + BG_DW_CR - 1) / BG_DW_CR) : 0;
+
+  // staging map: 16-byte piece cq of rows r0 + 16 i (i = 0, 1) of either operand
+  const int cq = tid & 31, r0 = tid >> 5;
+  const int m0 = 4 * cq;                                  // feature index kb (A) / column within the slice (B)
+  const uint32_t soff0 = (uint32_t)(m0 >> 5) * (BG_DW_CR * ATOM_ROW_BYTES);
+  // A source: feature kb of spatial term k -> h-part (kb < h), x-part, or zero padding
+  int apart = 2;                                          // 0 = h-part, 1 = x-part, 2 = zero
+  int aoff = 0;
+  if (m0 < h) { apart = 0; aoff = m0; }
+  else if (m0 - h < Din) { apart = 1; aoff = m0 - h; }
+  const int anvalid = apart == 1 ? min(4, Din - aoff) : 4;
+  const bool avec = apart == 0 || (apart == 1 && p.x_vec && anvalid == 4);
+  const int bn = nh * 128 + m0;                           // column of [Ds | Dm_1]
+  const bool blive = bn < p.N1;
+  const float* hsrc = (k == 0 ? a.h0 : a.yh + (size_t)(k - 1) * R * h);
+  const float* xsrc = (k == 0 ? a.x0 : a.yx + (size_t)(k - 1) * R * Din);
+
+  auto fetch = [&](int ch, float4 (&fa)[2], float4 (&fb)[2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long row = rbeg + (long long)ch * BG_DW_CR + r0 + 16 * i;
+      fa[i] = fb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row >= rend) continue;
+      if (apart == 0) {
+        fa[i] = *reinterpret_cast<const float4*>(hsrc + row * h + aoff);
+      } else if (apart == 1) {
+        const float* xs;
+        if (k == 0) {     // Xt carries a batch stride: row -> (sample, row within the sample)
+          const long long rows_per_sample = (long long)a.N * C;
+          const long long b = row / rows_per_sample;
+          xs = xsrc + b * a.x0_bs + (row - b * rows_per_sample) * Din + aoff;
+        } else {
+          xs = xsrc + row * Din + aoff;
+        }
+        if (avec) {
+          fa[i] = *reinterpret_cast<const float4*>(xs);
+        } else {
+          fa[i].x = xs[0];
+          if (anvalid > 1) fa[i].y = xs[1];
+          if (anvalid > 2) fa[i].z = xs[2];
+          if (anvalid > 3) fa[i].w = xs[3];
+        }
+      }
+      if (blive) fb[i] = *reinterpret_cast<const float4*>(a.dpre + row * a.dpre_ld + bn);
+    }
+  };
+
+  // accumulator ownership: TMEM lane = feature kb, four threads per lane split the 128 columns
+  const int sp = warp & 3, qtr = warp >> 2;
+  const int mrow = sp * 32 + lane;
+  const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  uint32_t acc_phase = 0;
+  auto drain = [&]() {          // every MMA issued so far has been committed to acc_full by the issuer
+    mbar_wait(acc_full, acc_phase);
+    acc_phase ^= 1u;
+    fence_after_sync();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t t0[8], t1[8], t2[8];
+      const uint32_t c0 = (uint32_t)(32 * qtr + 8 * i);
+      tmem_ld8_async(tl + 256u + c0, t2);
+      tmem_ld8_async(tl + c0, t0);
+      tmem_ld8_async(tl + 128u + c0, t1);
+      tmem_ld_wait();
+      tmem_ld_pin8(t0); tmem_ld_pin8(t1); tmem_ld_pin8(t2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        acc[i][j] += (__uint_as_float(t2[j]) + __uint_as_float(t0[j])) + __uint_as_float(t1[j]);
+    }
+    fence_before_sync();
+    __syncthreads();            // the next chain's first MMAs overwrite the accumulators
+  };
+
+  float4 ca[2], cb[2], na[2], nb[2];
+  if (nchunks > 0) fetch(0, ca, cb);
+  int in_chain = 0;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    if (ch + 1 < nchunks) fetch(ch + 1, na, nb);
+    const int buf = ch & 1;
+    const uint32_t ub = (uint32_t)ch >> 1;
+    if (ub >= 1u) mbar_wait(&img_free[buf], (ub - 1u) & 1u);
+    uint8_t* A_hi = img + (size_t)buf * p.img_bytes;
+    uint8_t* A_lo = A_hi + IMG1;
+    uint8_t* B_hi = A_lo + IMG1;
+    uint8_t* B_lo = B_hi + IMG1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t off = soff0 + mn32_chunk_offset(r0 + 16 * i, (m0 & 31) >> 2);
+      store_split4(A_hi, A_lo, off, ca[i]);
+      store_split4(B_hi, B_lo, off, cb[i]);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (warp_u == 0 && elect_one_sync()) {
+      fence_after_sync();
+      const uint32_t lbo = BG_DW_CR * ATOM_ROW_BYTES;
+      const uint32_t base = smem_u32(A_hi);
+#pragma unroll
+      for (int ks = 0; ks < BG_DW_CR / 8; ++ks) {
+        const uint32_t o = (uint32_t)ks * 2u * MN32_GROUP_BYTES;
+        const uint64_t ah = make_smem_desc_mn32(base + o, lbo, MN32_GROUP_BYTES);
+        const uint64_t al = make_smem_desc_mn32(base + IMG1 + o, lbo, MN32_GROUP_BYTES);
+        const uint64_t bh = make_smem_desc_mn32(base + 2 * IMG1 + o, lbo, MN32_GROUP_BYTES);
+        const uint64_t bl = make_smem_desc_mn32(base + 3 * IMG1 + o, lbo, MN32_GROUP_BYTES);
+        const uint32_t d_main = tmem_base + (uint32_t)((ks & 1) * 128);
+        mma_tf32(d_small, al, bh, idesc, (in_chain > 0 || ks > 0) ? 1u : 0u);
+        mma_tf32(d_main, ah, bh, idesc, (in_chain > 0 || ks >= 2) ? 1u : 0u);
+        mma_tf32(d_small, ah, bl, idesc, 1u);
+      }
+      mma_commit(&img_free[buf]);
+      if (in_chain == BG_DW_DRAIN - 1 || ch == nchunks - 1) mma_commit(acc_full);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      ca[i] = na[i];
+      cb[i] = nb[i];
+    }
+    if (++in_chain == BG_DW_DRAIN || ch == nchunks - 1) {
+      drain();
+      in_chain = 0;
+    }
+  }
+  // ---- one atomicAdd per owned element: dW[((k*Kc + c)*L + l)*Hout + o] ----
+  if (nchunks > 0 && mrow < p.KBL) {
+    const int l = mrow < h ? Din + mrow : (mrow - h < Din ? mrow - h : -1);
+    if (l >= 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n = nh * 128 + 32 * qtr + 8 * i + j;
+          if (n < p.N1) {
+            const int c = n / Hout, o = n - c * Hout;
+            atomicAdd(&a.dW[((size_t)(k * a.Kc + c) * L + l) * Hout + o], acc[i][j]);
+          }
+        }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512u);
+}
+
+bool conv_big_bwd_shape_ok(int C, int Din, int h, int Ks, int Kc, int Hout) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.C = C; a.Din = Din; a.h = h; a.Ks = Ks; a.Kc = Kc; a.Hout = Hout;
+  return big_dx_shape_ok(a);
+}
+
+int try_launch_conv_bwd_dw_big(const ConvArgs& a, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (a.Wimg == nullptr || !big_dx_shape_ok(a) || a.dpre_ld < 2 * a.Hout || (a.opt & OPT_WIDE_DX_FFMA)) return STC_OK;
+  if (!aligned16g(a.dpre) || !aligned16g(a.h0) || !aligned16g(a.yh) || (a.dpre_ld % 4) != 0) return STC_OK;
+  BigDwPlan p;
+  p.Dp = (a.Din + 7) & ~7;
+  p.KBL = a.h + p.Dp;
+  p.N1 = 2 * a.Hout;
+  p.NH = (p.N1 + 127) / 128;
+  p.x_vec = (a.Din % 4 == 0) && (a.x0_bs % 4 == 0) && aligned16g(a.x0) && aligned16g(a.yx);
+  const long long R = (long long)a.B * a.N * a.C;
+  const int T = a.Ks * p.NH;
+  p.nsplit = device_sm_count() / T;
+  if (p.nsplit < 1) p.nsplit = 1;
+  p.rows_per = (R + p.nsplit - 1) / p.nsplit;
+  p.rows_per = (p.rows_per + BG_DW_CR - 1) / BG_DW_CR * BG_DW_CR;
+  p.img_bytes = 4u * 4u * BG_DW_CR * ATOM_ROW_BYTES;
+  size_t o = 0;
+  p.off_img = (uint32_t)o; o += 2 * (size_t)p.img_bytes;
+  p.off_bar = (uint32_t)o; o += 8 * 3 + 16;
+  p.smem_bytes = (uint32_t)o;
+  STC_TRY(set_smem(tc_conv_bwd_dw_big_kernel, p.smem_bytes));
+  const int L = a.Din + a.h;
+  ScopedKernelTimer _t(KK_TC_CONV_BWD_DW, st, 4.0 * (double)R * (a.Ks * L + a.Kc * a.Hout));
+  tc_conv_bwd_dw_big_kernel<<<T * p.nsplit, BG_THREADS, p.smem_bytes, st>>>(a, p);
+  STC_LAUNCH_OK("tc_conv_bwd_dw_big_kernel");
   *handled = true;
   return STC_OK;
 }

@@ -31,6 +31,9 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 SF = dict(N=100, C=5, h=16, Din=1, Ks=2, Kc=2, layers=2, T=9, horizon=3, grid=(10, 10))
+# BASELINE.json configs[2] (side workload, --workload g4096): 64x64 grid, constant CSR support, encoder only
+G4096 = dict(N=4096, C=16, h=64, Din=1, Ks=2, Kc=2, layers=2, T=12, horizon=0, grid=(64, 64))
+WL = SF          # selected in main() from --workload
 METRIC = "train samples/s (fwd+bwd), SF-shape STC cell stack"
 UNIT = "samples/s"
 
@@ -45,6 +48,9 @@ def parse():
     p.add_argument("--cpu-batch", type=int, default=128, help="windows per CPU-baseline step (bounded sample)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-roofline", action="store_true", help="skip the instrumented per-kernel pass")
+    p.add_argument("--workload", default="sf", choices=["sf", "g4096"],
+                   help="sf = BASELINE configs[1] (headline); g4096 = configs[2]: N=4096 grid, C=16, F=64, T=12, CSR support "
+                        "(default batch 4 per GPU; no CPU arm)")
     p.add_argument("--cuda-graph", action="store_true",
                    help="capture the whole fwd+bwd step once and replay it (stc_gnn_b200.GraphedStep; N=1 only)")
     return p.parse_args()
@@ -79,9 +85,12 @@ def measured_peaks():
 def synthetic_inputs(B, seed, device="cpu", pin=False):
     from stc_gnn_b200.synth import sf_supports
     g = torch.Generator().manual_seed(seed)
-    X = (torch.rand(B, SF["T"], SF["N"], SF["C"], 1, generator=g) < 0.1635).float()   # Bernoulli(data mean)
-    y = (torch.rand(B, SF["horizon"], SF["N"], SF["C"], generator=g) < 0.1635).float()
-    Gs, Gc = sf_supports(seed=0)
+    X = (torch.rand(B, WL["T"], WL["N"], WL["C"], 1, generator=g) < 0.1635).float()   # Bernoulli(data mean)
+    y = (torch.rand(B, WL["horizon"] or WL["T"], WL["N"], WL["C"], generator=g) < 0.1635).float()
+    if WL is SF:
+        Gs, Gc = sf_supports(seed=0)
+    else:   # constant supports: the CSR grid is built on the device by the caller, Gc ~ U(0,1)/C
+        Gs, Gc = None, torch.rand(WL["C"], WL["C"], generator=torch.Generator().manual_seed(0)) / WL["C"]
     if pin:
         X, y = X.pin_memory(), y.pin_memory()
     return X, y, Gs, Gc
@@ -200,14 +209,17 @@ def run_reference(args, rank):
 
 
 def workload_config(B, n_gpus, reference=False, graph=False):
+    name = ("sf_cell_stack: encoder 2x9 + decoder 3x2 = 24 STC cell steps/sample, fwd+bwd incl. dGs,dGc "
+            "(BASELINE.json configs[1], SF shape)") if WL is SF else (
+            "g4096_encoder: 2 layers x T=12 = 24 STC cell steps/sample, fwd+bwd, constant CSR 64x64-grid support and "
+            "constant Gc (BASELINE.json configs[2]: N=4096, C=16, F=64)")
     return {
-        "workload": "sf_cell_stack: encoder 2x9 + decoder 3x2 = 24 STC cell steps/sample, fwd+bwd incl. dGs,dGc "
-                    "(BASELINE.json configs[1], SF shape)",
-        "N": SF["N"], "C": SF["C"], "hidden": SF["h"], "Ks": SF["Ks"], "Kc": SF["Kc"], "layers": SF["layers"],
-        "T": SF["T"], "horizon": SF["horizon"], "batch_per_gpu": B, "global_batch": B * (1 if reference else n_gpus),
+        "workload": name,
+        "N": WL["N"], "C": WL["C"], "hidden": WL["h"], "Ks": WL["Ks"], "Kc": WL["Kc"], "layers": WL["layers"],
+        "T": WL["T"], "horizon": WL["horizon"], "batch_per_gpu": B, "global_batch": B * (1 if reference else n_gpus),
         "parallelism": "cpu" if reference else f"dp{n_gpus}",
         "launch": "cuda-graph replay of the captured step" if graph else "eager (one C-ABI call per cell and direction)",
-        "l2": "inputs+activations exceed L2 (no flush needed)" if B >= 1024 else "working set may fit L2",
+        "l2": "inputs+activations exceed L2 (no flush needed)" if (B >= 1024 or WL is not SF) else "working set may fit L2",
         "bytes_model": "per-kernel compulsory bytes of the multi-kernel pipeline (DESIGN.md section 4); the fused-cell floor "
                        "of SURVEY 8d is 9.94 MB per sample fwd+bwd",
     }
@@ -235,24 +247,30 @@ def run_b200(args):
 
     B = args.batch
     torch.manual_seed(0)
-    stack = S.RecurrentStack(SF["N"], SF["C"], SF["Ks"], SF["Kc"], SF["Din"], SF["h"], SF["layers"], SF["horizon"]).to(dev)
+    stack = S.RecurrentStack(WL["N"], WL["C"], WL["Ks"], WL["Kc"], WL["Din"], WL["h"], WL["layers"], WL["horizon"]).to(dev)
     params = list(stack.parameters())
     Xh, yh, Gs_h, Gc_h = synthetic_inputs(B, seed=rank, pin=True)
-    Gs = Gs_h.to(dev).requires_grad_(True)
-    Gc = Gc_h.to(dev).requires_grad_(True)
+    if WL is SF:
+        Gs = Gs_h.to(dev).requires_grad_(True)
+        Gc = Gc_h.to(dev).requires_grad_(True)
+        leaves = params + [Gs, Gc]
+    else:   # constant supports (no dGs / dGc): 8-neighbour grid scaled by 1/8 as CSR
+        from stc_gnn_b200.synth import grid_csr
+        rp, ci, va = grid_csr(*WL["grid"])
+        Gs = S.CsrSupport(rp.to(dev), ci.to(dev), va.to(dev), WL["N"])
+        Gc = Gc_h.to(dev)
+        leaves = params
     X_res, y_res = Xh.to(dev), yh.to(dev)
     # data-parallel: one flat fp32 bucket (cell parameters + dGs + dGc), one NCCL all-reduce per step (dp.py)
-    bucket = S.dp.GradBucket(params + [Gs, Gc]) if world > 1 else None
+    bucket = S.dp.GradBucket(leaves) if world > 1 else None
 
     def allreduce_grads():
         if bucket is not None:
             bucket.allreduce()
 
     def step(X, y):
-        for p in params:
+        for p in leaves:
             p.grad = None
-        Gs.grad = None
-        Gc.grad = None
         out = stack(Gs, Gc, X)
         loss = loss_fn(out, y)
         loss.backward()
@@ -288,7 +306,7 @@ def run_b200(args):
         l0 = _lib.LAUNCHES
         step(X_res, y_res)
         per_step_launches = _lib.LAUNCHES - l0
-        graphed = S.GraphedStep(lambda X, y: loss_fn(stack(Gs, Gc, X), y), [X_res, y_res], params + [Gs, Gc],
+        graphed = S.GraphedStep(lambda X, y: loss_fn(stack(Gs, Gc, X), y), [X_res, y_res], leaves,
                                 warmup=max(args.warmup, 3))
         run_resident = lambda: graphed.replay(X_res, y_res)
     else:
@@ -347,7 +365,7 @@ def run_b200(args):
                             "convolutions, Din = 1 and Din = 16 cells); 3xTF32 tcgen05 kernel (see DESIGN.md section 4)"}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and WL is SF:
         v, ms, n, cores = cpu_port_throughput(args.cpu_batch, 40, 1, budget_s=15.0)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
                         "sample": f"{n} timed fwd+bwd steps of B={args.cpu_batch} windows of the same workload "
@@ -368,8 +386,18 @@ def run_b200(args):
 
 
 def main():
+    global WL, METRIC
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
+    if args.workload == "g4096":
+        WL = G4096
+        METRIC = "train samples/s (fwd+bwd), N=4096 C=16 F=64 STC encoder stack"
+        if args.batch == 4096:
+            args.batch = 4
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for the g4096 side workload"}), flush=True)
+            return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -26,7 +26,8 @@ class RecurrentStack(nn.Module):
                      activation=activation) for _ in range(num_layers))
 
     def forward(self, Gs, Gc: torch.Tensor, X_seq: torch.Tensor) -> torch.Tensor:
-        """X_seq [B,T,N,C,Din] -> decoder hidden states [B,horizon,N,C,h]."""
+        """X_seq [B,T,N,C,Din] -> decoder hidden states [B,horizon,N,C,h] (out_horizon = 0: the last encoder
+        layer's hidden states [B,T,N,C,h])."""
         assert X_seq.dim() == 5, "X_seq must be [B,T,N,C,Din]"
         B, T = X_seq.shape[0], X_seq.shape[1]
         # Layer l > 0 consumes layer l-1's per-step outputs directly: the reference stacks them and slices the stack
@@ -42,6 +43,8 @@ class RecurrentStack(nn.Module):
                 outs.append(Ht)
             seq = outs
             last.append(Ht)
+        if self.out_horizon == 0:   # encoder only (the large synthetic graphs drive STC_Encoder directly)
+            return torch.stack(seq, dim=1)
         states, x, outs = last, last[-1], []
         for _ in range(self.out_horizon):
             new_states, inp = [], x

@@ -113,7 +113,7 @@ def bench_config3():
     emit(kind="config3_cell_step", N=N, C=C, F=F, B=B, Ks=2, Kc=2, support="csr grid 8-neighbour", ms=ms,
          cell_step_samples_per_s=B / ms * 1e3, alg_bytes_train=alg, achieved_GBs=alg / ms / 1e6, peak_GBs=pk,
          frac_hbm=alg / ms / 1e6 / pk, gate_gemm_TFLOPs=flops / ms / 1e9, kernels=kernel_breakdown(step),
-         note="F=64 exceeds the 512 TMEM columns of the per-atom 3xTF32 accumulator scheme: gate contraction on the FFMA path")
+         note="gate contraction: wide-state tcgen05 kernels (stc_conv_tc_big.cu), 3xTF32; gate_gemm_TFLOPs counts useful FLOPs once")
 
 
 def bench_config4():

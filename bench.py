@@ -221,7 +221,7 @@ def workload_config(B, n_gpus, reference=False, graph=False):
         "launch": "cuda-graph replay of the captured step" if graph else "eager (one C-ABI call per cell and direction)",
         "l2": "inputs+activations exceed L2 (no flush needed)" if (B >= 1024 or WL is not SF) else "working set may fit L2",
         "bytes_model": "per-kernel compulsory bytes of the multi-kernel pipeline (DESIGN.md section 4); the fused-cell floor "
-                       "of SURVEY 8d is 9.94 MB per sample fwd+bwd",
+                       "of SURVEY 8d is " + ("9.94 MB" if WL is SF else "5.6 GB") + " per sample fwd+bwd",
     }
 
 
@@ -355,7 +355,7 @@ def run_b200(args):
         top = max(kinds.items(), key=lambda kv: kv[1][0])
         name, (kms, kn, kbytes) = top
         achieved = kbytes / (kms * 1e-3) / 1e9
-        traffic, traffic_src = measured_traffic(name)
+        traffic, traffic_src = measured_traffic(name) if (WL is SF and B == 4096) else (None, None)
         roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "avg_launch_us": 1e3 * kms / kn, "alg_bytes_per_launch": kbytes / kn,

@@ -113,6 +113,22 @@ def exchange(plan: HaloPlan, X_local: torch.Tensor, group: Optional[dist.Process
     return torch.cat([X_local, halo], dim=1).contiguous()
 
 
+def exchange_into(plan: HaloPlan, X_ext: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> None:
+    """In-place form of `exchange` on an extended tensor [B, nloc + nhalo, W]: only the boundary rows are packed and
+    only the halo rows are written (the local block is never copied)."""
+    B, next_, W = X_ext.shape
+    assert next_ == plan.next, (next_, plan.next)
+    if plan.nhalo == 0 and sum(plan.send_counts) == 0:
+        return
+    send_rows = [X_ext[:, idx.to(X_ext.device)].permute(1, 0, 2).reshape(-1, B * W) for idx in plan.send_idx]
+    send = torch.cat(send_rows, dim=0).contiguous() if send_rows else X_ext.new_empty(0, B * W)
+    recv = X_ext.new_empty(plan.nhalo, B * W)
+    if plan.world > 1:
+        dist.all_to_all_single(recv, send, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts,
+                               group=group)
+    X_ext[:, plan.nloc:] = recv.view(plan.nhalo, B, W).permute(1, 0, 2)
+
+
 class PartitionedSupport:
     """A constant CSR spatial support `Gs` [N, N] row-partitioned over `world` ranks.
 
@@ -181,6 +197,20 @@ class PartitionedSupport:
                               alpha=alpha, beta=beta, Z=Z_ext)
         return Y_ext[:, :plan.nloc].reshape(shape)
 
+    def hop_ext(self, X_ext: torch.Tensor, out_ext: torch.Tensor, Z_ext: Optional[torch.Tensor] = None,
+                alpha: float = 1.0, beta: float = 0.0, direction: str = "fwd") -> None:
+        """One hop on EXTENDED tensors [B, nloc + nhalo, ...] (CUDA): the halo rows of `X_ext` are refreshed in place
+        from their owners, then `out_ext = alpha * A X_ext + beta * Z_ext` with the local operator (square over the
+        extended index set, empty rows for the halo nodes -- their output rows are meaningless and get overwritten
+        by the next exchange).  No tensor is copied or sliced."""
+        from .support import support_apply
+        plan = self.fwd if direction == "fwd" else self.bwd
+        B = X_ext.shape[0]
+        exchange_into(plan, X_ext.view(B, plan.next, -1), self.group)
+        support_apply(self.device_support(direction, X_ext.device), X_ext.view(B, plan.next, -1),
+                      transpose=(direction == "fwd"), alpha=alpha, beta=beta,
+                      Z=None if Z_ext is None else Z_ext.view(B, plan.next, -1), out=out_ext.view(B, plan.next, -1))
+
     def spatial_terms(self, X_local: torch.Tensor, Ks: int, apply_fn=None) -> List[torch.Tensor]:
         """Feature-side Chebyshev terms Y_0..Y_{Ks-1} of this rank's block (Y_1 = Gs^T Y_0, Y_k = 2 Gs^T Y_{k-1} - Y_{k-2};
         `framework/STC_GNN.py:24-29` applied on the feature side): Ks-1 hops, one halo exchange each."""
@@ -215,31 +245,48 @@ def partitioned_cell_forward(ps: PartitionedSupport, Gc: torch.Tensor, Xt: torch
     h = Ht_1.shape[-1]
     if n != ps.nloc or Ht_1.shape != (B, n, C, h):
         raise RuntimeError(f"local block has {n} nodes, the partition owns {ps.nloc}; Ht_1 {tuple(Ht_1.shape)}")
-    Xt, Ht_1, Gc = Xt.contiguous(), Ht_1.contiguous(), Gc.contiguous()
+    # Everything lives in the EXTENDED node set [local | halo] of the forward plan: the node-local stages simply run
+    # over nloc + nhalo nodes (the halo rows, ~1 % at k = 8, are recomputed garbage that the next exchange overwrites),
+    # so the spatial terms are written straight into the `saved` regions the stages read -- no slicing, no compaction.
+    ne = ps.fwd.next
+    Gc = Gc.contiguous()
     Wg, Wc = Wg.contiguous(), Wc.contiguous()
-    dims = _lib.StcDims(B, n, C, Din, h, Ks, Kc, _activation_code(activation), 1 if bg is not None else 0)
+    Xe = Xt.new_zeros(B, ne, C, Din)
+    Xe[:, :n] = Xt
+    He = Ht_1.new_zeros(B, ne, C, h)
+    He[:, :n] = Ht_1
+    dims = _lib.StcDims(B, ne, C, Din, h, Ks, Kc, _activation_code(activation), 1 if bg is not None else 0)
     lay = _lib.saved_layout(dims)
     saved = torch.empty(lib.stc_cell_saved_bytes(dims) // 4, dtype=torch.float32, device=Xt.device)
-    Hn = torch.empty_like(Ht_1)
-    R = B * n * C
+    Hn = torch.empty_like(He)
+    R = B * ne * C
     stream = torch.cuda.current_stream().cuda_stream
 
     def region(name, k, width):
         o = lay[name] + k * R * width
-        return saved[o:o + R * width].view(B, n, C, width)
+        return saved[o:o + R * width].view(B, ne, C, width)
 
     def stage(which):
-        _lib.check(lib.stc_cell_fwd_stage(dims, which, Gc.data_ptr(), Xt.data_ptr(), n * C * Din, Ht_1.data_ptr(),
+        _lib.check(lib.stc_cell_fwd_stage(dims, which, Gc.data_ptr(), Xe.data_ptr(), ne * C * Din, He.data_ptr(),
                                           Wg.data_ptr(), _ptr(bg), Wc.data_ptr(), _ptr(bc), Hn.data_ptr(),
                                           saved.data_ptr(), saved.numel() * 4, stream), "stc_cell_fwd_stage")
         _lib.note_launches()
 
-    for k, y in enumerate(ps.spatial_terms(Xt, Ks)[1:]):
-        region("Yx", k, Din).copy_(y)
-    for k, y in enumerate(ps.spatial_terms(Ht_1, Ks)[1:]):
-        region("Yh", k, h).copy_(y)
+    def chain(term0, name, width, first):
+        """Y_1 = Gs^T Y_0, Y_k = 2 Gs^T Y_{k-1} - Y_{k-2} into regions `name`[first ...]."""
+        prev2, prev = None, term0
+        for k in range(1, Ks):
+            out = region(name, first + k - 1, width)
+            if k == 1:
+                ps.hop_ext(prev, out)
+            else:
+                ps.hop_ext(prev, out, Z_ext=prev2, alpha=2.0, beta=-1.0)
+            prev2, prev = prev, out
+
+    chain(Xe, "Yx", Din, 0)
+    chain(He, "Yh", h, 0)
     stage(_lib.STAGE_GATES)
-    for k, y in enumerate(ps.spatial_terms(region("Yr", 0, h), Ks)[1:]):
-        region("Yr", k + 1, h).copy_(y)
+    chain(region("Yr", 0, h), "Yr", h, 1)
     stage(_lib.STAGE_CANDI)
-    return Hn
+    return Hn[:, :n].contiguous()
+

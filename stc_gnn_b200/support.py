@@ -60,15 +60,21 @@ def dense_struct(G: torch.Tensor) -> _lib.StcSupport:
 
 
 def support_apply(Gs, X: torch.Tensor, transpose: bool = True, alpha: float = 1.0, beta: float = 0.0,
-                  Z: torch.Tensor = None) -> torch.Tensor:
-    """Y[b,m,...] = alpha * sum_n A(m,n) X[b,n,...] + beta * Z  with A = Gs^T (transpose) or Gs. CUDA only."""
+                  Z: torch.Tensor = None, out: torch.Tensor = None) -> torch.Tensor:
+    """Y[b,m,...] = alpha * sum_n A(m,n) X[b,n,...] + beta * Z  with A = Gs^T (transpose) or Gs. CUDA only.
+    `out` (contiguous, X's shape) receives the result in place of a fresh tensor."""
     lib = _lib.load()
     if not X.is_cuda or X.dtype != torch.float32:
         raise RuntimeError("support_apply needs a float32 CUDA tensor (there is no CPU path)")
     B, N = X.shape[0], X.shape[1]
     Xc = X.contiguous()
     width = Xc[0, 0].numel() if Xc.numel() else 0
-    Y = torch.empty_like(Xc)
+    if out is not None:
+        if out.shape != Xc.shape or not out.is_contiguous() or out.dtype != torch.float32 or out.device != Xc.device:
+            raise RuntimeError("support_apply: `out` must be a contiguous float32 tensor of X's shape on X's device")
+        Y = out
+    else:
+        Y = torch.empty_like(Xc)
     if isinstance(Gs, CsrSupport):
         st = Gs.struct()
         keep = Gs

@@ -68,6 +68,7 @@ SHAPES = [
     (5, 12, 8, 64, 64, 4, 2),     # Ks = 4 (kNN64K-like)
     (3, 40, 8, 1, 32, 2, 2),      # wide-state forward kernel: Din = 1 (partial last K chunk), h = 32
     (2, 21, 5, 20, 48, 3, 2),     # ... h = 48 (Hout 96 / 48), 3 spatial terms, ragged last tile
+    (1, 10, 64, 64, 64, 2, 2),    # LongC-like: C = 64 categories, F = 64 (two nodes per 128-row tile)
     (2, 9, 2, 3, 4, 1, 3),
     (4, 1, 1, 1, 1, 2, 2),        # degenerate sizes
 ]

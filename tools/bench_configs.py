@@ -137,6 +137,31 @@ def bench_config4():
          frac_hbm=alg / ms / 1e6 / pk, kernels=kernel_breakdown(step))
 
 
+def bench_config5():
+    """LongC-like cell step (BASELINE configs[4] shapes): N = 100 regions, C = 64 categories, F = 64, dense learned supports
+    (dGs, dGc required), forward + backward, B = 16."""
+    pk, src = peak()
+    N, C, F, B = 100, 64, 64, 16
+    Gs, _ = sf_supports()
+    Gs = Gs.to(DEV).requires_grad_(True)
+    Gc = torch.softmax(torch.randn(C, C, generator=torch.Generator().manual_seed(0)), dim=-1).to(DEV).requires_grad_(True)
+    cell = S.STC_Cell(N, C, 2, 2, F, F).to(DEV)
+    X = torch.randn(B, N, C, F, device=DEV, requires_grad=True)
+    H = (torch.randn(B, N, C, F, device=DEV) * 0.5).requires_grad_(True)
+    dH = torch.randn(B, N, C, F, device=DEV)
+
+    def step():
+        for p in list(cell.parameters()) + [Gs, Gc, X, H]:
+            p.grad = None
+        cell(Gs=Gs, Gc=Gc, Xt=X, Ht_1=H).backward(dH)
+
+    ms = timed(step, 5, warm=2)
+    alg = 4.0 * N * C * (3 * F + 11 * F) * B
+    emit(kind="config5_cell_step", N=N, C=C, F=F, B=B, Ks=2, Kc=2, support="dense learned (dGs, dGc)", ms=ms,
+         cell_step_samples_per_s=B / ms * 1e3, alg_bytes_train=alg, achieved_GBs=alg / ms / 1e6, peak_GBs=pk,
+         kernels=kernel_breakdown(step))
+
+
 def bench_sweep():
     import subprocess
     for B in (32, 64, 128, 256, 512, 1024, 2048, 4096):
@@ -160,7 +185,8 @@ if __name__ == "__main__":
     _lib.load()
     for w in which:
         try:
-            {"support": bench_support, "config3": bench_config3, "config4": bench_config4, "sweep": bench_sweep}[w]()
+            {"support": bench_support, "config3": bench_config3, "config4": bench_config4, "config5": bench_config5,
+             "sweep": bench_sweep}[w]()
         except Exception as e:  # keep going: each part is an independent measurement
             emit(kind=w, error=repr(e)[:600])
             torch.cuda.synchronize()

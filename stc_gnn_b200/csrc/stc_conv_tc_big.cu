@@ -394,6 +394,7 @@ struct BigDxPlan {
   int npt, Dp, KBL, KBLp;   // KBLp = KBL rounded up to 16: GEMM N per spatial term
   int nkc;                  // 32-wide K chunks = 2 Hout / 32
   int ntiles, DP, x_vec;
+  int stages;               // depth of the weight-chunk ring (3, or 2 when the Ds tile of a wide category axis needs the room)
   uint32_t stage_bytes;     // [hi: KBLp rows x 128 B | lo]
   uint32_t off_b, off_ds, off_q, off_qacc, off_bar, smem_bytes;
 };
@@ -435,7 +436,7 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
   float* Qs = reinterpret_cast<float*>(smem + p.off_q);         // [C][C] = T_1(Gc)
   float* dQacc = reinterpret_cast<float*>(smem + p.off_qacc);   // [C][C] per-CTA partial sums of dT_1(Gc)
   uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-  uint64_t* b_free = b_full + BG_STAGES;
+  uint64_t* b_free = b_full + BG_STAGES;   // (arrays sized for the deepest ring)
   uint64_t* a_free = b_free + BG_STAGES;
   uint64_t* acc_full = a_free + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -480,7 +481,7 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
   const uint32_t total_chunks = (uint32_t)my_tiles * per_tile;
   auto img_of = [&](uint32_t g) { return img + (size_t)(g % per_tile) * p.stage_bytes; };   // (k, kc) order = issue order
   if (warp_u == 1 && elect_one_sync()) {
-    for (uint32_t g = 0; g < (uint32_t)(BG_STAGES - 1) && g < total_chunks; ++g) {
+    for (uint32_t g = 0; g < (uint32_t)(p.stages - 1) && g < total_chunks; ++g) {
       mbar_arrive_expect_tx(&b_full[g], p.stage_bytes);
       bulk_g2s(Bring + (size_t)g * p.stage_bytes, img_of(g), p.stage_bytes, &b_full[g]);
     }
@@ -612,9 +613,9 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
         tmem_st_wait();
         fence_before_sync();
         __syncthreads();
-        const int st = (int)(g % (uint32_t)BG_STAGES);
+        const int st = (int)(g % (uint32_t)p.stages);
         if (warp_u == 0 && elect_one_sync()) {
-          mbar_wait(&b_full[st], (g / (uint32_t)BG_STAGES) & 1u);
+          mbar_wait(&b_full[st], (g / (uint32_t)p.stages) & 1u);
           fence_after_sync();
           const uint32_t a_hi0 = tmem_base + (uint32_t)(BG_ACOL + 64 * buf);
           const uint64_t dBh = make_smem_desc_sw128(smem_u32(Bring + (size_t)st * p.stage_bytes));
@@ -633,9 +634,9 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
           if (kc == p.nkc - 1) mma_commit(acc_full);
         }
         if (warp_u == 1 && elect_one_sync()) {
-          const uint32_t t = g + (uint32_t)(BG_STAGES - 1);
+          const uint32_t t = g + (uint32_t)(p.stages - 1);
           if (t < total_chunks) {
-            const uint32_t ts = t % (uint32_t)BG_STAGES, tu = t / (uint32_t)BG_STAGES;
+            const uint32_t ts = t % (uint32_t)p.stages, tu = t / (uint32_t)p.stages;
             if (tu >= 1u) mbar_wait(&b_free[ts], (tu - 1u) & 1u);
             mbar_arrive_expect_tx(&b_full[ts], p.stage_bytes);
             bulk_g2s(Bring + (size_t)ts * p.stage_bytes, img_of(t), p.stage_bytes, &b_full[ts]);
@@ -707,8 +708,8 @@ static bool big_dx_shape_ok(const ConvArgs& a) {
   if (!conv_big_shape_ok(a.C, a.Din, a.h, a.Ks, a.Kc, a.Hout)) return false;
   const int KBLp = (a.h + ((a.Din + 7) & ~7) + 15) & ~15;
   if (KBLp > 128) return false;
-  const size_t smem = (size_t)BG_STAGES * 2 * KBLp * ATOM_ROW_BYTES + (size_t)(128 + a.C) * (a.Hout + 4) * sizeof(float) +
-                      2 * (size_t)a.C * a.C * sizeof(float) + 2048;
+  const size_t smem = (size_t)2 * 2 * KBLp * ATOM_ROW_BYTES + (size_t)(128 + a.C) * (a.Hout + 4) * sizeof(float) +
+                      2 * (size_t)a.C * a.C * sizeof(float) + 2048;   // with the shallowest (2-stage) ring
   return smem <= 220 * 1024;
 }
 
@@ -741,8 +742,11 @@ int try_launch_conv_bwd_dx_big(const ConvArgs& a, cudaStream_t st, bool* handled
   const long long total_nodes = (long long)a.B * a.N;
   p.ntiles = ceil_div(total_nodes, p.npt);
   p.stage_bytes = (uint32_t)(2 * p.KBLp * ATOM_ROW_BYTES);
+  const size_t rest = round_up((size_t)(128 + a.C) * p.DP * sizeof(float), 16) +
+                      2 * round_up((size_t)a.C * a.C * sizeof(float), 16) + 8 * (2 * BG_STAGES + 3) + 16;
+  p.stages = ((size_t)BG_STAGES * p.stage_bytes + rest <= 226 * 1024) ? BG_STAGES : 2;
   size_t o = 0;
-  p.off_b = (uint32_t)o; o += (size_t)BG_STAGES * p.stage_bytes;
+  p.off_b = (uint32_t)o; o += (size_t)p.stages * p.stage_bytes;
   p.off_ds = (uint32_t)o; o += round_up((size_t)(128 + a.C) * p.DP * sizeof(float), 16);
   p.off_q = (uint32_t)o; o += round_up((size_t)a.C * a.C * sizeof(float), 16);
   p.off_qacc = (uint32_t)o; o += round_up((size_t)a.C * a.C * sizeof(float), 16);

@@ -578,17 +578,24 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
           const float4 x0 = *reinterpret_cast<const float4*>(Dsm + erow * DP + kk0);
           const float4 x1 = *reinterpret_cast<const float4*>(Dsm + erow * DP + kk0 + 4);
           av[0] = x0.x; av[1] = x0.y; av[2] = x0.z; av[3] = x0.w; av[4] = x1.x; av[5] = x1.y; av[6] = x1.z; av[7] = x1.w;
+        } else if (k > 0 && valid && a.dpre_ld >= 2 * Hout) {
+          // Dm_1 does not depend on the spatial term: this thread left these 8 values in dpre during term 0
+          const float4* dp = reinterpret_cast<const float4*>(a.dpre + gr * a.dpre_ld + kk0);
+          const float4 x0 = dp[0], x1 = dp[1];
+          av[0] = x0.x; av[1] = x0.y; av[2] = x0.z; av[3] = x0.w; av[4] = x1.x; av[5] = x1.y; av[6] = x1.z; av[7] = x1.w;
         } else {
           const float* spm = Dsm + (enode * C) * DP + (kk0 - Hout);
 #pragma unroll
           for (int i = 0; i < 8; ++i) av[i] = 0.f;
+          if (valid) {
 #pragma unroll 4
-          for (int d = 0; d < C; ++d) {
-            const float w = qrow[d];
-            const float4 x0 = *reinterpret_cast<const float4*>(spm + d * DP);
-            const float4 x1 = *reinterpret_cast<const float4*>(spm + d * DP + 4);
-            av[0] = fmaf(w, x0.x, av[0]); av[1] = fmaf(w, x0.y, av[1]); av[2] = fmaf(w, x0.z, av[2]); av[3] = fmaf(w, x0.w, av[3]);
-            av[4] = fmaf(w, x1.x, av[4]); av[5] = fmaf(w, x1.y, av[5]); av[6] = fmaf(w, x1.z, av[6]); av[7] = fmaf(w, x1.w, av[7]);
+            for (int d = 0; d < C; ++d) {
+              const float w = qrow[d];
+              const float4 x0 = *reinterpret_cast<const float4*>(spm + d * DP);
+              const float4 x1 = *reinterpret_cast<const float4*>(spm + d * DP + 4);
+              av[0] = fmaf(w, x0.x, av[0]); av[1] = fmaf(w, x0.y, av[1]); av[2] = fmaf(w, x0.z, av[2]); av[3] = fmaf(w, x0.w, av[3]);
+              av[4] = fmaf(w, x1.x, av[4]); av[5] = fmaf(w, x1.y, av[5]); av[6] = fmaf(w, x1.z, av[6]); av[7] = fmaf(w, x1.w, av[7]);
+            }
           }
         }
         if (k == 0 && kk0 >= Hout && valid && a.dpre_ld >= 2 * Hout) {   // the wide dW kernel contracts Y_k^T with [Ds | Dm_1]
@@ -783,7 +790,9 @@ int try_launch_conv_bwd_dx_big(const ConvArgs& a, cudaStream_t st, bool* handled
 // (bounded accumulation chains), one atomicAdd per element at the end.
 // =================================================================================================
 constexpr int BG_DW_CR = 32;       // rows per chunk (K extent of one image)
-constexpr int BG_DW_DRAIN = 32;    // chunks per accumulation chain: 64 K-steps into each main accumulator
+constexpr int BG_DW_DRAIN = 8;     // chunks per accumulation chain: 16 K-steps (128 rows) into each main accumulator.  The tensor core
+                                   // truncates when it adds into the accumulator, so the error grows with the chain: at 32 chunks one
+                                   // dWg element of the N = 4096 parity case sat at 3.0e-5 x mean|ref| against an allowance of 3e-5
 
 struct BigDwPlan {
   int Dp, KBL, N1, NH;             // N1 = 2 Hout, NH = 128-column slices of it

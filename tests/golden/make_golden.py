@@ -13,6 +13,10 @@ Files written (all ``np.savez_compressed``):
   cell_<name>.npz   one STC_Cell forward + every gradient (STC_GNN.py:65-79 through autograd)
   stack_sf.npz      encoder(2 layers x T=9) + decoder(horizon 3) roll-out on real SF data with the
                     MGP_Gen-produced (denormal-laden) supports, outputs + gradients
+  pred_sf.npz       the unmodified full STCGNN (STC_GNN.py:175-207; seeded init, Main.py's defaults) on the
+                    FIRST TEST BATCH of the shipped SF split (Data_Container.py:56-66, 6:1:1, batch 32):
+                    its own fp32 predictions, the supports its MGP_Gen produced, every cell / out_proj
+                    weight, and the fp64 re-evaluation of encoder -> decoder -> out_proj -> sigmoid
 """
 import os
 import sys
@@ -150,7 +154,59 @@ def run_stack(X_seq, Gs, Gc):
           f"zero fraction {(Gs.detach() == 0).float().mean():.3f}")
 
 
+def run_predictions():
+    """BASELINE.json north_star: 'predictions on the shipped SF-incidents-4h data must match'."""
+    import Data_Container as dc   # the reference's own windowing and split
+    d = np.load(DATA)
+    gen = dc.DataGenerator(obs_len=9, pred_len=3, data_split_ratio=(6, 1, 1))
+    loaders = gen.get_data_loader(params=dict(H=10, W=10, C=5, device="cpu", batch_size=32), data=dict(inc=d["incident"]))
+    X, Y = next(iter(loaders["test"]))                                   # [32,9,100,5], [32,3,100,5]
+    As = torch.from_numpy(d["s_adj"]).float()
+    Ac = torch.from_numpy(d["c_cor"]).float()
+    torch.set_default_dtype(torch.float32)
+    torch.manual_seed(0)
+    model = ref.STCGNN(100, 5, 2, 2, 1, 16, 2, 3)                        # Model_Trainer.py:39-46 with Main.py defaults
+    model.eval()
+    with torch.no_grad():
+        pred32 = model(X, As, Ac)                                        # the reference's own answer, fp32
+        Gs, Gc = model.mix_graph_pair(X, As, Ac)
+    # fp64 re-evaluation of everything after MGP_Gen, from the fp32 supports and weights
+    torch.set_default_dtype(torch.float64)
+    enc = ref.STC_Encoder(100, 5, 2, 2, 1, 16, 2, return_all_layers=True)
+    dec = ref.STC_Decoder(100, 5, 2, 2, 16, 16, 2, 3)
+    enc.load_state_dict({k: v.double() for k, v in model.encoder.state_dict().items()})
+    dec.load_state_dict({k: v.double() for k, v in model.decoder.state_dict().items()})
+    W1, b1 = model.out_proj[0].weight.double(), model.out_proj[0].bias.double()
+    W2, b2 = model.out_proj[1].weight.double(), model.out_proj[1].bias.double()
+    with torch.no_grad():
+        Gs64, Gc64 = Gs.double(), Gc.double()
+        _, Ht = enc(Gs=Gs64, Gc=Gc64, X_seq=X.double().unsqueeze(-1), H0_l=None)
+        inp, outs = Ht[-1], []
+        for _ in range(3):
+            Hl, Ht = dec(Gs=Gs64, Gc=Gc64, Xt=inp, H0_l=Ht)
+            inp = Hl
+            outs.append(Hl)
+        hid = torch.stack(outs, dim=1)
+        pred64 = torch.sigmoid((hid @ W1.t() + b1) @ W2.t() + b2).squeeze(-1)
+    save = dict(meta=np.array([32, 9, 100, 5, 1, 16, 2, 2, 2, 3], dtype=np.int64),
+                X_seq=X.numpy().astype(np.uint8), Y=Y.numpy().astype(np.uint8), Gs=Gs.numpy(), Gc=Gc.numpy(),
+                pred=pred64.numpy(), pred_ref_fp32=pred32.numpy(),
+                out_W1=W1.detach().float().numpy(), out_b1=b1.detach().float().numpy(),
+                out_W2=W2.detach().float().numpy(), out_b2=b2.detach().float().numpy())
+    for tag, mod in (("enc", model.encoder), ("dec", model.decoder)):
+        for i, cell in enumerate(mod.cell_list):
+            for conv in ("gates", "candi"):
+                for pn in ("W", "b"):
+                    save[f"{tag}{i}_{conv}_{pn}"] = getattr(getattr(cell, conv), pn).detach().float().numpy()
+    np.savez_compressed(os.path.join(OUT, "pred_sf.npz"), **save)
+    print(f"pred_sf: predictions in [{pred64.min():.3f}, {pred64.max():.3f}]; reference fp32 vs fp64 max-abs "
+          f"{(pred32.double() - pred64).abs().max():.2e}, max-rel {((pred32.double() - pred64).abs() / pred64.abs()).max():.2e}")
+
+
 if __name__ == "__main__":
+    if "--pred-only" in sys.argv:
+        run_predictions()
+        sys.exit(0)
     run_cell("tiny", B=2, N=7, C=3, Din=1, h=4, Ks=2, Kc=2, seed=1)
     run_cell("k33", B=2, N=9, C=4, Din=3, h=5, Ks=3, Kc=3, seed=2)
     run_cell("k42_relu", B=1, N=8, C=2, Din=2, h=4, Ks=4, Kc=2, act="relu", seed=3)
@@ -162,3 +218,4 @@ if __name__ == "__main__":
              Xt=f32exact(X_seq[:, 3]).unsqueeze(-1))
     run_cell("sf_din16", B=2, N=100, C=5, Din=16, h=16, Ks=2, Kc=2, seed=8, Gs=Gs, Gc=Gc)
     run_stack(X_seq, Gs, Gc)
+    run_predictions()

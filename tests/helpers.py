@@ -28,6 +28,16 @@ def load_stack():
     return cfg, t
 
 
+def load_pred():
+    """Full-model predictions of the unmodified reference on the first SF test batch (tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(GOLDEN, "pred_sf.npz"))
+    B, T, N, C, Din, h, Ks, Kc, layers, horizon = (int(v) for v in z["meta"])
+    cfg = dict(B=B, T=T, N=N, C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, layers=layers, horizon=horizon)
+    t = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    t["X_seq"] = t["X_seq"].float().unsqueeze(-1)      # stored as uint8 incident flags [B,T,N,C]
+    return cfg, t
+
+
 def random_case(B, N, C, Din, h, Ks, Kc, seed=0, use_bias=True, sparse_frac=None, dtype=torch.float64):
     """Seeded inputs with fp32-exact values. ``sparse_frac`` zeroes that fraction of Gs (for CSR tests)."""
     g = torch.Generator().manual_seed(seed)

@@ -9,7 +9,7 @@ import torch
 
 import stc_gnn_b200 as S
 from oracle import stc_oracle as O
-from tests.helpers import CELL_CASES, GRAD_KEYS, load_cell, load_stack, oracle_cell_with_grads, random_case
+from tests.helpers import CELL_CASES, GRAD_KEYS, load_cell, load_pred, load_stack, oracle_cell_with_grads, random_case
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -154,6 +154,26 @@ def test_stack_matches_reference_golden():
                 for pn in ("W", "b"):
                     chk(getattr(getattr(cell, conv), pn).grad.cpu(), t[f"d_{tag}{i}_{conv}_{pn}"], f"{tag}{i}.{conv}.{pn}")
     assert not bad, "; ".join(bad)
+
+
+def test_predictions_on_shipped_sf_test_batch():
+    """BASELINE.json north_star: predictions on the shipped SF-incidents-4h data match to rtol 1e-4 (no atol).
+    Golden = the unmodified reference STCGNN (seeded init) on the first test batch of its own 6:1:1 split; the B200
+    cells replace encoder + decoder, out_proj + sigmoid (STC_GNN.py:206) are evaluated around them as the reference does."""
+    cfg, t = load_pred()
+    stack = S.RecurrentStack(cfg["N"], cfg["C"], cfg["Ks"], cfg["Kc"], cfg["Din"], cfg["h"], cfg["layers"],
+                             cfg["horizon"]).to(DEV)
+    with torch.no_grad():
+        for tag, mods in (("enc", stack.encoder), ("dec", stack.decoder)):
+            for i, cell in enumerate(mods):
+                for conv in ("gates", "candi"):
+                    for pn in ("W", "b"):
+                        getattr(getattr(cell, conv), pn).copy_(t[f"{tag}{i}_{conv}_{pn}"])
+        hid = stack(t["Gs"].to(DEV), t["Gc"].to(DEV), t["X_seq"].to(DEV))
+        pred = torch.sigmoid(torch.nn.functional.linear(torch.nn.functional.linear(
+            hid, t["out_W1"].to(DEV), t["out_b1"].to(DEV)), t["out_W2"].to(DEV), t["out_b2"].to(DEV))).squeeze(-1)
+    O.assert_close(pred.cpu(), t["pred"], "SF predictions vs fp64 reference", rtol=1e-4, atol_scale=0.0)
+    O.assert_close(pred.cpu(), t["pred_ref_fp32"], "SF predictions vs the reference's own fp32 output", rtol=1e-4, atol_scale=0.0)
 
 
 @pytest.mark.parametrize("kind", ["dense", "csr"])

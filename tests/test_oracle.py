@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import stc_oracle as O
-from tests.helpers import CELL_CASES, GRAD_KEYS, load_cell, load_stack, oracle_cell_with_grads, random_case
+from tests.helpers import CELL_CASES, GRAD_KEYS, load_cell, load_pred, load_stack, oracle_cell_with_grads, random_case
 
 REF_DIR = os.environ.get("STC_REF_DIR", "/root/reference/framework")
 
@@ -92,6 +92,22 @@ def test_stack_matches_golden():
     O.assert_close(X.grad, t["dX_seq"], "dX_seq", rtol=1e-8, atol_scale=1e-9)
     for k, v in leaves.items():
         O.assert_close(v.grad, t["d_" + k], k, rtol=1e-8, atol_scale=1e-9)
+
+
+def test_predictions_on_shipped_sf_test_batch_match_golden():
+    """Encoder -> decoder -> out_proj -> sigmoid (STC_GNN.py:191-207) on the first SF test batch, fp64 oracle vs the
+    fp64 evaluation of the reference's own modules; the reference's native fp32 answer must sit inside rtol 1e-4."""
+    cfg, t = load_pred()
+    enc, dec = [], []
+    for tag, lst in (("enc", enc), ("dec", dec)):
+        for i in range(cfg["layers"]):
+            lst.append(O.CellParams(*[t[f"{tag}{i}_{conv}_{pn}"].double() for conv in ("gates", "candi") for pn in ("W", "b")]))
+    hid = O.stack_forward(t["Gs"].double(), t["Gc"].double(), t["X_seq"].double(), enc, dec, cfg["horizon"], cfg["Ks"], cfg["Kc"])
+    pred = torch.sigmoid((hid @ t["out_W1"].double().t() + t["out_b1"].double()) @ t["out_W2"].double().t()
+                         + t["out_b2"].double()).squeeze(-1)
+    assert pred.shape == t["pred"].shape == (32, 3, 100, 5)
+    O.assert_close(pred, t["pred"], "SF predictions", rtol=1e-9, atol_scale=0.0)
+    O.assert_close(t["pred_ref_fp32"], t["pred"], "reference fp32 predictions", rtol=1e-4, atol_scale=0.0)
 
 
 def test_grid_adjacency_matches_shipped_shape():

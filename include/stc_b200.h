@@ -130,6 +130,29 @@ int stc_cell_bwd(const StcDims* d, const StcSupport* gs, const float* gc,
                  int32_t accumulate_params, const void* saved, size_t saved_bytes,
                  void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- the backward split the same way (gradients through a row-partitioned graph) ----
+ * Order: stage STC_STAGE_CANDI first, then STC_STAGE_GATES (the reverse of the forward).
+ *   1. STC_STAGE_CANDI: clears the parameter and Gc gradients unless accumulate_params, runs the candidate-conv adjoint.  Leaves
+ *      d(r*H spatial terms) in region STC_SCRATCH_DYR of `scratch` (Ks terms, [B][N][C][h] each), the x-part adjoint
+ *      of term 0 in d_xt and of terms 1..Ks-1 in region STC_SCRATCH_DYX.
+ *   2. the caller folds terms Ks-1..1 of STC_SCRATCH_DYR into term 0 with the adjoint hops
+ *      (ybar[k-1] += (k >= 2 ? 2 : 1) Gs ybar[k], ybar[k-2] -= ybar[k]; stc_support_apply with transpose = 0 + its exchange),
+ *   3. STC_STAGE_GATES: GRU adjoint + gates-conv adjoint (reads term 0 of STC_SCRATCH_DYR as d(r*H)); adds its x-part
+ *      adjoints to d_xt / STC_SCRATCH_DYX, writes the h-part adjoints to d_h_prev / STC_SCRATCH_DYH (Ks-1 terms),
+ *      finishes dGc,
+ *   4. the caller folds STC_SCRATCH_DYX into d_xt and STC_SCRATCH_DYH into d_h_prev the same way.
+ * Rows whose d_h_out and STC_SCRATCH_DYR term-0 entries are zero contribute nothing to any parameter gradient (that
+ * is how the halo rows of an extended node set are kept out of dW).  A constant (CSR) support has no dGs.      */
+enum { STC_SCRATCH_DYR = 0, STC_SCRATCH_DYX, STC_SCRATCH_DYH, STC_SCRATCH_REGIONS };
+int stc_cell_bwd_scratch_layout(const StcDims* d, int64_t* offsets_floats, int32_t n_offsets);
+int stc_cell_bwd_stage(const StcDims* d, int32_t stage, const float* gc,
+                       const float* xt, int64_t xt_batch_stride, const float* h_prev,
+                       const float* Wg, const float* Wc, const float* d_h_out,
+                       float* d_xt, float* d_h_prev,
+                       float* dWg, float* dbg, float* dWc, float* dbc, float* dGc,
+                       int32_t accumulate_params, const void* saved, size_t saved_bytes,
+                       void* scratch, size_t scratch_bytes, void* stream);
+
 /* Y[b,m,:] = alpha * sum_n A(m,n) X[b,n,:] + beta * Z[b,m,:]  with A = Gs^T (transpose != 0, the
  * forward mode product of STC_GNN.py:37) or A = Gs.  X,Z,Y: [B][N][width]; X and Z may carry a batch
  * stride (elements), Y is contiguous; Z may be NULL when beta == 0; Y may alias Z.  Exposed because it

@@ -20,9 +20,11 @@ EXPORTED = (
     "stc_cell_fwd", "stc_cell_bwd", "stc_support_apply", "stc_last_launch_count",
     "stc_timing_enable", "stc_timing_collect", "stc_kernel_kind_name", "stc_tf32x3_gemm",
     "stc_cell_saved_layout", "stc_cell_fwd_stage", "stc_debug_trace_set",
+    "stc_cell_bwd_scratch_layout", "stc_cell_bwd_stage",
 )
 STAGE_GATES, STAGE_CANDI = 0, 1
 SAVED_REGIONS = ("u", "r", "c", "Yr", "Yx", "Yh", "Q", "Pg", "Pc")
+SCRATCH_REGIONS = ("dYr", "dYx", "dYh")
 
 
 class StcDims(Structure):
@@ -68,6 +70,12 @@ def load(build_if_missing: bool = True):
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_void_p, c_size_t,
                                  c_void_p]
+    lib.stc_cell_bwd_scratch_layout.restype = c_int
+    lib.stc_cell_bwd_scratch_layout.argtypes = [POINTER(StcDims), POINTER(c_int64), c_int32]
+    lib.stc_cell_bwd_stage.restype = c_int
+    lib.stc_cell_bwd_stage.argtypes = [POINTER(StcDims), c_int32, c_void_p, c_void_p, c_int64, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]
     lib.stc_support_apply.restype = c_int
     lib.stc_support_apply.argtypes = [POINTER(StcSupport), c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
                                       c_void_p, c_int64, c_void_p, c_float, c_float, c_void_p]
@@ -93,6 +101,14 @@ def saved_layout(dims: StcDims) -> dict:
     offs = (c_int64 * len(SAVED_REGIONS))()
     check(lib.stc_cell_saved_layout(dims, offs, len(SAVED_REGIONS)), "stc_cell_saved_layout")
     return {n: int(offs[i]) for i, n in enumerate(SAVED_REGIONS)}
+
+
+def scratch_layout(dims: StcDims) -> dict:
+    """{region name: offset in floats} of the adjoint regions of the backward `scratch` buffer."""
+    lib = load()
+    offs = (c_int64 * len(SCRATCH_REGIONS))()
+    check(lib.stc_cell_bwd_scratch_layout(dims, offs, len(SCRATCH_REGIONS)), "stc_cell_bwd_scratch_layout")
+    return {n: int(offs[i]) for i, n in enumerate(SCRATCH_REGIONS)}
 
 
 def check(status: int, what: str) -> None:

@@ -464,24 +464,38 @@ static int adjoint_chain(const StcDims& d, const StcSupport& gs, int width, cons
   return STC_OK;
 }
 
-int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
-                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* Wc,
-                 const float* d_h_out, float* d_xt, float* d_h_prev, float* dWg, float* dbg, float* dWc, float* dbc,
-                 float* dGs, float* dGc, int32_t accumulate_params, const void* savedv, size_t saved_bytes,
-                 void* scratchv, size_t scratch_bytes, void* stream) {
-  reset_launch_count();
+// ---- backward pieces (stc_cell_bwd runs all of them; the row-partitioned path runs the two node-local stages and
+//      does the adjoint spatial hops itself, with a halo exchange before each) ----
+struct BwdCtx {
+  const StcDims& d;
+  const WsLayout& w;
+  const float* gc;
+  const float* xt;
+  int64_t xt_bs;
+  const float* h_prev;
+  const float* d_h_out;
+  float* d_xt;        // may be NULL: the x-part adjoint then lives in scratch
+  float* d_h_prev;
+  float* dGc;
+  float* sv;          // saved (read-only here)
+  float* sc;          // scratch
+  cudaStream_t st;
+  bool want_dGc() const { return dGc != nullptr && d.Kc > 1; }
+  float* dYx0() const { return d_xt ? d_xt : sc + w.dYx0; }
+};
+
+static int check_bwd_args(const StcDims* dp, const float* gc, const float* xt, const float* h_prev, const float* Wg,
+                          const float* Wc, const float* d_h_out, float* d_h_prev, float* dWg, float* dbg, float* dWc,
+                          float* dbc, const void* savedv, size_t saved_bytes, void* scratchv, size_t scratch_bytes,
+                          const char* who) {
   STC_TRY(check_dims(dp));
   const StcDims& d = *dp;
-  if (!gs || !gc || !xt || !h_prev || !Wg || !Wc || !d_h_out || !d_h_prev || !dWg || !dWc || !savedv || !scratchv) {
-    set_error("stc_cell_bwd: NULL argument");
+  if (!gc || !xt || !h_prev || !Wg || !Wc || !d_h_out || !d_h_prev || !dWg || !dWc || !savedv || !scratchv) {
+    set_error("%s: NULL argument", who);
     return STC_ERR_BAD_ARG;
   }
   if (d.has_bias && (!dbg || !dbc)) {
-    set_error("stc_cell_bwd: has_bias set but a bias-gradient pointer is NULL");
-    return STC_ERR_BAD_ARG;
-  }
-  if (dGs && gs->kind != STC_SUPPORT_DENSE) {
-    set_error("stc_cell_bwd: dGs is only defined for a dense support");
+    set_error("%s: has_bias set but a bias-gradient pointer is NULL", who);
     return STC_ERR_BAD_ARG;
   }
   const WsLayout w = make_layout(d);
@@ -490,86 +504,161 @@ int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
               w.saved_total * sizeof(float), scratch_bytes, w.scratch_total * sizeof(float));
     return STC_ERR_WORKSPACE;
   }
+  return STC_OK;
+}
+
+// zero the parameter / support gradients unless the caller accumulates over a time loop; zero the dT_k(Gc) partials
+static int bwd_begin(const BwdCtx& b, float* dWg, float* dbg, float* dWc, float* dbc, float* dGs, int accumulate_params) {
+  const StcDims& d = b.d;
+  const int L = d.Din + d.h, P = d.Ks * d.Kc;
+  if (!accumulate_params) {
+    STC_CUDA_OK(cudaMemsetAsync(dWg, 0, sizeof(float) * P * L * 2 * d.h, b.st));
+    STC_CUDA_OK(cudaMemsetAsync(dWc, 0, sizeof(float) * P * L * d.h, b.st));
+    if (d.has_bias) {
+      STC_CUDA_OK(cudaMemsetAsync(dbg, 0, sizeof(float) * 2 * d.h, b.st));
+      STC_CUDA_OK(cudaMemsetAsync(dbc, 0, sizeof(float) * d.h, b.st));
+    }
+    if (dGs) STC_CUDA_OK(cudaMemsetAsync(dGs, 0, sizeof(float) * d.N * d.N, b.st));
+    if (b.dGc) STC_CUDA_OK(cudaMemsetAsync(b.dGc, 0, sizeof(float) * d.C * d.C, b.st));
+  }
+  if (d.B > 0 && b.want_dGc()) STC_CUDA_OK(cudaMemsetAsync(b.sc + b.w.dQ, 0, sizeof(float) * d.Kc * d.C * d.C, b.st));
+  return STC_OK;
+}
+
+// candidate conv adjoint: leaves d(r*H terms) in scratch dYr[0..Ks-1], the x-part adjoint in dYx0 / scratch dYx
+static int bwd_candi(const BwdCtx& b, const float* Wc, float* dWc, float* dbc) {
+  const StcDims& d = b.d;
+  const WsLayout& w = b.w;
+  const size_t Rh = w.R * d.h;
+  ConvArgs a = base_args(d, b.xt, b.xt_bs, Wc, b.sv + w.Q, b.sv, w, 1);
+  a.h0 = b.sv + w.Yr;
+  a.yh = b.sv + w.Yr + Rh;
+  a.Hprev = b.h_prev;
+  a.u = b.sv + w.u;
+  a.c = b.sv + w.c;
+  a.dHn = b.d_h_out;
+  a.dpre = b.sc + w.dpre;
+  a.dbias = d.has_bias ? dbc : nullptr;
+  a.dYx0 = b.dYx0();
+  a.dYx = b.sc + w.dYx;
+  a.accum_x = 0;
+  a.dYh0 = b.sc + w.dYr;
+  a.dYh = b.sc + w.dYr + Rh;
+  a.dQ = b.want_dGc() ? b.sc + w.dQ : nullptr;
+  a.dW = dWc;
+  a.Psave = b.sv + w.Pc;
+  a.Wimg = (w.saved_total > w.Wimg_c && w.scratch_total > w.Wimg_dx) ? b.sc + w.Wimg_dx : nullptr;   // wide forward ran
+  STC_TRY(launch_conv_bwd_dx(a, b.st));
+  return launch_conv_bwd_dw(a, b.st);
+}
+
+// GRU elementwise adjoint + gates conv adjoint (reads d(r*H) = scratch dYr[0]); then dGc from the dT_k(Gc) partials
+static int bwd_gates(const BwdCtx& b, const float* Wg, float* dWg, float* dbg) {
+  const StcDims& d = b.d;
+  const WsLayout& w = b.w;
+  ConvArgs a = base_args(d, b.xt, b.xt_bs, Wg, b.sv + w.Q, b.sv, w, 0);
+  a.h0 = b.h_prev;
+  a.yh = b.sv + w.Yh;
+  a.Hprev = b.h_prev;
+  a.u = b.sv + w.u;
+  a.r = b.sv + w.r;
+  a.c = b.sv + w.c;
+  a.dHn = b.d_h_out;
+  a.drH = b.sc + w.dYr;
+  a.dpre = b.sc + w.dpre;
+  a.dbias = d.has_bias ? dbg : nullptr;
+  a.dYx0 = b.dYx0();
+  a.dYx = b.sc + w.dYx;
+  a.accum_x = 1;
+  a.dYh0 = b.d_h_prev;
+  a.dYh = b.sc + w.dYh;
+  a.dQ = b.want_dGc() ? b.sc + w.dQ : nullptr;
+  a.dW = dWg;
+  a.Psave = b.sv + w.Pg;
+  a.Wimg = (w.Wimg_c > w.Wimg_g && w.scratch_total > w.Wimg_dx) ? b.sc + w.Wimg_dx : nullptr;   // wide forward ran
+  STC_TRY(launch_conv_bwd_dx(a, b.st));
+  STC_TRY(launch_conv_bwd_dw(a, b.st));
+  if (b.want_dGc()) STC_TRY(launch_cheby_small_bwd(b.gc, b.sv + w.Q, b.sc + w.dQ, d.C, d.Kc, b.dGc, b.st));
+  return STC_OK;
+}
+
+int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* Wc,
+                 const float* d_h_out, float* d_xt, float* d_h_prev, float* dWg, float* dbg, float* dWc, float* dbc,
+                 float* dGs, float* dGc, int32_t accumulate_params, const void* savedv, size_t saved_bytes,
+                 void* scratchv, size_t scratch_bytes, void* stream) {
+  reset_launch_count();
+  STC_TRY(check_bwd_args(dp, gc, xt, h_prev, Wg, Wc, d_h_out, d_h_prev, dWg, dbg, dWc, dbc, savedv, saved_bytes, scratchv,
+                         scratch_bytes, "stc_cell_bwd"));
+  const StcDims& d = *dp;
+  if (!gs) {
+    set_error("stc_cell_bwd: NULL argument");
+    return STC_ERR_BAD_ARG;
+  }
+  if (dGs && gs->kind != STC_SUPPORT_DENSE) {
+    set_error("stc_cell_bwd: dGs is only defined for a dense support");
+    return STC_ERR_BAD_ARG;
+  }
+  const WsLayout w = make_layout(d);
   STC_TRY(check_arch());
   cudaStream_t st = (cudaStream_t)stream;
-  float* sv = const_cast<float*>((const float*)savedv);  // read-only here
-  float* sc = (float*)scratchv;
-  const int L = d.Din + d.h, P = d.Ks * d.Kc;
+  const BwdCtx b{d, w, gc, xt, xt_batch_stride, h_prev, d_h_out, d_xt, d_h_prev, dGc,
+                 const_cast<float*>((const float*)savedv), (float*)scratchv, st};
+  STC_TRY(bwd_begin(b, dWg, dbg, dWc, dbc, dGs, accumulate_params));
+  if (d.B == 0) return STC_OK;
   const size_t Rh = w.R * d.h;
   const int CD = d.C * d.Din, CH = d.C * d.h;
-  const bool want_dGc = dGc != nullptr && d.Kc > 1;
 
-  if (!accumulate_params) {
-    STC_CUDA_OK(cudaMemsetAsync(dWg, 0, sizeof(float) * P * L * 2 * d.h, st));
-    STC_CUDA_OK(cudaMemsetAsync(dWc, 0, sizeof(float) * P * L * d.h, st));
-    if (d.has_bias) {
-      STC_CUDA_OK(cudaMemsetAsync(dbg, 0, sizeof(float) * 2 * d.h, st));
-      STC_CUDA_OK(cudaMemsetAsync(dbc, 0, sizeof(float) * d.h, st));
-    }
-    if (dGs) STC_CUDA_OK(cudaMemsetAsync(dGs, 0, sizeof(float) * d.N * d.N, st));
-    if (dGc) STC_CUDA_OK(cudaMemsetAsync(dGc, 0, sizeof(float) * d.C * d.C, st));
+  STC_TRY(bwd_candi(b, Wc, dWc, dbc));
+  // d(rH) through the spatial recurrence
+  STC_TRY(adjoint_chain(d, *gs, CH, b.sv + w.Yr, (int64_t)d.N * CH, b.sv + w.Yr + Rh, b.sc + w.dYr, b.sc + w.dYr + Rh,
+                        dGs, st));
+  STC_TRY(bwd_gates(b, Wg, dWg, dbg));
+  STC_TRY(adjoint_chain(d, *gs, CD, xt, xt_batch_stride, b.sv + w.Yx, b.dYx0(), b.sc + w.dYx, dGs, st));
+  STC_TRY(adjoint_chain(d, *gs, CH, h_prev, (int64_t)d.N * CH, b.sv + w.Yh, d_h_prev, b.sc + w.dYh, dGs, st));
+  return STC_OK;
+}
+
+int stc_cell_bwd_scratch_layout(const StcDims* dp, int64_t* offsets, int32_t n_offsets) {
+  STC_TRY(check_dims(dp));
+  if (!offsets || n_offsets < STC_SCRATCH_REGIONS) {
+    set_error("stc_cell_bwd_scratch_layout: need room for %d offsets", (int)STC_SCRATCH_REGIONS);
+    return STC_ERR_BAD_ARG;
+  }
+  const WsLayout w = make_layout(*dp);
+  const size_t v[STC_SCRATCH_REGIONS] = {w.dYr, w.dYx, w.dYh};
+  for (int i = 0; i < STC_SCRATCH_REGIONS; ++i) offsets[i] = (int64_t)v[i];
+  return STC_OK;
+}
+
+int stc_cell_bwd_stage(const StcDims* dp, int32_t stage, const float* gc, const float* xt, int64_t xt_batch_stride,
+                       const float* h_prev, const float* Wg, const float* Wc, const float* d_h_out, float* d_xt,
+                       float* d_h_prev, float* dWg, float* dbg, float* dWc, float* dbc, float* dGc,
+                       int32_t accumulate_params, const void* savedv, size_t saved_bytes, void* scratchv,
+                       size_t scratch_bytes, void* stream) {
+  reset_launch_count();
+  STC_TRY(check_bwd_args(dp, gc, xt, h_prev, Wg, Wc, d_h_out, d_h_prev, dWg, dbg, dWc, dbc, savedv, saved_bytes, scratchv,
+                         scratch_bytes, "stc_cell_bwd_stage"));
+  if (stage != STC_STAGE_GATES && stage != STC_STAGE_CANDI) {
+    set_error("stc_cell_bwd_stage: bad stage %d", stage);
+    return STC_ERR_BAD_ARG;
+  }
+  if (!d_xt) {
+    set_error("stc_cell_bwd_stage: d_xt must be given (the caller runs the adjoint hops on it)");
+    return STC_ERR_BAD_ARG;
+  }
+  const StcDims& d = *dp;
+  const WsLayout w = make_layout(d);
+  STC_TRY(check_arch());
+  const BwdCtx b{d, w, gc, xt, xt_batch_stride, h_prev, d_h_out, d_xt, d_h_prev, dGc,
+                 const_cast<float*>((const float*)savedv), (float*)scratchv, (cudaStream_t)stream};
+  if (stage == STC_STAGE_CANDI) {   // the first backward stage: also clears the gradients it and the gates stage add into
+    STC_TRY(bwd_begin(b, dWg, dbg, dWc, dbc, nullptr, accumulate_params));
+    if (d.B == 0) return STC_OK;
+    return bwd_candi(b, Wc, dWc, dbc);
   }
   if (d.B == 0) return STC_OK;
-  if (want_dGc) STC_CUDA_OK(cudaMemsetAsync(sc + w.dQ, 0, sizeof(float) * d.Kc * d.C * d.C, st));
-
-  float* dYx0 = d_xt ? d_xt : sc + w.dYx0;
-
-  // ---- candidate conv adjoint ----
-  {
-    ConvArgs a = base_args(d, xt, xt_batch_stride, Wc, sv + w.Q, sv, w, 1);
-    a.h0 = sv + w.Yr;
-    a.yh = sv + w.Yr + Rh;
-    a.Hprev = h_prev;
-    a.u = sv + w.u;
-    a.c = sv + w.c;
-    a.dHn = d_h_out;
-    a.dpre = sc + w.dpre;
-    a.dbias = d.has_bias ? dbc : nullptr;
-    a.dYx0 = dYx0;
-    a.dYx = sc + w.dYx;
-    a.accum_x = 0;
-    a.dYh0 = sc + w.dYr;
-    a.dYh = sc + w.dYr + Rh;
-    a.dQ = want_dGc ? sc + w.dQ : nullptr;
-    a.dW = dWc;
-    a.Psave = sv + w.Pc;
-    a.Wimg = (w.saved_total > w.Wimg_c && w.scratch_total > w.Wimg_dx) ? sc + w.Wimg_dx : nullptr;   // wide forward ran
-    STC_TRY(launch_conv_bwd_dx(a, st));
-    STC_TRY(launch_conv_bwd_dw(a, st));
-  }
-  // d(rH) through the spatial recurrence
-  STC_TRY(adjoint_chain(d, *gs, CH, sv + w.Yr, (int64_t)d.N * CH, sv + w.Yr + Rh, sc + w.dYr, sc + w.dYr + Rh, dGs, st));
-
-  // ---- GRU elementwise adjoint + gates conv adjoint ----
-  {
-    ConvArgs a = base_args(d, xt, xt_batch_stride, Wg, sv + w.Q, sv, w, 0);
-    a.h0 = h_prev;
-    a.yh = sv + w.Yh;
-    a.Hprev = h_prev;
-    a.u = sv + w.u;
-    a.r = sv + w.r;
-    a.c = sv + w.c;
-    a.dHn = d_h_out;
-    a.drH = sc + w.dYr;
-    a.dpre = sc + w.dpre;
-    a.dbias = d.has_bias ? dbg : nullptr;
-    a.dYx0 = dYx0;
-    a.dYx = sc + w.dYx;
-    a.accum_x = 1;
-    a.dYh0 = d_h_prev;
-    a.dYh = sc + w.dYh;
-    a.dQ = want_dGc ? sc + w.dQ : nullptr;
-    a.dW = dWg;
-    a.Psave = sv + w.Pg;
-    a.Wimg = (w.Wimg_c > w.Wimg_g && w.scratch_total > w.Wimg_dx) ? sc + w.Wimg_dx : nullptr;   // wide forward ran
-    STC_TRY(launch_conv_bwd_dx(a, st));
-    STC_TRY(launch_conv_bwd_dw(a, st));
-  }
-  STC_TRY(adjoint_chain(d, *gs, CD, xt, xt_batch_stride, sv + w.Yx, dYx0, sc + w.dYx, dGs, st));
-  STC_TRY(adjoint_chain(d, *gs, CH, h_prev, (int64_t)d.N * CH, sv + w.Yh, d_h_prev, sc + w.dYh, dGs, st));
-
-  if (want_dGc) STC_TRY(launch_cheby_small_bwd(gc, sv + w.Q, sc + w.dQ, d.C, d.Kc, dGc, st));
-  return STC_OK;
+  return bwd_gates(b, Wg, dWg, dbg);
 }
 
 }  // extern "C"

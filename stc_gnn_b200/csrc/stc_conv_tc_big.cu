@@ -790,7 +790,7 @@ int try_launch_conv_bwd_dx_big(const ConvArgs& a, cudaStream_t st, bool* handled
 // (bounded accumulation chains), one atomicAdd per element at the end.
 // =================================================================================================
 constexpr int BG_DW_CR = 32;       // rows per chunk (K extent of one image)
-constexpr int BG_DW_DRAIN = 8;     // chunks per accumulation chain: 16 K-steps (128 rows) into each main accumulator.  The tensor core
+constexpr int BG_DW_DRAIN = 4;     // chunks per accumulation chain: 8 K-steps (64 rows) into each main accumulator.  The tensor core
                                    // truncates when it adds into the accumulator, so the error grows with the chain: at 32 chunks one
                                    // dWg element of the N = 4096 parity case sat at 3.0e-5 x mean|ref| against an allowance of 3e-5
 

@@ -6,8 +6,9 @@ output node given the features of that node's in-neighbours.  Nodes are split in
 every [B, N, C, L] tensor.  One Chebyshev hop = exchange the boundary-node slabs (`halo` rows of width B*C*L)
 with the ranks that own them, then apply the local operator whose columns are renumbered into
 `[local nodes | halo nodes]`.  The categorical mix and the gate contraction are node-local and never communicate.
-The adjoint (backward: `dX[b,n,:] = sum_m Gs[n,m] dY[b,m,:]`) is the same scheme on the un-transposed graph and
-has its own (generally different) halo set.
+The adjoint (backward: `dX[b,n,:] = sum_m Gs[n,m] dY[b,m,:]`) is the same scheme on the un-transposed graph; both
+directions use one halo set (the union of what either needs) so that forward and backward share buffer layouts.
+Parameter gradients are partial sums over a rank's nodes and are all-reduced once per cell backward.
 
 Everything here is host logic + `torch.distributed` plumbing (NCCL all-to-all over NVSwitch on the GPU box, gloo in
 the CPU tests); the arithmetic is `stc_support_apply` of libstc_b200.so.  There is no CPU arithmetic path: on
@@ -60,19 +61,24 @@ def _csr_to_coo(rowptr: torch.Tensor, col: torch.Tensor):
 
 
 def build_plan(out_idx: torch.Tensor, in_idx: torch.Tensor, vals: torch.Tensor, num_nodes: int, rank: int,
-               world: int) -> HaloPlan:
+               world: int, symmetric_halo: bool = False) -> HaloPlan:
     """Plan for the operator `Y[out] += val * X[in]` given as global COO triplets (host tensors).
 
     Deterministic and communication-free: every rank derives what each peer needs from the replicated graph.
+    `symmetric_halo`: the halo set is the one of the operator AND of its transpose (a superset of what this operator
+    reads), so that the plans of both directions share one extended node set -- the backward of the partitioned cell
+    runs its adjoint hops on buffers laid out for the forward.  For a structurally symmetric graph nothing is added.
     """
     out_idx, in_idx, vals = out_idx.long().cpu(), in_idx.long().cpu(), vals.float().cpu()
+    pair_out, pair_in = (torch.cat([out_idx, in_idx]), torch.cat([in_idx, out_idx])) if symmetric_halo else (out_idx, in_idx)
     bounds = [shard_bounds(num_nodes, p, world) for p in range(world)]
     starts = torch.tensor([b[0] for b in bounds] + [num_nodes])
     owner_of = lambda idx: torch.bucketize(idx, starts[1:], right=True)   # block index of each global node
-    out_owner, in_owner = owner_of(out_idx), owner_of(in_idx)
+    out_owner = owner_of(out_idx)
+    pair_out_owner, pair_in_owner = owner_of(pair_out), owner_of(pair_in)
 
     def halo_of(p: int) -> torch.Tensor:   # sorted global ids rank p needs from other ranks
-        need = in_idx[(out_owner == p) & (in_owner != p)]
+        need = pair_in[(pair_out_owner == p) & (pair_in_owner != p)]
         return torch.unique(need)          # sorted ascending => grouped by owner (blocks are contiguous)
 
     s, e = bounds[rank]
@@ -141,8 +147,10 @@ class PartitionedSupport:
                  world: int, group: Optional[dist.ProcessGroup] = None):
         n_idx, m_idx = _csr_to_coo(rowptr, col)      # Gs[n, m]
         self.N, self.rank, self.world, self.group = int(num_nodes), rank, world, group
-        self.fwd = build_plan(m_idx, n_idx, vals, num_nodes, rank, world)
-        self.bwd = build_plan(n_idx, m_idx, vals, num_nodes, rank, world)
+        # one extended node set [local | halo] for both directions (see build_plan)
+        self.fwd = build_plan(m_idx, n_idx, vals, num_nodes, rank, world, symmetric_halo=True)
+        self.bwd = build_plan(n_idx, m_idx, vals, num_nodes, rank, world, symmetric_halo=True)
+        assert self.fwd.nhalo == self.bwd.nhalo and torch.equal(self.fwd.halo_global, self.bwd.halo_global)
         self.start, self.nloc = self.fwd.start, self.fwd.nloc
         self._dev = {}
 
@@ -223,70 +231,160 @@ class PartitionedSupport:
         return terms
 
 
+def adjoint_chain_ext(ps: PartitionedSupport, ybar: List[torch.Tensor], hop: Optional[Callable] = None) -> torch.Tensor:
+    """Reverse of the feature-side recurrence (Y_1 = Gs^T Y_0, Y_k = 2 Gs^T Y_{k-1} - Y_{k-2}) on EXTENDED adjoints.
+
+    `ybar[k]` [B, nloc + nhalo, ...] holds dL/dY_k of this rank's nodes in its local rows (halo rows: anything).  In
+    place, for k = Ks-1 .. 1:  ybar[k-1] += (2 if k >= 2 else 1) * Gs ybar[k]  (one halo exchange of ybar[k], adjoint
+    plan) and ybar[k-2] -= ybar[k] (local rows only).  Returns ybar[0], whose local rows are dL/dY_0.
+    `hop(X_ext, out_ext, Z_ext, alpha, beta, direction)` replaces `ps.hop_ext` (the CPU tests inject a checker)."""
+    hop = hop or (lambda X, out, Z, alpha, beta, direction: ps.hop_ext(X, out, Z_ext=Z, alpha=alpha, beta=beta,
+                                                                       direction=direction))
+    n = ps.nloc
+    for k in range(len(ybar) - 1, 0, -1):
+        hop(ybar[k], ybar[k - 1], ybar[k - 1], 2.0 if k >= 2 else 1.0, 1.0, "bwd")
+        if k >= 2:
+            ybar[k - 2][:, :n].sub_(ybar[k][:, :n])
+    return ybar[0]
+
+
+class _PartitionedCell(torch.autograd.Function):
+    """One STC cell on this rank's node block; forward and backward are the C-ABI stages of include/stc_b200.h with
+    the spatial hops (halo exchange + `stc_support_apply`) in between."""
+
+    @staticmethod
+    def forward(ctx, Gc, Xt, Ht_1, Wg, bg, Wc, bc, cfg):
+        from . import _lib
+        from .cell import _activation_code, _ptr
+        ps, Ks, Kc, activation, reduce_params = cfg
+        lib = _lib.load()
+        B, n, C, Din = Xt.shape
+        h = Ht_1.shape[-1]
+        # Everything lives in the EXTENDED node set [local | halo]: the node-local stages simply run over
+        # nloc + nhalo nodes (the halo rows, ~1 % at k = 8, are recomputed garbage that the next exchange overwrites),
+        # so the spatial terms are written straight into the `saved` regions the stages read -- no slicing, no compaction.
+        ne = ps.fwd.next
+        Gc = Gc.detach().contiguous()
+        Wg, Wc = Wg.detach().contiguous(), Wc.detach().contiguous()
+        bg = bg.detach().contiguous() if bg is not None else None
+        bc = bc.detach().contiguous() if bc is not None else None
+        Xe = Xt.new_zeros(B, ne, C, Din)
+        Xe[:, :n] = Xt.detach()
+        He = Ht_1.new_zeros(B, ne, C, h)
+        He[:, :n] = Ht_1.detach()
+        dims = _lib.StcDims(B, ne, C, Din, h, Ks, Kc, _activation_code(activation), 1 if bg is not None else 0)
+        lay = _lib.saved_layout(dims)
+        saved = torch.empty(lib.stc_cell_saved_bytes(dims) // 4, dtype=torch.float32, device=Xt.device)
+        Hn = torch.empty_like(He)
+        R = B * ne * C
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def region(name, k, width):
+            o = lay[name] + k * R * width
+            return saved[o:o + R * width].view(B, ne, C, width)
+
+        def stage(which):
+            _lib.check(lib.stc_cell_fwd_stage(dims, which, Gc.data_ptr(), Xe.data_ptr(), ne * C * Din, He.data_ptr(),
+                                              Wg.data_ptr(), _ptr(bg), Wc.data_ptr(), _ptr(bc), Hn.data_ptr(),
+                                              saved.data_ptr(), saved.numel() * 4, stream), "stc_cell_fwd_stage")
+            _lib.note_launches()
+
+        def chain(term0, name, width, first):
+            """Y_1 = Gs^T Y_0, Y_k = 2 Gs^T Y_{k-1} - Y_{k-2} into regions `name`[first ...]."""
+            prev2, prev = None, term0
+            for k in range(1, Ks):
+                out = region(name, first + k - 1, width)
+                if k == 1:
+                    ps.hop_ext(prev, out)
+                else:
+                    ps.hop_ext(prev, out, Z_ext=prev2, alpha=2.0, beta=-1.0)
+                prev2, prev = prev, out
+
+        chain(Xe, "Yx", Din, 0)
+        chain(He, "Yh", h, 0)
+        stage(_lib.STAGE_GATES)
+        chain(region("Yr", 0, h), "Yr", h, 1)
+        stage(_lib.STAGE_CANDI)
+        ctx.cfg, ctx.dims = cfg, dims
+        ctx.has_bias = bg is not None
+        ctx.keep = (Gc, Xe, He, Wg, Wc, saved)
+        return Hn[:, :n].contiguous()
+
+    @staticmethod
+    def backward(ctx, dHn):
+        from . import _lib
+        ps, Ks, Kc, activation, reduce_params = ctx.cfg
+        Gc, Xe, He, Wg, Wc, saved = ctx.keep
+        dims = ctx.dims
+        lib = _lib.load()
+        B, ne, C, Din = Xe.shape
+        h = He.shape[-1]
+        n = ps.nloc
+        dev = Xe.device
+        stream = torch.cuda.current_stream().cuda_stream
+        dHe = He.new_zeros(B, ne, C, h)          # halo rows carry no output gradient: they stay out of every dW
+        dHe[:, :n] = dHn
+        scratch = torch.empty(lib.stc_cell_bwd_scratch_bytes(dims) // 4, dtype=torch.float32, device=dev)
+        lay = _lib.scratch_layout(dims)
+        R = B * ne * C
+        dXe = torch.empty_like(Xe)
+        dHp = torch.empty_like(He)
+        P, L = Ks * Kc, Din + h
+        # one flat buffer for every replicated-parameter gradient: the all-reduce below is a single call
+        sizes = [P * L * 2 * h, 2 * h if ctx.has_bias else 0, P * L * h, h if ctx.has_bias else 0, C * C]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        dWg, dbg, dWc, dbc, dGc = flat.split(sizes)
+        pz = lambda t: t.data_ptr() if t.numel() else None
+
+        def region(name, k, width):
+            o = lay[name] + k * R * width
+            return scratch[o:o + R * width].view(B, ne, C, width)
+
+        def stage(which):
+            _lib.check(lib.stc_cell_bwd_stage(dims, which, Gc.data_ptr(), Xe.data_ptr(), ne * C * Din, He.data_ptr(),
+                                              Wg.data_ptr(), Wc.data_ptr(), dHe.data_ptr(), dXe.data_ptr(), dHp.data_ptr(),
+                                              dWg.data_ptr(), pz(dbg), dWc.data_ptr(), pz(dbc), dGc.data_ptr(), 1,
+                                              saved.data_ptr(), saved.numel() * 4, scratch.data_ptr(),
+                                              scratch.numel() * 4, stream), "stc_cell_bwd_stage")
+            _lib.note_launches()
+
+        stage(_lib.STAGE_CANDI)
+        dYr = [region("dYr", k, h) for k in range(Ks)]
+        adjoint_chain_ext(ps, dYr)
+        dYr[0][:, n:].zero_()                    # d(r*H) of the halo rows belongs to their owners
+        stage(_lib.STAGE_GATES)
+        adjoint_chain_ext(ps, [dXe] + [region("dYx", k, Din) for k in range(Ks - 1)])
+        adjoint_chain_ext(ps, [dHp] + [region("dYh", k, h) for k in range(Ks - 1)])
+        if reduce_params and ps.world > 1:
+            dist.all_reduce(flat, group=ps.group)
+        need = ctx.needs_input_grad
+        return (dGc.view(C, C) if need[0] else None, dXe[:, :n].contiguous() if need[1] else None,
+                dHp[:, :n].contiguous() if need[2] else None, dWg.view(P * L, 2 * h) if need[3] else None,
+                dbg if (need[4] and ctx.has_bias) else None, dWc.view(P * L, h) if need[5] else None,
+                dbc if (need[6] and ctx.has_bias) else None, None)
+
+
 def partitioned_cell_forward(ps: PartitionedSupport, Gc: torch.Tensor, Xt: torch.Tensor, Ht_1: torch.Tensor,
                              Wg: torch.Tensor, bg: Optional[torch.Tensor], Wc: torch.Tensor,
-                             bc: Optional[torch.Tensor], Ks: int, Kc: int, activation=None) -> torch.Tensor:
+                             bc: Optional[torch.Tensor], Ks: int, Kc: int, activation=None,
+                             reduce_params: bool = True) -> torch.Tensor:
     """`STC_Cell.forward` (`framework/STC_GNN.py:65-79`) on this rank's node block of a row-partitioned graph.
 
     Xt [B, nloc, C, Din], Ht_1 [B, nloc, C, h] are the local blocks; returns the local block of H'.  The spatial
-    hops run here (halo exchange + `stc_support_apply`), the two node-local stages are `stc_cell_fwd_stage`
-    (include/stc_b200.h).  Forward only (inference / roll-out): gradients through the partitioned path are not
-    implemented yet, so inputs that require grad are rejected rather than silently detached.
+    hops run here (halo exchange + `stc_support_apply`), the node-local stages are `stc_cell_fwd_stage` /
+    `stc_cell_bwd_stage` (include/stc_b200.h).  Differentiable w.r.t. Gc, Xt, Ht_1 and the parameters (the support is a
+    constant CSR graph: no dGs).  The parameters and Gc are replicated over the ranks, so their gradients are partial
+    sums over this rank's nodes: with `reduce_params` (default) the backward all-reduces them in ONE flat bucket and
+    every rank receives the full gradient (all ranks must then run the backward); pass False to reduce later, e.g.
+    once per step through `dp.GradBucket` after a time loop.
     """
-    from . import _lib
-    from .cell import _activation_code, _ptr
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (Gc, Xt, Ht_1, Wg, bg, Wc, bc)):
-        raise RuntimeError("partitioned_cell_forward is forward-only: call it under torch.no_grad()")
     for name, t in (("Gc", Gc), ("Xt", Xt), ("Ht_1", Ht_1), ("gates.W", Wg), ("candi.W", Wc)):
         if not t.is_cuda or t.dtype != torch.float32:
             raise RuntimeError(f"partitioned cell: {name} must be a float32 CUDA tensor (there is no CPU path)")
-    lib = _lib.load()
     B, n, C, Din = Xt.shape
     h = Ht_1.shape[-1]
     if n != ps.nloc or Ht_1.shape != (B, n, C, h):
         raise RuntimeError(f"local block has {n} nodes, the partition owns {ps.nloc}; Ht_1 {tuple(Ht_1.shape)}")
-    # Everything lives in the EXTENDED node set [local | halo] of the forward plan: the node-local stages simply run
-    # over nloc + nhalo nodes (the halo rows, ~1 % at k = 8, are recomputed garbage that the next exchange overwrites),
-    # so the spatial terms are written straight into the `saved` regions the stages read -- no slicing, no compaction.
-    ne = ps.fwd.next
-    Gc = Gc.contiguous()
-    Wg, Wc = Wg.contiguous(), Wc.contiguous()
-    Xe = Xt.new_zeros(B, ne, C, Din)
-    Xe[:, :n] = Xt
-    He = Ht_1.new_zeros(B, ne, C, h)
-    He[:, :n] = Ht_1
-    dims = _lib.StcDims(B, ne, C, Din, h, Ks, Kc, _activation_code(activation), 1 if bg is not None else 0)
-    lay = _lib.saved_layout(dims)
-    saved = torch.empty(lib.stc_cell_saved_bytes(dims) // 4, dtype=torch.float32, device=Xt.device)
-    Hn = torch.empty_like(He)
-    R = B * ne * C
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def region(name, k, width):
-        o = lay[name] + k * R * width
-        return saved[o:o + R * width].view(B, ne, C, width)
-
-    def stage(which):
-        _lib.check(lib.stc_cell_fwd_stage(dims, which, Gc.data_ptr(), Xe.data_ptr(), ne * C * Din, He.data_ptr(),
-                                          Wg.data_ptr(), _ptr(bg), Wc.data_ptr(), _ptr(bc), Hn.data_ptr(),
-                                          saved.data_ptr(), saved.numel() * 4, stream), "stc_cell_fwd_stage")
-        _lib.note_launches()
-
-    def chain(term0, name, width, first):
-        """Y_1 = Gs^T Y_0, Y_k = 2 Gs^T Y_{k-1} - Y_{k-2} into regions `name`[first ...]."""
-        prev2, prev = None, term0
-        for k in range(1, Ks):
-            out = region(name, first + k - 1, width)
-            if k == 1:
-                ps.hop_ext(prev, out)
-            else:
-                ps.hop_ext(prev, out, Z_ext=prev2, alpha=2.0, beta=-1.0)
-            prev2, prev = prev, out
-
-    chain(Xe, "Yx", Din, 0)
-    chain(He, "Yh", h, 0)
-    stage(_lib.STAGE_GATES)
-    chain(region("Yr", 0, h), "Yr", h, 1)
-    stage(_lib.STAGE_CANDI)
-    return Hn[:, :n].contiguous()
-
+    if (bg is None) != (bc is None):
+        raise RuntimeError("partitioned cell: gates.b and candi.b must both be given or both be None")
+    return _PartitionedCell.apply(Gc, Xt, Ht_1, Wg, bg, Wc, bc, (ps, Ks, Kc, activation, reduce_params))

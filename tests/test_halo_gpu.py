@@ -1,4 +1,4 @@
-"""GPU tests of the row-partitioned path: staged cell forward (C ABI) + halo hops through stc_support_apply.
+"""GPU tests of the row-partitioned path: staged cell forward AND backward (C ABI) + halo hops through stc_support_apply.
 
 World size 1 runs on any GPU box; the 2-rank NCCL test needs two visible GPUs (`gpurun --gpus 2`) and is skipped otherwise.
 """
@@ -18,9 +18,14 @@ pytestmark = pytest.mark.gpu
 
 
 def _cell_block(rank, world, device, cfg, seed):
+    """Partitioned cell on this rank's node block == the block of the unpartitioned fp64 oracle: H' and every gradient
+    (activations: this rank's rows; replicated parameters and Gc: the all-reduced full gradient)."""
     import stc_gnn_b200 as S
     t = random_case(cfg["B"], cfg["N"], cfg["C"], cfg["Din"], cfg["h"], cfg["Ks"], cfg["Kc"], seed=seed, sparse_frac=0.85)
-    want = O.stc_cell(t["Gs"], t["Gc"], t["Xt"], t["H"], t["Wg"], t["bg"], t["Wc"], t["bc"], cfg["Ks"], cfg["Kc"])
+    leaves = {k: t[k].clone().requires_grad_(True) for k in ("Gc", "Xt", "H", "Wg", "bg", "Wc", "bc")}
+    want = O.stc_cell(t["Gs"], leaves["Gc"], leaves["Xt"], leaves["H"], leaves["Wg"], leaves["bg"], leaves["Wc"],
+                      leaves["bc"], cfg["Ks"], cfg["Kc"])
+    want.backward(t["dHn"])
     ps = S.halo.PartitionedSupport.from_dense(t["Gs"], rank, world)
     f = lambda x: x.float().to(device)
     with torch.no_grad():
@@ -30,21 +35,40 @@ def _cell_block(rank, world, device, cfg, seed):
         dY = torch.randn(cfg["B"], cfg["N"], cfg["C"], cfg["h"], generator=torch.Generator().manual_seed(seed + 1)).double()
         got_b = ps.apply(f(ps.local_slice(dY)), "bwd")
     torch.cuda.synchronize()
-    O.assert_close(got.cpu(), ps.local_slice(want), f"partitioned cell forward (rank {rank}/{world})")
+    O.assert_close(got.cpu(), ps.local_slice(want.detach()), f"partitioned cell forward (rank {rank}/{world})")
     O.assert_close(got_b.cpu(), ps.local_slice(torch.einsum("nm,bmcl->bncl", t["Gs"], dY)), f"adjoint hop (rank {rank})")
+    # gradients through the partitioned path
+    g = {k: f(ps.local_slice(t[k]) if k in ("Xt", "H") else t[k]).requires_grad_(True) for k in leaves}
+    out = S.halo.partitioned_cell_forward(ps, g["Gc"], g["Xt"], g["H"], g["Wg"], g["bg"], g["Wc"], g["bc"], cfg["Ks"], cfg["Kc"])
+    O.assert_close(out.detach().cpu(), ps.local_slice(want.detach()), f"partitioned cell forward, grad mode (rank {rank})")
+    out.backward(f(ps.local_slice(t["dHn"])))
+    torch.cuda.synchronize()
+    for k in leaves:
+        ref = leaves[k].grad
+        ref = ps.local_slice(ref) if k in ("Xt", "H") else ref
+        O.assert_close(g[k].grad.cpu(), ref, f"partitioned d{k} (rank {rank}/{world})")
     return ps
 
 
-@pytest.mark.parametrize("cfg", [dict(B=2, N=96, C=5, Din=16, h=16, Ks=2, Kc=2), dict(B=3, N=70, C=4, Din=3, h=8, Ks=4, Kc=2)])
-def test_staged_cell_forward_single_rank(cfg):
+@pytest.mark.parametrize("cfg", [dict(B=2, N=96, C=5, Din=16, h=16, Ks=2, Kc=2), dict(B=3, N=70, C=4, Din=3, h=8, Ks=4, Kc=2),
+                                 dict(B=1, N=40, C=8, Din=64, h=64, Ks=3, Kc=2)])
+def test_staged_cell_single_rank(cfg):
     ps = _cell_block(0, 1, torch.device("cuda:0"), cfg, seed=21)
     assert ps.fwd.nhalo == 0
+
+
+def test_staged_backward_error_paths():
     import stc_gnn_b200 as S
     t = random_case(2, 16, 2, 2, 8, 2, 2, seed=1)
-    ps2 = S.halo.PartitionedSupport.from_dense(t["Gs"], 0, 1)
-    f = lambda x: x.float().cuda().requires_grad_(True)
-    with pytest.raises(RuntimeError, match="forward-only"):
-        S.halo.partitioned_cell_forward(ps2, f(t["Gc"]), f(t["Xt"]), f(t["H"]), f(t["Wg"]), f(t["bg"]), f(t["Wc"]),
+    ps = S.halo.PartitionedSupport.from_dense(t["Gs"], 0, 1)
+    f = lambda x: x.float().cuda()
+    with pytest.raises(RuntimeError, match="both be given"):
+        S.halo.partitioned_cell_forward(ps, f(t["Gc"]), f(t["Xt"]), f(t["H"]), f(t["Wg"]), f(t["bg"]), f(t["Wc"]), None, 2, 2)
+    with pytest.raises(RuntimeError, match="partition owns"):
+        S.halo.partitioned_cell_forward(ps, f(t["Gc"]), f(t["Xt"])[:, :8], f(t["H"])[:, :8], f(t["Wg"]), f(t["bg"]),
+                                        f(t["Wc"]), f(t["bc"]), 2, 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        S.halo.partitioned_cell_forward(ps, t["Gc"].float(), f(t["Xt"]), f(t["H"]), f(t["Wg"]), f(t["bg"]), f(t["Wc"]),
                                         f(t["bc"]), 2, 2)
 
 
@@ -71,7 +95,7 @@ def _nccl_worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_halo_cell_forward_two_ranks_nccl():
+def test_halo_cell_two_ranks_nccl():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]

@@ -129,6 +129,55 @@ def _halo_case(rank, world):
     torch.testing.assert_close(ext[:, ps.nloc:], X.reshape(B, N, -1)[:, ps.fwd.halo_global])
 
 
+def _oracle_hop(ps):
+    """CPU stand-in for PartitionedSupport.hop_ext: the real in-place halo refresh, the checker's arithmetic."""
+    def hop(X_ext, out_ext, Z_ext, alpha, beta, direction):
+        plan = ps.fwd if direction == "fwd" else ps.bwd
+        B = X_ext.shape[0]
+        X3 = X_ext.view(B, plan.next, -1)
+        halo.exchange_into(plan, X3, ps.group)
+        Y = alpha * _oracle_apply(plan, X3)
+        if beta != 0.0:
+            Y = Y + beta * Z_ext.view(B, plan.next, -1)[:, :plan.nloc]
+        out_ext.view(B, plan.next, -1)[:, :plan.nloc] = Y
+    return hop
+
+
+def _halo_adjoint_case(rank, world):
+    """Adjoint of the Ks-term spatial recurrence on a row partition == autograd of the unpartitioned recurrence;
+    both directions share one extended node set even though the graph is not symmetric."""
+    N, B, C, L, Ks = 37, 2, 3, 4, 4
+    G = _sparse_graph(N, seed=21)
+    assert not torch.equal(G != 0, (G != 0).t())
+    ps = halo.PartitionedSupport.from_dense(G, rank, world)
+    assert ps.fwd.nhalo == ps.bwd.nhalo and torch.equal(ps.fwd.halo_global, ps.bwd.halo_global)
+    assert all(torch.equal(a, b) for a, b in zip(ps.fwd.send_idx, ps.bwd.send_idx))
+    g = torch.Generator().manual_seed(6)
+    X = torch.randn(B, N, C, L, generator=g, dtype=torch.float64).requires_grad_(True)
+    dY = [torch.randn(B, N, C, L, generator=g, dtype=torch.float64) for _ in range(Ks)]
+    terms = O.spatial_terms(X, G, Ks)
+    sum((t * d).sum() for t, d in zip(terms, dY)).backward()
+    ne = ps.fwd.next
+    ybar = []
+    for d in dY:
+        e = torch.full((B, ne, C, L), 7.0, dtype=torch.float64)      # halo rows: junk the chain must never read
+        e[:, :ps.nloc] = ps.local_slice(d)
+        ybar.append(e)
+    got = halo.adjoint_chain_ext(ps, ybar, hop=_oracle_hop(ps))
+    O.assert_close(got[:, :ps.nloc], ps.local_slice(X.grad), f"partitioned adjoint chain (rank {rank})", 1e-9, 1e-10)
+    # the forward recurrence through the same in-place hop (what the CUDA path does with hop_ext)
+    hop = _oracle_hop(ps)
+    ext = [torch.zeros(B, ne, C, L, dtype=torch.float64) for _ in range(Ks)]
+    ext[0][:, :ps.nloc] = ps.local_slice(X.detach())
+    for k in range(1, Ks):
+        if k == 1:
+            hop(ext[0], ext[1], None, 1.0, 0.0, "fwd")
+        else:
+            hop(ext[k - 1], ext[k], ext[k - 2], 2.0, -1.0, "fwd")
+    for k in range(Ks):
+        O.assert_close(ext[k][:, :ps.nloc], ps.local_slice(terms[k].detach()), f"in-place forward term {k}", 1e-9, 1e-10)
+
+
 def _halo_cell_case(rank, world):
     """Whole cell on a row partition: spatial terms via halo hops, everything else node-local."""
     cfg = dict(B=2, N=26, C=3, Din=2, h=4, Ks=3, Kc=2)
@@ -190,3 +239,7 @@ def test_halo_partitioned_terms_match_unpartitioned():
 
 def test_halo_partitioned_cell_matches_unpartitioned():
     run_ranks(_halo_cell_case)
+
+
+def test_halo_partitioned_adjoint_chain_matches_autograd():
+    run_ranks(_halo_adjoint_case)

@@ -2,7 +2,10 @@
 """BASELINE configs[3]: one STC cell forward on the N = 65,536 kNN graph (C = 8, F = 64, Ks = 4 = 3 hops), nodes
 row-partitioned over the ranks with a halo exchange per hop (stc_gnn_b200/halo.py).  Launch under torchrun:
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_halo.py [B]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_halo.py [B] [--train]
+
+`--train`: forward + backward of the cell (gradients w.r.t. Xt, H, Gc and the parameters; the partitioned backward runs
+the adjoint hops with their own halo exchanges and all-reduces the parameter gradients in one bucket).
 
 Strong scaling: the global problem is fixed, each rank owns N / world nodes.  Time = max over ranks (CUDA events,
 barrier on both sides).  Rank 0 prints one JSON line."""
@@ -22,7 +25,9 @@ from stc_gnn_b200.synth import knn_csr  # noqa: E402
 
 
 def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    train = "--train" in sys.argv
+    pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+    B = int(pos[0]) if pos else 2
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -36,7 +41,7 @@ def main():
     torch.manual_seed(0)
     cell = S.STC_Cell(N, C, Ks, Kc, F, F).to(dev)
     Gc = (torch.rand(C, C, generator=torch.Generator().manual_seed(1)) / C).to(dev)
-    with torch.no_grad():
+    with torch.set_grad_enabled(train):
         if world > 1:
             ps = PartitionedSupport(rp, ci, va, N, rank, world)
             n = ps.nloc
@@ -46,13 +51,22 @@ def main():
             n = N
             halo = {"fwd_halo_rows": 0, "local_rows": n}
         g = torch.Generator().manual_seed(100 + rank)
-        X = torch.randn(B, n, C, F, generator=g).to(dev)
-        H = (torch.randn(B, n, C, F, generator=g) * 0.5).to(dev)
+        X = torch.randn(B, n, C, F, generator=g).to(dev).requires_grad_(train)
+        H = (torch.randn(B, n, C, F, generator=g) * 0.5).to(dev).requires_grad_(train)
+        dHn = torch.randn(B, n, C, F, generator=g).to(dev)
+        Gc.requires_grad_(train)
 
-        def step():
+        def fwd():
             if world > 1:
                 return partitioned_cell_forward(ps, Gc, X, H, cell.gates.W, cell.gates.b, cell.candi.W, cell.candi.b, Ks, Kc)
             return cell(Gs=ps, Gc=Gc, Xt=X, Ht_1=H)
+
+        def step():
+            out = fwd()
+            if train:
+                for t in (X, H, Gc, *cell.parameters()):
+                    t.grad = None
+                out.backward(dHn)
 
         for _ in range(3):
             step()
@@ -72,7 +86,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
     if rank == 0:
-        print(json.dumps({"kind": "config4_cell_fwd_partitioned", "n_gpus": world, "N": N, "C": C, "F": F, "Ks": Ks, "B": B,
+        print(json.dumps({"kind": "config4_cell_step_partitioned" if train else "config4_cell_fwd_partitioned", "n_gpus": world, "N": N, "C": C, "F": F, "Ks": Ks, "B": B,
                           "ms": ms, "cell_step_samples_per_s": B / ms * 1e3, "scaling": "strong", **halo}), flush=True)
     if world > 1:
         dist.barrier()

@@ -14,6 +14,7 @@ from . import _lib
 from .support import CsrSupport, dense_struct
 
 _ACT_CODES = {None: _lib.ACT_NONE, nn.ReLU: _lib.ACT_RELU}
+_ACT_NAMES = {_lib.ACT_NONE: None, _lib.ACT_RELU: "relu"}
 
 
 def _activation_code(activation) -> int:
@@ -176,6 +177,13 @@ class STC_Cell(nn.Module):
         assert len(Xt.shape) == len(Ht_1.shape) == 4, 'STC-cell must take in 4D tensor as input [Xt, Ht-1]'
         if isinstance(Gs, torch.Tensor) and Gs.layout != torch.strided:
             Gs = _csr_cache(Gs)
+        if hasattr(Gs, "fwd") and hasattr(Gs, "hop_ext"):
+            # a halo.PartitionedSupport: Xt / Ht_1 are this rank's node blocks (construct the cell with num_nodes = the
+            # local count so that init_hidden matches); spatial hops exchange halos, everything else is node-local
+            from .halo import partitioned_cell_forward
+            return partitioned_cell_forward(Gs, Gc, Xt, Ht_1, self.gates.W, getattr(self.gates, "b", None), self.candi.W,
+                                            getattr(self.candi, "b", None), self.Ks, self.Kc, _ACT_NAMES[self._act],
+                                            reduce_params=getattr(Gs, "reduce_per_cell", True))
         return _CellFunction.apply(Gs, Gc, Xt, Ht_1, self.gates.W, getattr(self.gates, "b", None), self.candi.W,
                                    getattr(self.candi, "b", None), (self.Ks, self.Kc, self._act))
 

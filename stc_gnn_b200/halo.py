@@ -152,6 +152,9 @@ class PartitionedSupport:
         self.bwd = build_plan(n_idx, m_idx, vals, num_nodes, rank, world, symmetric_halo=True)
         assert self.fwd.nhalo == self.bwd.nhalo and torch.equal(self.fwd.halo_global, self.bwd.halo_global)
         self.start, self.nloc = self.fwd.start, self.fwd.nloc
+        # STC_Cell / RecurrentStack accept this object as `Gs` (blocks in, blocks out).  True: every cell backward
+        # all-reduces its parameter gradients; False: the caller reduces once per step (dp.allreduce_gradients).
+        self.reduce_per_cell = True
         self._dev = {}
 
     @classmethod
@@ -311,6 +314,7 @@ class _PartitionedCell(torch.autograd.Function):
         return Hn[:, :n].contiguous()
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dHn):
         from . import _lib
         ps, Ks, Kc, activation, reduce_params = ctx.cfg

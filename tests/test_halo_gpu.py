@@ -57,6 +57,33 @@ def test_staged_cell_single_rank(cfg):
     assert ps.fwd.nhalo == 0
 
 
+def test_recurrent_stack_accepts_a_partitioned_support():
+    """STC_Cell / RecurrentStack dispatch on a PartitionedSupport handed in as `Gs`: encoder 2 x T=3 + decoder roll-out,
+    output and every gradient == the same stack on the unpartitioned CSR support."""
+    import stc_gnn_b200 as S
+    N, C, Din, h, Ks, Kc, T, B = 48, 4, 1, 16, 3, 2, 3, 2
+    t = random_case(B, N, C, Din, h, Ks, Kc, seed=5, sparse_frac=0.85)
+    dev = torch.device("cuda:0")
+    csr = S.CsrSupport.from_torch_sparse(t["Gs"].float().to_sparse_csr().to(dev))
+    ps = S.halo.PartitionedSupport.from_dense(t["Gs"], 0, 1)
+    ps.reduce_per_cell = False
+    torch.manual_seed(3)
+    stack = S.RecurrentStack(N, C, Ks, Kc, Din, h, 2, 2).to(dev)
+    g = torch.Generator().manual_seed(8)
+    X = torch.randn(B, T, N, C, Din, generator=g).to(dev)
+    dOut = torch.randn(B, 2, N, C, h, generator=g).to(dev)
+    res = []
+    for Gs in (csr, ps):
+        Gc = t["Gc"].float().to(dev).requires_grad_(True)
+        Xl = X.clone().requires_grad_(True)
+        stack.zero_grad(set_to_none=True)
+        out = stack(Gs, Gc, Xl)
+        out.backward(dOut)
+        res.append([out.detach(), Gc.grad, Xl.grad] + [p.grad.clone() for p in stack.parameters()])
+    for i, (a, b) in enumerate(zip(*res)):
+        O.assert_close(b.cpu(), a.cpu(), f"stack tensor {i}: partitioned vs CSR support", rtol=1e-4, atol_scale=1e-5)
+
+
 def test_staged_backward_error_paths():
     import stc_gnn_b200 as S
     t = random_case(2, 16, 2, 2, 8, 2, 2, seed=1)

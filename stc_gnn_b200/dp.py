@@ -102,3 +102,36 @@ def allreduce_gradients(module: torch.nn.Module, extra: Iterable[torch.Tensor] =
         bucket = GradBucket(gradient_tensors(module, extra))
     bucket.allreduce(group=group, average=average)
     return bucket
+
+
+class _SumOverRanks(torch.autograd.Function):
+    """y = sum over ranks of x (every rank receives y).  With per-rank losses L_q that all depend on y, the gradient
+    of the total loss w.r.t. this rank's x is sum_q dL_q/dy: the backward is the same all-reduce of the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        y = x.detach().clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = dy.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def sum_over_ranks(x: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Differentiable cross-rank sum for quantities the reference sums over the WHOLE batch before a non-linearity.
+
+    The case on this path's doorstep: `MGP_Gen` builds its score matrices `Ps [N,N]`, `Pc [C,C]` with einsums that sum
+    over b and t (`framework/STC_GNN.py:231, 239`) and only then applies relu / softmax, so under batch data-parallelism
+    each rank would generate different supports from its shard.  Wrapping those two einsum results in `sum_over_ranks`
+    (40 KB + 100 B at SF sizes) makes `Gs, Gc` -- and, through this function's backward, the generator's gradients --
+    equal to the single-process global-batch values; the cells downstream need nothing else (their `dGs`, `dGc` stay
+    per-rank partial sums of per-rank losses, which is exactly what the backward all-reduce here adds up).
+    Identity outside a process group or at world size 1."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return x
+    return _SumOverRanks.apply(x, group)

@@ -107,6 +107,39 @@ def _dp_case(rank, world):
         O.assert_close(p.grad, full[k].grad, f"DP-reduced d{k} (rank {rank})", rtol=1e-4, atol_scale=1e-5)
 
 
+def _global_supports_case(rank, world):
+    """A batch-summed score followed by a non-linearity (the shape of MGP_Gen, STC_GNN.py:231-232): with sum_over_ranks
+    on the pre-relu sum, sharded-batch values and gradients equal the single-process global-batch ones."""
+    g = torch.Generator().manual_seed(4)
+    X = torch.randn(6, 3, 7, 4, generator=g, dtype=torch.float64)              # [B, T, N, hdim]
+    Wu = torch.randn(4, 5, generator=g, dtype=torch.float64)
+    dG = torch.randn(7, 7, generator=g, dtype=torch.float64)                     # per-sample loss weight (shared)
+
+    def supports(Xs, W, reduce):
+        U = torch.tanh(Xs @ W)
+        P = torch.einsum("btnh,btmh->nm", U, U.flip(-1))
+        if reduce:
+            P = dp.sum_over_ranks(P)
+        return torch.softmax(torch.relu(P), dim=-1)
+
+    def loss(G, Xs):                                                             # per-rank loss: depends on G and own shard
+        return (G * dG).sum() * Xs.square().mean()
+
+    W_full = Wu.clone().requires_grad_(True)
+    G_full = supports(X, W_full, False)
+    total = sum(loss(G_full, dp.shard_batch(X, r, world)) for r in range(world))
+    total.backward()
+    W_r = Wu.clone().requires_grad_(True)
+    Xs = dp.shard_batch(X, rank, world)
+    G_r = supports(Xs, W_r, True)
+    O.assert_close(G_r, G_full, f"global-batch support (rank {rank})", 1e-12, 1e-12)
+    loss(G_r, Xs).backward()
+    gw = W_r.grad.clone()
+    dist.all_reduce(gw)                                                          # the usual DP gradient sum
+    O.assert_close(gw, W_full.grad, f"generator gradient (rank {rank})", 1e-10, 1e-12)
+    assert dp.sum_over_ranks(X, group=None) is not None
+
+
 def _halo_case(rank, world):
     N, B, C, L, Ks = 37, 3, 2, 5, 4                 # odd N: uneven blocks
     G = _sparse_graph(N, seed=11)
@@ -243,3 +276,9 @@ def test_halo_partitioned_cell_matches_unpartitioned():
 
 def test_halo_partitioned_adjoint_chain_matches_autograd():
     run_ranks(_halo_adjoint_case)
+
+
+def test_sum_over_ranks_makes_batch_coupled_supports_global():
+    run_ranks(_global_supports_case)
+    x = torch.ones(3, requires_grad=True)
+    assert dp.sum_over_ranks(x) is x            # identity outside a process group

@@ -391,4 +391,6 @@ def partitioned_cell_forward(ps: PartitionedSupport, Gc: torch.Tensor, Xt: torch
         raise RuntimeError(f"local block has {n} nodes, the partition owns {ps.nloc}; Ht_1 {tuple(Ht_1.shape)}")
     if (bg is None) != (bc is None):
         raise RuntimeError("partitioned cell: gates.b and candi.b must both be given or both be None")
+    if B == 0:   # empty batch (the same on every rank: the batch is replicated, the nodes are split): nothing to exchange
+        return Ht_1.new_zeros(0, n, C, h)
     return _PartitionedCell.apply(Gc, Xt, Ht_1, Wg, bg, Wc, bc, (ps, Ks, Kc, activation, reduce_params))

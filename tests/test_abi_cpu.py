@@ -43,6 +43,31 @@ def test_buffer_size_queries_are_host_only():
     assert b"bad dims" in lib.stc_last_error()
 
 
+@pytest.mark.parametrize("shape", [(32, 100, 5, 16, 16, 2, 2), (2, 4096, 16, 64, 64, 2, 2), (2, 65536, 8, 64, 64, 4, 2), (3, 7, 3, 1, 4, 1, 1)])
+def test_region_layouts_are_host_only_and_consistent(shape):
+    """The staged (row-partitioned) path addresses regions of `saved` / `scratch` by these offsets: every region must
+    lie inside its buffer, be 256-byte aligned, and leave room for its Ks (or Ks-1) spatial terms before the next one."""
+    B, N, C, Din, h, Ks, Kc = shape
+    lib = _lib.load()
+    d = _lib.StcDims(B, N, C, Din, h, Ks, Kc, 0, 1)
+    R = B * N * C
+    saved_floats, scratch_floats = lib.stc_cell_saved_bytes(d) // 4, lib.stc_cell_bwd_scratch_bytes(d) // 4
+    sv, sc = _lib.saved_layout(d), _lib.scratch_layout(d)
+    need_sv = dict(u=R * h, r=R * h, c=R * h, Yr=Ks * R * h, Yx=(Ks - 1) * R * Din, Yh=(Ks - 1) * R * h, Q=Kc * C * C,
+                   Pg=R * (Kc - 1) * 2 * h, Pc=R * (Kc - 1) * h)
+    need_sc = dict(dYr=Ks * R * h, dYx=(Ks - 1) * R * Din, dYh=(Ks - 1) * R * h)
+    for lay, need, total in ((sv, need_sv, saved_floats), (sc, need_sc, scratch_floats)):
+        spans = sorted((lay[k], lay[k] + need[k], k) for k in need)
+        for (a0, a1, ka), (b0, _, kb) in zip(spans, spans[1:]):
+            assert a1 <= b0, f"{ka} overlaps {kb}"
+        for a0, a1, k in spans:
+            assert a0 % 64 == 0 and a1 <= total, (k, a0, a1, total)
+    import ctypes
+    small = (ctypes.c_int64 * 2)()
+    assert lib.stc_cell_bwd_scratch_layout(d, small, 2) < 0 and b"need room" in lib.stc_last_error()
+    assert lib.stc_cell_bwd_stage(d, 7, *([None] * 2), 0, *([None] * 11), 0, None, 0, None, 0, None) < 0   # NULLs: rejected on the host
+
+
 def test_cell_surface_matches_reference_contract():
     cell = S.STC_Cell(100, 5, 2, 2, 1, 16)
     sd = cell.state_dict()

@@ -304,8 +304,15 @@ def test_config3_grid4096_f64_csr_cell():
     Hn, g = run_cuda_cell(t, cfg, Gs_override=csr)
     Hn_o, g_o = oracle_cell_with_grads(t, cfg)
     O.assert_close(Hn, Hn_o, "config3 Hn")
-    for k in ("dXt", "dH", "dWg", "dWc", "dbg", "dbc", "dGc"):
+    for k in ("dXt", "dH", "dbg", "dbc", "dGc"):
         O.assert_close(g[k], g_o[k], f"config3 {k}")
+    # dW sums 65,536 rows.  The reference-shaped fp32 evaluation on the CPU (MKL) is itself off by 1.0e-5 (dWg) and
+    # 6.5e-6 (dWc) x mean|ref| from fp64 on exactly this case, i.e. it sits ON the per-cell allowance of 1e-5 x mean|ref|;
+    # the tensor-core path measures the same 1.0e-5 / 6.7e-6 (profiles/r2c_config3_error_margins.jsonl, +-1e-6 from the
+    # order of its atomics).  As for the 24-cell stack, the check of these two tensors states that floor: rtol 1e-4 +
+    # 3e-5 x mean|ref|.
+    for k in ("dWg", "dWc"):
+        O.assert_close(g[k], g_o[k], f"config3 {k}", atol_scale=3e-5)
 
 
 def test_config4_knn65536_csr_forward():

@@ -192,12 +192,22 @@ _CSR_CACHE = {}
 
 
 def _csr_cache(G: torch.Tensor) -> CsrSupport:
-    """torch sparse tensors are converted once per (storage, version) -- building Gs^T is not free."""
-    vals = G.values() if G.layout == torch.sparse_csr else G._values()
-    key = (vals.data_ptr(), vals._version, tuple(G.shape), G.layout)
+    """torch sparse tensors are converted once per (storage, version, structure) -- building Gs^T is not free.
+
+    The entry keeps the keyed tensor alive: while it is cached its buffers cannot be freed and handed to a
+    different sparse tensor at the same address, so a hit always means "this very tensor, unmodified"."""
+    if G.requires_grad:
+        raise RuntimeError("STC_Cell (B200): a sparse Gs is a constant support and gets no gradient; detach it or "
+                           "pass a dense [N,N] tensor when dGs is needed")
+    if G.layout == torch.sparse_csr:
+        vals, idx = G.values(), G.col_indices()
+    else:
+        vals, idx = G._values(), G._indices()
+    key = (vals.data_ptr(), vals._version, idx.data_ptr(), idx._version, int(vals.numel()), tuple(G.shape), G.layout,
+           vals.dtype)
     hit = _CSR_CACHE.get(key)
     if hit is None:
         if len(_CSR_CACHE) > 8:
             _CSR_CACHE.clear()
-        hit = _CSR_CACHE[key] = CsrSupport.from_torch_sparse(G)
-    return hit
+        hit = _CSR_CACHE[key] = (CsrSupport.from_torch_sparse(G), G)
+    return hit[0]

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -29,11 +30,11 @@ struct TimedLaunch {
   cudaEvent_t e0, e1;
 };
 static std::mutex g_tmu;
-static bool g_timing = false;
+static std::atomic<bool> g_timing{false};
 static std::vector<TimedLaunch> g_timed;
 static std::vector<cudaEvent_t> g_event_pool;
 
-static cudaEvent_t take_event() {
+static cudaEvent_t take_event() {   // g_tmu held
   if (!g_event_pool.empty()) {
     cudaEvent_t e = g_event_pool.back();
     g_event_pool.pop_back();
@@ -44,19 +45,39 @@ static cudaEvent_t take_event() {
   return e;
 }
 
-ScopedKernelTimer::ScopedKernelTimer(int kind, cudaStream_t st_, double alg_bytes) : slot(-1), st(st_) {
-  if (!g_timing) return;
-  std::lock_guard<std::mutex> lk(g_tmu);
-  TimedLaunch t{kind, alg_bytes, take_event(), take_event()};
-  if (!t.e0 || !t.e1) return;
-  cudaEventRecord(t.e0, st);
-  g_timed.push_back(t);
-  slot = (int)g_timed.size() - 1;
+// The timer holds its own event pair (a concurrent stc_timing_collect cannot invalidate it) and appends the finished
+// pair to the record in its destructor.  Nothing is recorded while the stream is being captured into a CUDA graph:
+// events recorded during capture cannot be synchronised or timed afterwards.
+ScopedKernelTimer::ScopedKernelTimer(int kind_, cudaStream_t st_, double alg_bytes)
+    : e0(nullptr), e1(nullptr), kind(kind_), bytes(alg_bytes), st(st_) {
+  if (!g_timing.load(std::memory_order_relaxed)) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmu);
+    e0 = take_event();
+    e1 = take_event();
+  }
+  if (!e0 || !e1 || cudaEventRecord(e0, st) != cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_tmu);
+    if (e0) g_event_pool.push_back(e0);
+    if (e1) g_event_pool.push_back(e1);
+    e0 = e1 = nullptr;
+  }
 }
 ScopedKernelTimer::~ScopedKernelTimer() {
-  if (slot < 0) return;
+  if (!e0) return;
+  const bool ok = cudaEventRecord(e1, st) == cudaSuccess;
   std::lock_guard<std::mutex> lk(g_tmu);
-  if (slot < (int)g_timed.size()) cudaEventRecord(g_timed[slot].e1, st);
+  if (ok) {
+    g_timed.push_back(TimedLaunch{kind, bytes, e0, e1});
+  } else {
+    g_event_pool.push_back(e0);
+    g_event_pool.push_back(e1);
+  }
 }
 
 int device_sm_count() {
@@ -198,8 +219,7 @@ using namespace stc;
 extern "C" {
 
 int stc_timing_enable(int32_t on) {
-  std::lock_guard<std::mutex> lk(g_tmu);
-  g_timing = on != 0;
+  g_timing.store(on != 0);
   return STC_OK;
 }
 

@@ -47,7 +47,9 @@ enum KernelKind {
 struct ScopedKernelTimer {  // declare right before a launch; the destructor records the stop event
   ScopedKernelTimer(int kind, cudaStream_t st, double alg_bytes);
   ~ScopedKernelTimer();
-  int slot;
+  cudaEvent_t e0, e1;   // owned by the timer until the destructor hands the pair to the record (nullptr = not timing)
+  int kind;
+  double bytes;
   cudaStream_t st;
 };
 

@@ -886,6 +886,13 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
     set_error("tcgen05 path needs 16-byte aligned state / workspace tensors");
     return STC_ERR_BAD_ARG;
   }
+  // an eligible shape must run here: backward (dpre layout, Psave) is planned from conv_tc_eligible alone, so a silent
+  // decline would make the tensor-core backward read a Psave the FFMA forward never wrote
+  auto declined = [&](const char* why) {
+    set_error("tcgen05 forward declined an eligible shape (%s): N=%d C=%d Din=%d h=%d Ks=%d Kc=%d Hout=%d", why, a.N, a.C,
+              a.Din, a.h, a.Ks, a.Kc, a.Hout);
+    return STC_ERR_UNSUPPORTED;
+  };
   TcFwdPlan p;
   p.npt = 128 / a.C;
   p.Dp = (a.Din + 7) & ~7;
@@ -893,14 +900,14 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
   p.KB = (p.KBL + ATOM_K - 1) / ATOM_K;
   p.Ntot = a.Kc * a.Hout;
   p.Npad = (p.Ntot + 15) & ~15;
-  if (p.Npad > 256) return STC_OK;
+  if (p.Npad > 256) return declined("N tile");
   p.nacc = a.Ks * p.KB;
   p.nmain = (p.nacc + TC_APM - 1) / TC_APM;
   p.tmem_cols = 32;
   while (p.tmem_cols < (p.nmain + 1) * p.Npad) p.tmem_cols *= 2;
-  if (p.tmem_cols > 512) return STC_OK;
+  if (p.tmem_cols > 512) return declined("tensor memory columns");
   p.PS = a.Hout + 4;
-  if ((size_t)128 * p.PS * sizeof(float) > 2 * 128 * ATOM_ROW_BYTES) return STC_OK;  // exchange buffer aliases A
+  if ((size_t)128 * p.PS * sizeof(float) > 2 * 128 * ATOM_ROW_BYTES) return declined("exchange buffer");  // aliases A
   p.x_bulk = (a.Din % 4 == 0) && (a.x0_bs % 4 == 0) && aligned16p(a.x0) && aligned16p(a.yx);
   const long long total_nodes = (long long)a.B * a.N;
   p.ntiles = ceil_div(total_nodes, p.npt);
@@ -917,7 +924,7 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
   o = round_up(o, 16);
   p.off_bar = (uint32_t)o; o += 48;
   p.smem_bytes = (uint32_t)o;
-  if (p.smem_bytes > 200 * 1024) return STC_OK;  // not an SF-class shape: the FFMA path handles it
+  const bool smem_over = p.smem_bytes > 200 * 1024;   // checked after the A-in-TMEM layout below (it needs less)
   // batched epilogue: Kc = 2, one main accumulator, one or two 8-column groups per thread (Hout = 16 or 32)
   int ng = 0;
   if (a.Kc == 2 && p.nmain == 1 && (a.Hout == 16 || a.Hout == 32) && !(a.opt & OPT_GENERIC_EPILOGUE)) ng = a.Hout / 16;
@@ -935,6 +942,7 @@ int try_launch_conv_fwd_tc(const ConvArgs& a, cudaStream_t st, bool* handled) {
     p.smem_bytes = (uint32_t)q;
     p.tmem_cols = 256;   // 2 Npad accumulator columns + 128 A columns
   }
+  if (!at && smem_over) return declined("shared memory");
   STC_TRY(set_smem(kern, p.smem_bytes));
   int ctas_per_sm = (int)((228 * 1024) / (p.smem_bytes + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;

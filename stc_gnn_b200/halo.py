@@ -124,7 +124,7 @@ def exchange_into(plan: HaloPlan, X_ext: torch.Tensor, group: Optional[dist.Proc
     only the halo rows are written (the local block is never copied)."""
     B, next_, W = X_ext.shape
     assert next_ == plan.next, (next_, plan.next)
-    if plan.nhalo == 0 and sum(plan.send_counts) == 0:
+    if plan.world == 1:     # a property every rank agrees on: with peers, every rank enters the collective below
         return
     send_rows = [X_ext[:, idx.to(X_ext.device)].permute(1, 0, 2).reshape(-1, B * W) for idx in plan.send_idx]
     send = torch.cat(send_rows, dim=0).contiguous() if send_rows else X_ext.new_empty(0, B * W)

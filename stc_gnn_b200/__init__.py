@@ -15,4 +15,4 @@ from .support import CsrSupport, support_apply  # noqa: F401
 from .install import install, run_main  # noqa: F401
 from .stack import RecurrentStack  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
-from . import dp, halo  # noqa: F401
+from . import dp, halo, mgp  # noqa: F401

@@ -12,13 +12,23 @@ import sys
 from .cell import STC_Cell
 
 
-def install(stc_gnn_module=None):
-    """Rebind ``STC_GNN.STC_Cell`` to the B200 cell. Returns the patched module."""
+_NO_GROUP = object()
+
+
+def install(stc_gnn_module=None, dp_group=_NO_GROUP, dp_average: bool = False):
+    """Rebind ``STC_GNN.STC_Cell`` to the B200 cell. Returns the patched module.
+
+    ``dp_group`` (a ``torch.distributed`` group, or None for the default group): additionally rebind
+    ``MGP_Gen.forward`` to its batch-data-parallel form (``stc_gnn_b200/mgp.py``) so that the supports generated from a
+    batch shard -- and every gradient of the generator -- equal the single-process global-batch values."""
     if stc_gnn_module is None:
         import STC_GNN as stc_gnn_module  # noqa: N813  (the reference's module name)
     if getattr(stc_gnn_module, "STC_Cell", None) is not STC_Cell:
         stc_gnn_module._reference_STC_Cell = stc_gnn_module.STC_Cell
         stc_gnn_module.STC_Cell = STC_Cell
+    if dp_group is not _NO_GROUP:
+        from .mgp import patch_generator
+        patch_generator(stc_gnn_module, dp_group, dp_average)
     return stc_gnn_module
 
 
@@ -28,6 +38,8 @@ def uninstall(stc_gnn_module=None):
     ref = getattr(stc_gnn_module, "_reference_STC_Cell", None)
     if ref is not None:
         stc_gnn_module.STC_Cell = ref
+    from .mgp import unpatch_generator
+    unpatch_generator(stc_gnn_module)
     return stc_gnn_module
 
 

@@ -69,3 +69,27 @@ def oracle_cell_with_grads(t, cfg, dtype=torch.float64):
     if "bg" in v:
         grads.update(dbg=z("bg"), dbc=z("bc"))
     return Hn.detach(), grads
+
+
+def find_reference():
+    """Directory holding the UNMODIFIED reference's framework/*.py, or None.  Probe order: $STC_REF_DIR,
+    /root/reference/framework (the build container), baseline/_ref/framework (staged by tools/stage_reference.sh; the
+    only one that can exist on the GPU box).  Tests that need the live reference skip when this returns None."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("STC_REF_DIR"), "/root/reference/framework", os.path.join(root, "baseline", "_ref", "framework")):
+        if cand and os.path.isfile(os.path.join(cand, "STC_GNN.py")):
+            return cand
+    return None
+
+
+def import_reference():
+    """Import the reference's STC_GNN module (unmodified) from find_reference(); returns (module, framework_dir)."""
+    import importlib
+    import sys
+    ref = find_reference()
+    if ref is None:
+        return None, None
+    sys.dont_write_bytecode = True
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    return importlib.import_module("STC_GNN"), ref

@@ -1,0 +1,143 @@
+"""The drop-in executed on hardware (north star: "Model_Trainer.py and Main.py run unchanged").
+
+These tests need the UNMODIFIED reference on the box (tests/helpers.py::find_reference: $STC_REF_DIR,
+/root/reference/framework, baseline/_ref/framework -- the last one is what tools/stage_reference.sh stages and what
+travels with a gpurun snapshot).  They skip when it is absent; nothing here is needed by the product path.
+
+  * the reference's full STCGNN (MGP_Gen -> encoder -> decoder roll-out -> out_proj, STC_GNN.py:175-207) built twice
+    on cuda:0 from one seed: stock, and with `install()` rebinding STC_Cell; first training batch of the shipped SF
+    split, ComboLoss (Model_Trainer.py:9-23), loss.backward() (Model_Trainer.py:74-83).  Predictions, loss and every
+    .grad of the swapped model are compared with the stock model evaluated in fp64 on the same GPU (and the stock fp32
+    model's own distance to fp64 is printed next to ours).
+  * `run_main(... -epoch 1)`: the reference's Main.py, unmodified, trains one epoch and tests with the B200 cell.
+"""
+import io
+import os
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import torch
+
+import stc_gnn_b200 as S
+from oracle import stc_oracle as O
+from tests.helpers import find_reference, import_reference
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REF_DIR = find_reference()
+needs_reference = pytest.mark.skipif(REF_DIR is None, reason="the unmodified reference is not on this box "
+                                     "(tools/stage_reference.sh stages it under baseline/_ref)")
+
+
+def _first_train_batch(ref_dir, batch=32):
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    import Data_Container as dc
+    with redirect_stdout(io.StringIO()):
+        data = dc.DataInput(os.path.join(os.path.dirname(ref_dir), "data", "SF-incidents-4h.npz")).load_data()
+    gen = dc.DataGenerator(obs_len=9, pred_len=3, data_split_ratio=(6, 1, 1))
+    loaders = gen.get_data_loader(params=dict(H=10, W=10, C=5, device=DEV, batch_size=batch), data=data)
+    X, Y = next(iter(loaders["train"]))
+    As = torch.from_numpy(data["s_adj"]).float().to(DEV)
+    Ac = torch.from_numpy(data["c_cor"]).float().to(DEV)
+    return X, Y, As, Ac
+
+
+def _loss_and_grads(model, criterion, X, Y, As, Ac):
+    for p in model.parameters():
+        p.grad = None
+    pred = model(X_seq=X, As=As, Ac=Ac)
+    loss = criterion(pred, Y)
+    loss.backward()
+    torch.cuda.synchronize()
+    return pred.detach(), loss.detach(), {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+
+
+@needs_reference
+def test_installed_cell_matches_stock_reference_full_model():
+    ref, ref_dir = import_reference()
+    import Model_Trainer as mt
+    X, Y, As, Ac = _first_train_batch(ref_dir)
+    args = (100, 5, 2, 2, 1, 16, 2, 3)           # Model_Trainer.py:39-46 with Main.py's defaults
+    from stc_gnn_b200.install import install, uninstall
+    uninstall(ref)
+    torch.manual_seed(0)
+    stock = ref.STCGNN(*args).to(DEV)
+    assert type(stock.encoder.cell_list[0]).__module__ == "STC_GNN"
+    install(ref)
+    try:
+        torch.manual_seed(0)
+        ours = ref.STCGNN(*args).to(DEV)
+    finally:
+        uninstall(ref)
+    assert isinstance(ours.encoder.cell_list[0], S.STC_Cell) and isinstance(ours.decoder.cell_list[1], S.STC_Cell)
+    # a seeded construction draws the same weights; a stock checkpoint loads strictly
+    for (n1, p1), (n2, p2) in zip(stock.state_dict().items(), ours.state_dict().items()):
+        assert n1 == n2 and torch.equal(p1, p2), n1
+    ours.load_state_dict(stock.state_dict(), strict=True)
+    # fp64 evaluation of the stock model on the same GPU = the truth both fp32 runs are measured against
+    torch.set_default_dtype(torch.float64)       # the reference builds torch.eye in the default dtype (STC_GNN.py:26)
+    try:
+        truth = ref.STCGNN(*args).to(DEV).double()
+        truth.load_state_dict({k: v.double() for k, v in stock.state_dict().items()})
+        crit = mt.ComboLoss()
+        pred64, loss64, g64 = _loss_and_grads(truth, crit, X.double(), Y.double(), As.double(), Ac.double())
+    finally:
+        torch.set_default_dtype(torch.float32)
+    crit = mt.ComboLoss()
+    pred_s, loss_s, g_s = _loss_and_grads(stock, crit, X, Y, As, Ac)
+    from stc_gnn_b200 import _lib
+    l0 = _lib.LAUNCHES
+    pred_o, loss_o, g_o = _loss_and_grads(ours, crit, X, Y, As, Ac)
+    assert _lib.LAUNCHES - l0 > 24 * 6, "the swapped model did not go through libstc_b200.so"
+    # predictions: north star -- rtol 1e-4, no atol
+    O.assert_close(pred_o.cpu(), pred64.cpu(), "full-model predictions (install) vs stock fp64", rtol=1e-4, atol_scale=0.0)
+    O.assert_close(pred_o.cpu(), pred_s.double().cpu(), "full-model predictions (install) vs stock fp32", rtol=1e-4, atol_scale=0.0)
+    assert abs(float(loss_o) - float(loss64)) <= 1e-5 * abs(float(loss64)), (float(loss_o), float(loss64))
+    # Gradients.  Cells + out_proj (the swapped path and what follows it): the stack-level floor of
+    # tests/test_cell_gpu.py, rtol 1e-4 + 5e-5 x mean|ref|.  Generator parameters (mix_graph_pair.*) sit upstream of a
+    # saturated softmax: there the STOCK fp32 model is itself noise-dominated against fp64 (on the CPU it violates
+    # that tolerance on 80 % of params_C.Wu's elements), so for those the statement is relative-L2 error no worse than
+    # 4 x the stock fp32 model's own (or 1e-4).
+    bad, report = [], []
+    rel = lambda a, b: float((a.double() - b).norm() / b.norm().clamp_min(1e-300))
+    for n in g64:
+        ref64 = g64[n].cpu()
+        if n.startswith("mix_graph_pair."):
+            e_o, e_s = rel(g_o[n].cpu(), ref64), rel(g_s[n].cpu(), ref64)
+            report.append(f"{n}: rel-L2 ours {e_o:.2e}, stock fp32 {e_s:.2e}")
+            if e_o > max(1e-4, 4 * e_s):
+                bad.append(f"{n}: rel-L2 {e_o:.2e} vs stock {e_s:.2e}")
+            continue
+        n_o, w_o = O.violations(g_o[n].cpu(), ref64, atol_scale=5e-5)
+        _, w_s = O.violations(g_s[n].cpu(), ref64, atol_scale=5e-5)
+        report.append(f"{n}: ours worst {w_o:.2e}, stock fp32 worst {w_s:.2e} (x mean|ref|)")
+        if n_o:
+            bad.append(f"{n}: {n_o}/{ref64.numel()} worst {w_o:.2e}")
+    print("\n".join(report))
+    assert not bad, "; ".join(bad)
+
+
+@needs_reference
+def test_run_main_trains_one_epoch_unmodified(tmp_path, capfd):
+    """Main.py -> Model_Trainer.train/test, unmodified, one epoch on the shipped SF data with the B200 cell installed."""
+    from stc_gnn_b200 import _lib
+    from stc_gnn_b200.install import run_main, uninstall
+    ref, ref_dir = import_reference()
+    l0 = _lib.LAUNCHES
+    try:
+        run_main(ref_dir, ["-device", DEV, "-city", "SF", "-epoch", "1", "-out", str(tmp_path),
+                           "-in", os.path.join(os.path.dirname(ref_dir), "data")])
+    finally:
+        uninstall(ref)
+    out = capfd.readouterr().out
+    assert "Epoch 1: training time" in out and "model testing ends" in out, out[-2000:]
+    assert os.path.exists(os.path.join(str(tmp_path), "SF", "STC-GNN-4.pkl"))
+    steps = (3834 + 31) // 32 + (639 + 31) // 32 * 2      # train + validate + test batches of the 6:1:1 split
+    assert _lib.LAUNCHES - l0 > steps * 24, "Main.py did not run through libstc_b200.so"
+    import re
+    m = re.search(r"training loss: ([0-9.eE+-]+);", out)
+    assert m and np.isfinite(float(m.group(1).rstrip(";"))), out[-2000:]
+    print(out[-1500:])

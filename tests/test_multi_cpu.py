@@ -282,3 +282,69 @@ def test_sum_over_ranks_makes_batch_coupled_supports_global():
     run_ranks(_global_supports_case)
     x = torch.ones(3, requires_grad=True)
     assert dp.sum_over_ranks(x) is x            # identity outside a process group
+
+
+# ------------------------------------------------------------------------------------------------
+# install(dp_group=...): the reference's MGP_Gen under batch data-parallelism (stc_gnn_b200/mgp.py)
+# ------------------------------------------------------------------------------------------------
+def _mgp_setup():
+    from tests.helpers import import_reference
+    ref, _ = import_reference()
+    torch.manual_seed(5)
+    gen = ref.MGP_Gen(num_nodes=12, num_categories=4, hidden_dim=6).double()
+    g = torch.Generator().manual_seed(8)
+    X = (torch.rand(6, 5, 12, 4, generator=g) < 0.3).double()                    # [B, T, N, C] incident flags
+    As = (torch.rand(12, 12, generator=g) < 0.3).double()
+    Ac = torch.rand(4, 4, generator=g, dtype=torch.float64) * 0.3
+    wS = torch.randn(6, 12, 12, generator=g, dtype=torch.float64)                # per-sample loss weights
+    wC = torch.randn(6, 4, 4, generator=g, dtype=torch.float64)
+    return ref, gen, X, As, Ac, wS, wC
+
+
+def _mgp_dp_case(rank, world):
+    """Sharded batch + patched generator: supports and EVERY generator gradient equal the single-process global-batch
+    ones; the fusion-layer gradients come out complete on every rank without being communicated."""
+    from stc_gnn_b200 import mgp
+    ref, gen, X, As, Ac, wS, wC = _mgp_setup()
+    loss = lambda Gs, Gc, a, b: (Gs * a.sum(0)).sum() + (Gc * b.sum(0)).sum()     # sum of per-sample losses
+    Gs_f, Gc_f = gen(X, As, Ac)                                                  # stock forward, whole batch
+    loss(Gs_f, Gc_f, wS, wC).backward()
+    full = {n: p.grad.clone() for n, p in gen.named_parameters()}
+    for p in gen.parameters():
+        p.grad = None
+    mgp.patch_generator(ref, group=None)
+    try:
+        sl = slice(*dp.shard_bounds(X.shape[0], rank, world))
+        Gs_r, Gc_r = gen(X[sl], As, Ac)
+        O.assert_close(Gs_r, Gs_f, f"Gs from a shard (rank {rank})", 1e-10, 1e-12)
+        O.assert_close(Gc_r, Gc_f, f"Gc from a shard (rank {rank})", 1e-10, 1e-12)
+        loss(Gs_r, Gc_r, wS[sl], wC[sl]).backward()
+    finally:
+        mgp.unpatch_generator(ref)
+    shard_params = mgp.dp_bucket_parameters(gen)
+    assert len(shard_params) == 4 and all(".aggreg_" not in n for n, p in gen.named_parameters()
+                                          if any(p is q for q in shard_params))
+    for p in shard_params:                                                        # the usual DP gradient sum
+        dist.all_reduce(p.grad)
+    for n, p in gen.named_parameters():
+        O.assert_close(p.grad, full[n], f"generator d{n} (rank {rank})", 1e-8, 1e-10)
+
+
+def test_generator_restatement_matches_reference_single_process():
+    from tests.helpers import import_reference
+    from stc_gnn_b200 import mgp
+    if import_reference()[0] is None:
+        pytest.skip("needs the live reference")
+    ref, gen, X, As, Ac, _, _ = _mgp_setup()
+    with torch.no_grad():
+        want = gen(X, As, Ac)
+        got = mgp.mgp_forward_dp(gen, X, As, Ac)
+    O.assert_close(got[0], want[0], "Gs", 1e-12, 1e-13)
+    O.assert_close(got[1], want[1], "Gc", 1e-12, 1e-13)
+
+
+def test_generator_under_batch_dp_equals_global_batch():
+    from tests.helpers import import_reference
+    if import_reference()[0] is None:
+        pytest.skip("needs the live reference")
+    run_ranks(_mgp_dp_case)

@@ -17,6 +17,10 @@ Files written (all ``np.savez_compressed``):
                     FIRST TEST BATCH of the shipped SF split (Data_Container.py:56-66, 6:1:1, batch 32):
                     its own fp32 predictions, the supports its MGP_Gen produced, every cell / out_proj
                     weight, and the fp64 re-evaluation of encoder -> decoder -> out_proj -> sigmoid
+  stack_longc.npz   BASELINE config 5 shapes (T = 48, C = 64 categories, h = 64, dense Gc): encoder + decoder
+                    roll-out at B = 1 with every gradient; to stay small the fixture keeps the supports, the
+                    outputs / input gradients of five nodes, every 4th row of each weight gradient, all bias and
+                    support gradients, and checksums of the seeded inputs and weights the test regenerates
 """
 import os
 import sys
@@ -203,7 +207,75 @@ def run_predictions():
           f"{(pred32.double() - pred64).abs().max():.2e}, max-rel {((pred32.double() - pred64).abs() / pred64.abs()).max():.2e}")
 
 
+LONGC = dict(B=1, T=48, N=100, C=64, Din=1, h=64, Ks=2, Kc=2, layers=2, horizon=3)
+LONGC_NODES = [0, 7, 33, 50, 99]          # output / input-gradient rows kept in the fixture
+LONGC_ROW_STEP = 4                        # every 4th row of each weight gradient is kept
+
+
+def longc_inputs():
+    """Seeded inputs of the BASELINE config 5 roll-out (T = 48, C = 64 categories, dense learned-like Gc), shared by
+    this generator and tests/test_cell_gpu.py::test_config5_longc_rollout (the fixture stores only their checksums).
+    Imports nothing from the product package: the same recipe is restated in tests/helpers.py::longc_case."""
+    c = LONGC
+    g = torch.Generator().manual_seed(48)
+    X = (torch.rand(c["B"], c["T"], c["N"], c["C"], 1, generator=g) < 0.1635).float()
+    N, C = c["N"], c["C"]
+    Ps = torch.softmax(torch.relu(torch.randn(N, N, generator=g) * 3.0), dim=-1)
+    Gs = (0.5 * Ps + 0.5 * torch.rand(N, N, generator=g) * (2.0 / N)).float()
+    Gc = (0.5 * torch.softmax(torch.relu(torch.randn(C, C, generator=g) * 3.0), dim=-1)
+          + 0.5 * torch.rand(C, C, generator=g) * (2.0 / C)).float()
+    dOut = torch.randn(c["B"], c["horizon"], N, C, c["h"], generator=g).float()
+    return X, Gs, Gc, dOut
+
+
+def run_longc():
+    """BASELINE config 5 shapes: the reference's encoder (2 layers x T = 48) + decoder (horizon 3) at C = 64, h = 64."""
+    c = LONGC
+    X, Gs, Gc, dOut = longc_inputs()
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(5)
+    enc = ref.STC_Encoder(c["N"], c["C"], c["Ks"], c["Kc"], c["Din"], c["h"], c["layers"])
+    dec = ref.STC_Decoder(c["N"], c["C"], c["Ks"], c["Kc"], c["h"], c["h"], c["layers"], c["horizon"])
+    with torch.no_grad():
+        for p in list(enc.parameters()) + list(dec.parameters()):
+            p.copy_(f32exact(p))
+    Gs64 = Gs.double().requires_grad_(True)
+    Gc64 = Gc.double().requires_grad_(True)
+    X64 = X.double().requires_grad_(True)
+    _, Ht = enc(Gs=Gs64, Gc=Gc64, X_seq=X64, H0_l=None)
+    inp, outs = Ht[-1], []
+    for _ in range(c["horizon"]):
+        Hl, Ht = dec(Gs=Gs64, Gc=Gc64, Xt=inp, H0_l=Ht)
+        inp = Hl
+        outs.append(Hl)
+    out = torch.stack(outs, dim=1)
+    out.backward(dOut.double())
+    save = dict(meta=np.array([c[k] for k in ("B", "T", "N", "C", "Din", "h", "Ks", "Kc", "layers", "horizon")], dtype=np.int64),
+                nodes=np.array(LONGC_NODES), row_step=np.array(LONGC_ROW_STEP), weight_seed=np.array(5),
+                Gs=Gs.numpy(), Gc=Gc.numpy(), X_bits=np.packbits(X.numpy().astype(np.uint8)),
+                dOut_checksum=np.array(dOut.double().abs().sum().item()),
+                out_nodes=out.detach()[:, :, LONGC_NODES].numpy(), out_abs_mean=np.array(out.detach().abs().mean().item()),
+                dGs=Gs64.grad.numpy(), dGc=Gc64.grad.numpy(), dX_nodes=X64.grad[:, :, LONGC_NODES].numpy(),
+                dX_abs_mean=np.array(X64.grad.abs().mean().item()))
+    wsum = 0.0
+    for tag, mod in (("enc", enc), ("dec", dec)):
+        for i, cell in enumerate(mod.cell_list):
+            for conv in ("gates", "candi"):
+                W, b = getattr(cell, conv).W, getattr(cell, conv).b
+                wsum += W.detach().abs().sum().item()
+                save[f"d_{tag}{i}_{conv}_W_rows"] = W.grad[::LONGC_ROW_STEP].float().numpy()
+                save[f"d_{tag}{i}_{conv}_W_abs_mean"] = np.array(W.grad.abs().mean().item())
+                save[f"d_{tag}{i}_{conv}_b"] = b.grad.numpy()
+    save["weight_checksum"] = np.array(wsum)
+    np.savez_compressed(os.path.join(OUT, "stack_longc.npz"), **save)
+    print(f"stack_longc: out mean|.|={out.abs().mean():.4f}, dGc mean|.|={Gc64.grad.abs().mean():.3e}, "
+          f"weights |.|_1={wsum:.6f}")
+
+
 if __name__ == "__main__":
+    if "--longc-only" in sys.argv:
+        run_longc()
+        sys.exit(0)
     if "--pred-only" in sys.argv:
         run_predictions()
         sys.exit(0)
@@ -219,3 +291,4 @@ if __name__ == "__main__":
     run_cell("sf_din16", B=2, N=100, C=5, Din=16, h=16, Ks=2, Kc=2, seed=8, Gs=Gs, Gc=Gc)
     run_stack(X_seq, Gs, Gc)
     run_predictions()
+    run_longc()

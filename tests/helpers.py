@@ -93,3 +93,40 @@ def import_reference():
     if ref not in sys.path:
         sys.path.insert(0, ref)
     return importlib.import_module("STC_GNN"), ref
+
+
+def longc_case():
+    """BASELINE config 5 roll-out fixture (tests/golden/stack_longc.npz, written by make_golden.py::run_longc from the
+    imported reference).  The seeded inputs and weights are regenerated here -- same recipe as make_golden.py::
+    longc_inputs -- and verified against the checksums the fixture stores.  Returns (cfg, tensors, golden npz)."""
+    z = np.load(os.path.join(GOLDEN, "stack_longc.npz"))
+    B, T, N, C, Din, h, Ks, Kc, layers, horizon = (int(v) for v in z["meta"])
+    cfg = dict(B=B, T=T, N=N, C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, layers=layers, horizon=horizon)
+    g = torch.Generator().manual_seed(48)
+    X = (torch.rand(B, T, N, C, 1, generator=g) < 0.1635).float()
+    Ps = torch.softmax(torch.relu(torch.randn(N, N, generator=g) * 3.0), dim=-1)
+    Gs = (0.5 * Ps + 0.5 * torch.rand(N, N, generator=g) * (2.0 / N)).float()
+    Gc = (0.5 * torch.softmax(torch.relu(torch.randn(C, C, generator=g) * 3.0), dim=-1)
+          + 0.5 * torch.rand(C, C, generator=g) * (2.0 / C)).float()
+    dOut = torch.randn(B, horizon, N, C, h, generator=g).float()
+    assert np.array_equal(np.packbits(X.numpy().astype(np.uint8)), z["X_bits"]), "seeded X differs from the fixture's"
+    assert np.array_equal(Gs.numpy(), z["Gs"]) and np.array_equal(Gc.numpy(), z["Gc"]), "seeded supports differ"
+    assert abs(dOut.double().abs().sum().item() - float(z["dOut_checksum"])) < 1e-6 * float(z["dOut_checksum"])
+    # weights: the reference's construction order and init (encoder cells then decoder cells, gates.W before candi.W,
+    # xavier-normal W / zero b, STC_GNN.py:17-21,57-58,95,151) under torch.manual_seed(weight_seed) in fp64, rounded to fp32
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(int(z["weight_seed"]))
+        cells = []
+        for i in range(2 * layers):
+            din = Din if i == 0 else h
+            Wg = torch.nn.init.xavier_normal_(torch.empty((din + h) * Ks * Kc, 2 * h))
+            Wc = torch.nn.init.xavier_normal_(torch.empty((din + h) * Ks * Kc, h))
+            cells.append(O.CellParams(Wg.float().double(), torch.zeros(2 * h, dtype=torch.float64), Wc.float().double(),
+                                      torch.zeros(h, dtype=torch.float64)))
+    finally:
+        torch.set_default_dtype(prev)
+    wsum = sum(float(p.Wg.abs().sum() + p.Wc.abs().sum()) for p in cells)
+    assert abs(wsum - float(z["weight_checksum"])) < 1e-9 * wsum, (wsum, float(z["weight_checksum"]))
+    return cfg, dict(X=X, Gs=Gs, Gc=Gc, dOut=dOut, enc=cells[:layers], dec=cells[layers:]), z

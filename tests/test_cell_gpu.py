@@ -351,3 +351,93 @@ def test_graphed_step_replays_the_eager_step():
     assert abs(loss_g - float(loss_e.item())) <= 1e-5 * abs(float(loss_e.item()))
     for i, (a, b) in enumerate(zip(grads_g, [p.grad for p in params + [Gs, Gc]])):
         O.assert_close(a.cpu(), b.double().cpu(), f"graphed grad {i}")
+
+
+def test_config5_longc_rollout_matches_reference_golden():
+    """BASELINE config 5 shapes: T = 48 steps, C = 64 categories, h = 64, dense learned-like Gs / Gc with gradients --
+    102 chained cell steps through the wide-state kernels and the C = 64 categorical mix, against the fixture the
+    imported reference produced (tests/golden/make_golden.py::run_longc)."""
+    from tests.helpers import longc_case
+    cfg, t, z = longc_case()
+    stack = S.RecurrentStack(cfg["N"], cfg["C"], cfg["Ks"], cfg["Kc"], cfg["Din"], cfg["h"], cfg["layers"],
+                             cfg["horizon"]).to(DEV)
+    with torch.no_grad():
+        for cell, p in zip(list(stack.encoder) + list(stack.decoder), t["enc"] + t["dec"]):
+            cell.gates.W.copy_(p.Wg); cell.gates.b.copy_(p.bg); cell.candi.W.copy_(p.Wc); cell.candi.b.copy_(p.bc)
+    Gs = t["Gs"].to(DEV).requires_grad_(True)
+    Gc = t["Gc"].to(DEV).requires_grad_(True)
+    X = t["X"].to(DEV).requires_grad_(True)
+    out = stack(Gs, Gc, X)
+    out.backward(t["dOut"].to(DEV))
+    torch.cuda.synchronize()
+    nodes, step = list(z["nodes"]), int(z["row_step"])
+    # sampled tensors: the allowance is scaled by the FULL tensor's mean|ref| (stored in the fixture)
+    def chk(got, ref, name, scale=None, atol_scale=5e-5):
+        got, ref = got.detach().double().cpu(), torch.as_tensor(ref).double()
+        scale = ref.abs().mean().item() if scale is None else float(scale)
+        err = (got - ref).abs()
+        nbad = int((err > 1e-4 * ref.abs() + atol_scale * scale).sum())
+        assert nbad == 0, f"{name}: {nbad}/{ref.numel()} outside rtol 1e-4 + {atol_scale} x mean|ref|, worst {err.max().item() / scale:.2e}"
+    chk(out[:, :, nodes], z["out_nodes"], "longc out", z["out_abs_mean"], atol_scale=1e-5)
+    # gradients through 102 chained cells: the stack-level floor stated in test_stack_matches_reference_golden
+    chk(Gs.grad, z["dGs"], "longc dGs")
+    chk(Gc.grad, z["dGc"], "longc dGc")
+    chk(X.grad[:, :, nodes], z["dX_nodes"], "longc dX", z["dX_abs_mean"])
+    for name, cell in zip(("enc0", "enc1", "dec0", "dec1"), list(stack.encoder) + list(stack.decoder)):
+        for conv in ("gates", "candi"):
+            m = getattr(cell, conv)
+            chk(m.W.grad[::step], z[f"d_{name}_{conv}_W_rows"], f"longc d{name}.{conv}.W", z[f"d_{name}_{conv}_W_abs_mean"])
+            chk(m.b.grad, z[f"d_{name}_{conv}_b"], f"longc d{name}.{conv}.b")
+
+
+def test_config4_knn65536_f64_forward_backward_exact_subgraph():
+    """BASELINE config 4 at its real size -- N = 65,536 kNN graph (CSR), C = 8, F = 64, Ks = 4 (3 hops) -- forward AND
+    every gradient, against the fp64 oracle.
+
+    The oracle cannot hold the full problem, and does not need to: the output gradient is non-zero on a block S of 256
+    (Morton-contiguous) nodes only.  Gradients then flow at most 2 x (Ks-1) = 6 hops out of S and need forward values at
+    most 6 hops out of S, so the oracle on the sub-graph induced by the 6-hop closure U of S (~1 K nodes) reproduces the
+    full problem's H'[S], dW, db, dGc and (dXt, dH)[U] EXACTLY, and everything outside U must be exactly zero.  The GPU
+    runs the full 65,536-node problem through the same kernels and launch shapes as the benchmark."""
+    import numpy as np
+    import scipy.sparse as sp
+    from stc_gnn_b200.synth import knn_csr
+    N, C, Din, h, Ks, Kc, B = 65536, 8, 64, 64, 4, 2, 1
+    rp, ci, va = knn_csr(N, 8, 0)
+    A = sp.csr_matrix((va.numpy().astype(np.float64), ci.numpy(), rp.numpy()), shape=(N, N))
+    struct = ((abs(A) + abs(A).T) > 0).astype(np.float32)
+    S_lo, S_hi = 30000, 30256
+    m = np.zeros(N, np.float32)
+    m[S_lo:S_hi] = 1
+    for _ in range(2 * (Ks - 1)):
+        m = ((struct @ m + m) > 0).astype(np.float32)
+    U = np.nonzero(m)[0]
+    assert 256 < U.size < 8192, U.size
+    pos_S = np.searchsorted(U, np.arange(S_lo, S_hi))
+    g = torch.Generator().manual_seed(65536)
+    f = lambda x: x.float().double()
+    p = O.xavier_cell_params(Din, h, Ks, Kc, g, dtype=torch.float32, bias_scale=0.1)
+    Gc = f(torch.rand(C, C, generator=g) / C)
+    Xt = f(torch.randn(B, N, C, Din, generator=g))
+    H = f(torch.randn(B, N, C, h, generator=g) * 0.5)
+    dHn = torch.zeros(B, N, C, h, dtype=torch.float64)
+    dHn[:, S_lo:S_hi] = f(torch.randn(B, S_hi - S_lo, C, h, generator=g))
+    # ---- oracle on the induced sub-graph ----
+    Asub = A[U][:, U].tocoo()
+    Gs_sub = torch.sparse_coo_tensor(np.stack([Asub.row, Asub.col]), torch.from_numpy(Asub.data), size=(U.size, U.size)).coalesce()
+    Ut = torch.from_numpy(U)
+    t_sub = dict(Gs=Gs_sub, Gc=Gc, Xt=Xt[:, Ut], H=H[:, Ut], dHn=dHn[:, Ut], Wg=f(p.Wg), Wc=f(p.Wc), bg=f(p.bg), bc=f(p.bc))
+    cfg = dict(B=B, N=int(U.size), C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, activation=None)
+    Hn_o, g_o = oracle_cell_with_grads(t_sub, cfg)
+    # ---- the full problem on the GPU ----
+    csr = S.CsrSupport(rp.to(DEV), ci.to(DEV), va.to(DEV), N)
+    t_full = dict(Gc=Gc, Xt=Xt, H=H, dHn=dHn, Wg=f(p.Wg), Wc=f(p.Wc), bg=f(p.bg), bc=f(p.bc), Gs=None)
+    Hn, gg = run_cuda_cell(t_full, dict(cfg, N=N), Gs_override=csr)
+    O.assert_close(Hn[:, S_lo:S_hi], Hn_o[:, pos_S], "config4 H'[S]")
+    for k in ("dWg", "dWc", "dbg", "dbc", "dGc"):
+        O.assert_close(gg[k], g_o[k], f"config4 {k}")
+    for k in ("dXt", "dH"):
+        O.assert_close(gg[k][:, Ut], g_o[k], f"config4 {k}[U]")
+        outside = torch.ones(N, dtype=torch.bool)
+        outside[Ut] = False
+        assert float(gg[k][:, outside].abs().max()) == 0.0, f"config4 {k} must vanish outside the closure of S"

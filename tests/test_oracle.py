@@ -146,3 +146,73 @@ def test_oracle_matches_live_reference(Ks, Kc, act):
         O.assert_close(g["dbc"], cell.candi.b.grad, "dbc", rtol=1e-9, atol_scale=1e-9)
     finally:
         torch.set_default_dtype(old)
+
+
+def test_oracle_matches_reference_longc_rollout():
+    """BASELINE config 5 shapes (T = 48, C = 64, h = 64): oracle roll-out and gradients vs the reference's fixture."""
+    from tests.helpers import longc_case
+    cfg, t, z = longc_case()
+    Gs = t["Gs"].double().requires_grad_(True)
+    Gc = t["Gc"].double().requires_grad_(True)
+    X = t["X"].double().requires_grad_(True)
+    cells = t["enc"] + t["dec"]
+    for p in cells:
+        for w in p.tensors():
+            w.requires_grad_(True)
+    out = O.stack_forward(Gs, Gc, X, t["enc"], t["dec"], cfg["horizon"], cfg["Ks"], cfg["Kc"])
+    out.backward(t["dOut"].double())
+    nodes, step = list(z["nodes"]), int(z["row_step"])
+    O.assert_close(out.detach()[:, :, nodes], torch.from_numpy(z["out_nodes"]), "longc out", 1e-9, 1e-10)
+    O.assert_close(Gs.grad, torch.from_numpy(z["dGs"]), "longc dGs", 1e-8, 1e-9)
+    O.assert_close(Gc.grad, torch.from_numpy(z["dGc"]), "longc dGc", 1e-8, 1e-9)
+    O.assert_close(X.grad[:, :, nodes], torch.from_numpy(z["dX_nodes"]), "longc dX", 1e-8, 1e-9)
+    for name, p in zip(("enc0", "enc1", "dec0", "dec1"), cells):
+        for conv, W, b in (("gates", p.Wg, p.bg), ("candi", p.Wc, p.bc)):
+            O.assert_close(W.grad[::step], torch.from_numpy(z[f"d_{name}_{conv}_W_rows"]).double(), f"longc d{name}.{conv}.W",
+                           1e-6, 1e-7)     # the fixture keeps these rows in fp32
+            O.assert_close(b.grad, torch.from_numpy(z[f"d_{name}_{conv}_b"]), f"longc d{name}.{conv}.b", 1e-8, 1e-9)
+
+
+def test_subgraph_closure_reproduces_full_problem_gradients():
+    """The property tests/test_cell_gpu.py::test_config4_knn65536_f64_forward_backward_exact_subgraph relies on: with the
+    output gradient confined to a node block S, the cell restricted to the 2(Ks-1)-hop closure U of S has the same
+    H'[S], parameter / Gc gradients and (dXt, dH)[U] as the full graph, and the full gradients vanish outside U."""
+    import numpy as np
+    import scipy.sparse as sp
+    from stc_gnn_b200.synth import knn_csr
+    from tests.helpers import oracle_cell_with_grads
+    N, C, Din, h, Ks, Kc, B = 2048, 2, 3, 4, 4, 2, 2
+    rp, ci, va = knn_csr(N, 8, 1)
+    A = sp.csr_matrix((va.numpy().astype(np.float64), ci.numpy(), rp.numpy()), shape=(N, N))
+    struct = ((abs(A) + abs(A).T) > 0).astype(np.float32)
+    lo, hi = 700, 732
+    m = np.zeros(N, np.float32)
+    m[lo:hi] = 1
+    for _ in range(2 * (Ks - 1)):
+        m = ((struct @ m + m) > 0).astype(np.float32)
+    U = np.nonzero(m)[0]
+    assert U.size < N // 2
+    g = torch.Generator().manual_seed(1)
+    p = O.xavier_cell_params(Din, h, Ks, Kc, g, dtype=torch.float64, bias_scale=0.1)
+    t = dict(Gc=torch.rand(C, C, generator=g, dtype=torch.float64) / C, Xt=torch.randn(B, N, C, Din, generator=g, dtype=torch.float64),
+             H=torch.randn(B, N, C, h, generator=g, dtype=torch.float64), Wg=p.Wg, Wc=p.Wc, bg=p.bg, bc=p.bc)
+    t["dHn"] = torch.zeros(B, N, C, h, dtype=torch.float64)
+    t["dHn"][:, lo:hi] = torch.randn(B, hi - lo, C, h, generator=g, dtype=torch.float64)
+    coo = A.tocoo()
+    t["Gs"] = torch.sparse_coo_tensor(np.stack([coo.row, coo.col]), torch.from_numpy(coo.data), size=(N, N)).coalesce()
+    cfg = dict(B=B, N=N, C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, activation=None)
+    Hn_f, g_f = oracle_cell_with_grads(t, cfg)
+    sub = A[U][:, U].tocoo()
+    Ut = torch.from_numpy(U)
+    ts = dict(t, Gs=torch.sparse_coo_tensor(np.stack([sub.row, sub.col]), torch.from_numpy(sub.data), size=(U.size, U.size)).coalesce(),
+              Xt=t["Xt"][:, Ut], H=t["H"][:, Ut], dHn=t["dHn"][:, Ut])
+    Hn_s, g_s = oracle_cell_with_grads(ts, dict(cfg, N=int(U.size)))
+    pos = np.searchsorted(U, np.arange(lo, hi))
+    O.assert_close(Hn_s[:, pos], Hn_f[:, lo:hi], "H'[S]", 1e-12, 1e-13)
+    for k in ("dWg", "dWc", "dbg", "dbc", "dGc"):
+        O.assert_close(g_s[k], g_f[k], k, 1e-11, 1e-12)
+    outside = torch.ones(N, dtype=torch.bool)
+    outside[Ut] = False
+    for k in ("dXt", "dH"):
+        O.assert_close(g_s[k], g_f[k][:, Ut], k, 1e-11, 1e-12)
+        assert float(g_f[k][:, outside].abs().max()) == 0.0

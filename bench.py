@@ -13,8 +13,12 @@ Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = th
 public module API with host (pinned) inputs copied in and the loss read back every step;
 `roofline` = the dominant kernel's algorithmic bytes / its device time (CUDA events around every launch
 of that kernel during a second, instrumented pass over the same K steps) against the measured HBM peak;
-`cpu_baseline` = the oracle's reference-shaped port timed on this box's host cores on a bounded sample.
-`--impl reference` runs only that CPU port (rank 0) and prints the same line shape.
+`roofline_step` = the whole step against SURVEY 8d's fused-cell floor (ALG_BYTES_TRAIN); `cpu_baseline` = the
+reference's cell stack on this box's host cores on a bounded sample -- the UNMODIFIED reference when the probe finds
+it ($STC_REF_DIR, /root/reference/framework, baseline/_ref/framework; kind "reference"), else the oracle's
+reference-shaped port (kind "port") -- default and flush-denormal; `gpu_eager_baseline` = the same stack run by stock
+PyTorch eager on this GPU (the kernels to beat), swept over B in {32, 512, 4096} next to this repo's own numbers.
+`--impl reference` runs only the CPU arm (rank 0) and prints the same line shape.
 """
 import argparse
 import json
@@ -47,6 +51,7 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-batch", type=int, default=128, help="windows per CPU-baseline step (bounded sample)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-eager-baseline", action="store_true", help="skip the stock-PyTorch-eager-on-GPU sweep")
     p.add_argument("--no-roofline", action="store_true", help="skip the instrumented per-kernel pass")
     p.add_argument("--workload", default="sf", choices=["sf", "g4096"],
                    help="sf = BASELINE configs[1] (headline); g4096 = configs[2]: N=4096 grid, C=16, F=64, T=12, CSR support "
@@ -151,64 +156,169 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU port of the reference (oracle/) -- the reference arm and the cpu_baseline leg
+# The reference's cell stack through stock PyTorch: the CPU arm (cpu_baseline / --impl reference) and the
+# eager-on-GPU arm.  The UNMODIFIED reference is used when the probe finds it; else the oracle's reference-shaped port.
 # ------------------------------------------------------------------------------------------------
-def cpu_port_throughput(B, steps, warmup, seed=0, budget_s=20.0):
-    """fwd+bwd samples/s of the reference-shaped CPU port (same operator sequence as the reference's
-    BDG_Dif/STC_Cell through autograd, fp32, all host threads) on B windows of the same workload."""
-    from oracle import stc_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    g = torch.Generator().manual_seed(seed)
-    X, y, Gs, Gc = synthetic_inputs(B, seed)
-    enc = [O.xavier_cell_params(SF["Din"] if i == 0 else SF["h"], SF["h"], SF["Ks"], SF["Kc"], g, torch.float32)
-           for i in range(SF["layers"])]
-    dec = [O.xavier_cell_params(SF["h"], SF["h"], SF["Ks"], SF["Kc"], g, torch.float32) for _ in range(SF["layers"])]
-    leaves = [Gs.requires_grad_(True), Gc.requires_grad_(True)]
-    for p in enc + dec:
-        for t in p.tensors():
-            leaves.append(t.requires_grad_(True))
+def find_reference():
+    for cand in (os.environ.get("STC_REF_DIR"), "/root/reference/framework", os.path.join(ROOT, "baseline", "_ref", "framework")):
+        if cand and os.path.isfile(os.path.join(cand, "STC_GNN.py")):
+            return cand
+    return None
 
-    def step():
-        for t in leaves:
+
+class ReferenceStack:
+    """encoder(2 x T) + decoder(horizon x 2) of the reference with the supports handed in (= STCGNN.forward minus MGP_Gen
+    and out_proj, STC_GNN.py:188-204): the same unit of work as stc_gnn_b200.RecurrentStack, same seeded weights."""
+
+    def __init__(self, device, seed=0):
+        self.ref_dir = find_reference()
+        self.device = device
+        torch.manual_seed(seed)
+        if self.ref_dir is not None:
+            sys.dont_write_bytecode = True
+            if self.ref_dir not in sys.path:
+                sys.path.insert(0, self.ref_dir)
+            import STC_GNN as ref
+            self.kind = "reference"
+            self.enc = ref.STC_Encoder(SF["N"], SF["C"], SF["Ks"], SF["Kc"], SF["Din"], SF["h"], SF["layers"]).to(device)
+            self.dec = ref.STC_Decoder(SF["N"], SF["C"], SF["Ks"], SF["Kc"], SF["h"], SF["h"], SF["layers"], SF["horizon"]).to(device)
+            self.leaves = list(self.enc.parameters()) + list(self.dec.parameters())
+        else:
+            from oracle import stc_oracle as O
+            self.kind, self.O = "port", O
+            g = torch.Generator().manual_seed(seed)
+            self.enc = [O.xavier_cell_params(SF["Din"] if i == 0 else SF["h"], SF["h"], SF["Ks"], SF["Kc"], g, torch.float32)
+                        for i in range(SF["layers"])]
+            self.dec = [O.xavier_cell_params(SF["h"], SF["h"], SF["Ks"], SF["Kc"], g, torch.float32) for _ in range(SF["layers"])]
+            self.leaves = []
+            for p in self.enc + self.dec:
+                for name in ("Wg", "bg", "Wc", "bc"):
+                    t = getattr(p, name).to(device).requires_grad_(True)
+                    setattr(p, name, t)
+                    self.leaves.append(t)
+
+    def describe(self):
+        return ("the unmodified reference's STC_Encoder + STC_Decoder (" + self.ref_dir + ")") if self.kind == "reference" \
+            else "oracle/stc_oracle.py reference-shaped port (same operator sequence as BDG_Dif/STC_Cell, autograd)"
+
+    def forward(self, Gs, Gc, X):
+        if self.kind == "port":
+            return self.O.stack_forward(Gs, Gc, X, self.enc, self.dec, SF["horizon"], SF["Ks"], SF["Kc"],
+                                        cell_fn=self.O.stc_cell_refshape)
+        _, Ht = self.enc(Gs=Gs, Gc=Gc, X_seq=X, H0_l=None)
+        inp, outs = Ht[-1], []
+        for _ in range(SF["horizon"]):
+            inp, Ht = self.dec(Gs=Gs, Gc=Gc, Xt=inp, H0_l=Ht)
+            outs.append(inp)
+        return torch.stack(outs, dim=1)
+
+    def step(self, Gs, Gc, X, y):
+        for t in self.leaves + [Gs, Gc]:
             t.grad = None
-        out = O.stack_forward(Gs, Gc, X, enc, dec, SF["horizon"], SF["Ks"], SF["Kc"], cell_fn=O.stc_cell_refshape)
-        loss = loss_fn(out, y)
+        loss = loss_fn(self.forward(Gs, Gc, X), y)
         loss.backward()
-        return float(loss.detach())
+        return loss
 
-    times = []
-    t_begin = time.perf_counter()
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        step()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-        if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
-            break
+
+def cpu_reference_throughput(B, steps, warmup, seed=0, budget_s=20.0, flush_denormal=False):
+    """fwd+bwd samples/s of the reference's cell stack on this box's host cores (fp32, all host threads, autograd) on B
+    windows of the same SF-shape workload.  Returns (samples/s, ms/step, timed steps, threads, kind, description)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    prev_ftz = torch.set_flush_denormal(bool(flush_denormal))
+    try:
+        X, y, Gs, Gc = synthetic_inputs(B, seed)
+        stack = ReferenceStack("cpu", seed)
+        Gs, Gc = Gs.requires_grad_(True), Gc.requires_grad_(True)
+        times = []
+        t_begin = time.perf_counter()
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            float(stack.step(Gs, Gc, X, y).detach())
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+                break
+    finally:
+        torch.set_flush_denormal(False)
     ms = 1e3 * sum(times) / len(times)
-    return B / (ms / 1e3), ms, len(times), torch.get_num_threads()
+    return B / (ms / 1e3), ms, len(times), torch.get_num_threads(), stack.kind, stack.describe()
+
+
+def cpu_baseline_record(B, steps, warmup, budget_s):
+    """The cpu_baseline object: default denormal handling (the reference as shipped) plus the flush-to-zero pair."""
+    v, ms, n, cores, kind, what = cpu_reference_throughput(B, steps, warmup, budget_s=budget_s)
+    v_ftz, ms_ftz, n_ftz, _, _, _ = cpu_reference_throughput(B, max(2, steps // 2), 1, budget_s=budget_s / 2, flush_denormal=True)
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": ms, "timed_steps": n,
+            "flush_denormal": {"value": v_ftz, "ms_per_step": ms_ftz, "timed_steps": n_ftz},
+            "sample": f"{n} timed fwd+bwd steps, each a bounded sample of B={B} windows of the same SF-shape workload "
+                      f"(throughput is per window; the benchmark's synthetic supports are denormal-free, so default and "
+                      f"torch.set_flush_denormal(True) time the same arithmetic -- the CPU-favourable case); {what}; fp32"}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    value, ms, n, cores = cpu_port_throughput(args.cpu_batch, max(2, args.steps), min(args.warmup, 1), budget_s=60.0)
-    sample = (f"{n} timed fwd+bwd steps of B={args.cpu_batch} windows (the reference's own batch size) of the same "
-              f"SF-shape workload, fp32, reference-shaped operator sequence through autograd, denormal-free Gs")
+    rec = cpu_baseline_record(args.cpu_batch, max(2, args.steps), max(0, args.warmup), budget_s=150.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": rec["timed_steps"],
+        "warmup": max(0, args.warmup), "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.cpu_batch, args.gpus, reference=True),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(args.batch, args.gpus),
+        "cpu_baseline": rec,
+        "e2e": {"value": rec["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(B, n_gpus, reference=False, graph=False):
+def gpu_eager_baseline(dev, batches, our_step_factory, steps=3):
+    """Stock PyTorch eager on this GPU (cuBLAS via einsum, STC_GNN.py:37-42): the reference's cell stack, same seeded
+    weights and inputs, fwd+bwd, device-resident, next to this repo's stack at the same batch sizes."""
+    rows = []
+    stack = ReferenceStack(dev, 0)
+    for B in batches:
+        row = {"batch": B}
+        try:
+            X, y, Gs, Gc = synthetic_inputs(B, seed=0)
+            X, y = X.to(dev), y.to(dev)
+            Gs, Gc = Gs.to(dev).requires_grad_(True), Gc.to(dev).requires_grad_(True)
+
+            def timed(fn, n):
+                fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / n
+
+            try:
+                ms = timed(lambda: stack.step(Gs, Gc, X, y), steps)
+                row.update(eager_samples_per_s=B / (ms / 1e3), eager_ms_per_step=ms,
+                           eager_peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2**30)
+            except torch.OutOfMemoryError:
+                row["eager_samples_per_s"] = None
+                row["eager_note"] = "stock eager ran out of device memory at this batch"
+            for t in stack.leaves + [Gs, Gc]:
+                t.grad = None
+            torch.cuda.empty_cache()
+            ours = our_step_factory(B)
+            ms_o = timed(ours, max(steps, 5))
+            row.update(b200_samples_per_s=B / (ms_o / 1e3), b200_ms_per_step=ms_o)
+            if row.get("eager_samples_per_s"):
+                row["speedup"] = row["b200_samples_per_s"] / row["eager_samples_per_s"]
+        except Exception as exc:   # the baseline sweep must never take the headline down with it
+            row["error"] = f"{type(exc).__name__}: {exc}"[:300]
+        torch.cuda.empty_cache()
+        rows.append(row)
+    return {"kind": stack.kind, "what": stack.describe(), "dtype": "f32 (torch default: TF32 off for matmul)",
+            "steps_per_point": steps, "sweep": rows}
+
+
+def workload_config(B, n_gpus, graph=False):
     name = ("sf_cell_stack: encoder 2x9 + decoder 3x2 = 24 STC cell steps/sample, fwd+bwd incl. dGs,dGc "
             "(BASELINE.json configs[1], SF shape)") if WL is SF else (
             "g4096_encoder: 2 layers x T=12 = 24 STC cell steps/sample, fwd+bwd, constant CSR 64x64-grid support and "
@@ -216,8 +326,8 @@ def workload_config(B, n_gpus, reference=False, graph=False):
     return {
         "workload": name,
         "N": WL["N"], "C": WL["C"], "hidden": WL["h"], "Ks": WL["Ks"], "Kc": WL["Kc"], "layers": WL["layers"],
-        "T": WL["T"], "horizon": WL["horizon"], "batch_per_gpu": B, "global_batch": B * (1 if reference else n_gpus),
-        "parallelism": "cpu" if reference else f"dp{n_gpus}",
+        "T": WL["T"], "horizon": WL["horizon"], "batch_per_gpu": B, "global_batch": B * n_gpus,
+        "parallelism": f"dp{n_gpus}",
         "launch": "cuda-graph replay of the captured step" if graph else "eager (one C-ABI call per cell and direction)",
         "l2": "inputs+activations exceed L2 (no flush needed)" if (B >= 1024 or WL is not SF) else "working set may fit L2",
         "bytes_model": "per-kernel compulsory bytes of the multi-kernel pipeline (DESIGN.md section 4); the fused-cell floor "
@@ -228,6 +338,39 @@ def workload_config(B, n_gpus, reference=False, graph=False):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def check_dp_parity(stack, leaves, Gs, Gc, bucket, rank, world, dev, b_small=4):
+    """Every rank steps on its own shard of a small global batch and all-reduces the flat bucket; every rank also
+    steps on the whole concatenated batch alone.  The two gradient sets must agree within the parity tolerance
+    (rtol 1e-4 + 5e-5 x mean|ref|: the stack-level floor of tests/test_cell_gpu.py; summation order differs)."""
+    import torch.distributed as dist
+    shards = [synthetic_inputs(b_small, seed=1000 + r) for r in range(world)]
+    Xg = torch.cat([sh[0] for sh in shards]).to(dev)
+    yg = torch.cat([sh[1] for sh in shards]).to(dev)
+
+    def grads_of(X, y, scale):
+        for p in leaves:
+            p.grad = None
+        (loss_fn(stack(Gs, Gc, X), y) * scale).backward()
+
+    grads_of(Xg, yg, 1.0)                                   # single process, concatenated batch (mean over world*b)
+    want = [p.grad.detach().clone() for p in leaves]
+    s, e = rank * b_small, (rank + 1) * b_small
+    grads_of(Xg[s:e], yg[s:e], 1.0 / world)                 # shard loss is a mean over b: scale so that the sum is the global mean
+    bucket.allreduce()
+    ok = True
+    for p, w in zip(leaves, want):
+        err = (p.grad.double() - w.double()).abs()
+        tol = 1e-4 * w.double().abs() + 5e-5 * w.double().abs().mean()
+        ok = ok and bool((err <= tol).all())
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    for p in leaves:
+        p.grad = None
+    if float(flag.item()) != 1.0:
+        raise SystemExit("dp_parity FAILED: bucket-reduced DP gradients differ from the single-process gradients")
+    return True
+
+
 def run_b200(args):
     import torch.distributed as dist
     import stc_gnn_b200 as S
@@ -298,6 +441,12 @@ def run_b200(args):
             ms = float(t.item())
         return ms
 
+    # ---- N > 1: bucket-reduced DP gradients == single-process gradients of the concatenated batch (small case,
+    #      both through the CUDA path), checked before anything is timed ----
+    dp_parity = None
+    if world > 1:
+        dp_parity = check_dp_parity(stack, leaves, Gs, Gc, bucket, rank, world, dev)
+
     # ---- device-resident throughput ----
     graphed = None
     if args.cuda_graph:
@@ -364,20 +513,39 @@ def run_b200(args):
                             "formula beside its launcher) / its mean launch time over every launch of the step (both "
                             "convolutions, Din = 1 and Din = 16 cells); 3xTF32 tcgen05 kernel (see DESIGN.md section 4)"}
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and WL is SF:
-        v, ms, n, cores = cpu_port_throughput(args.cpu_batch, 40, 1, budget_s=15.0)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
-                        "sample": f"{n} timed fwd+bwd steps of B={args.cpu_batch} windows of the same workload "
-                                  f"(oracle/stc_oracle.py reference-shaped port, fp32, autograd)"}
+    # ---- the whole step against the fused-cell floor of SURVEY 8d (ALG_BYTES_TRAIN = 4 N C (3 Din + 11 h) per
+    #      cell-step-sample: what a fully fused cell must move, forward incl. saving u,r,c + backward) ----
+    roofline_step = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        n_enc0 = WL["T"]                                              # layer-0 encoder cells: Din = input width
+        n_wide = WL["T"] * (WL["layers"] - 1) + WL["horizon"] * WL["layers"]
+        per_sample = 4.0 * WL["N"] * WL["C"] * (n_enc0 * (3 * WL["Din"] + 11 * WL["h"]) + n_wide * (3 * WL["h"] + 11 * WL["h"]))
+        ach = per_sample * B / (ms_step * 1e-3) / 1e9
+        roofline_step = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "alg_bytes_per_sample": per_sample, "peak_source": peak_src,
+                         "bytes_model": "SURVEY 8d ALG_BYTES_TRAIN summed over the cell steps of one sample "
+                                        "(compulsory traffic of a fully fused cell), x batch / device step time (per GPU)"}
+
+    cpu_baseline, eager = None, None
+    if rank == 0 and world == 1 and WL is SF:
+        if not args.no_eager_baseline:
+            def ours_at(Bq):
+                Xq, yq, _, _ = synthetic_inputs(Bq, seed=0)
+                Xq, yq = Xq.to(dev), yq.to(dev)
+                return lambda: step(Xq, yq)
+            eager = gpu_eager_baseline(dev, [32, 512, 4096], ours_at)
+        if not args.no_cpu_baseline:
+            cpu_baseline = cpu_baseline_record(args.cpu_batch, 40, 1, budget_s=14.0)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, world, graph=bool(graphed)),
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,
+            "cpu_baseline": cpu_baseline, "gpu_eager_baseline": eager, "dp_parity": dp_parity,
+            "kernel_breakdown": breakdown,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

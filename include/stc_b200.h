@@ -161,6 +161,22 @@ int stc_support_apply(const StcSupport* gs, int32_t N, int32_t B, int32_t width,
                       const float* x, int64_t x_batch_stride, const float* z, int64_t z_batch_stride,
                       float* y, float alpha, float beta, void* stream);
 
+/* The same product restricted to the output nodes listed in rows[n_rows] (int32, device): the other rows of Y are
+ * not touched.  CSR supports only.  The row-partitioned path (stc_gnn_b200/halo.py) computes the rows whose
+ * neighbours are all local while the halo exchange of the hop is in flight, then the boundary rows. */
+int stc_support_apply_rows(const StcSupport* gs, int32_t N, int32_t B, int32_t width, int32_t transpose,
+                           const float* x, int64_t x_batch_stride, const float* z, int64_t z_batch_stride,
+                           float* y, float alpha, float beta, const int32_t* rows, int32_t n_rows, void* stream);
+
+/* Halo rows of a row-partitioned hop.  x_ext is an extended tensor [B][nloc + nhalo][width] (batch stride in
+ * elements).  pack: send[j][b][:] = x_ext[b][idx[j]][:] for the n_rows local boundary nodes idx (int32, device;
+ * grouped by destination rank, so `send` is the input of one all-to-all with row counts as split sizes);
+ * unpack: x_ext[b][row0 + j][:] = recv[j][b][:] (row0 = nloc: the halo rows, ordered by owner rank). */
+int stc_halo_pack(const float* x_ext, int64_t x_batch_stride, int32_t width, int32_t B, const int32_t* idx,
+                  int32_t n_rows, float* send, void* stream);
+int stc_halo_unpack(const float* recv, int32_t width, int32_t B, int32_t row0, int32_t n_rows, float* x_ext,
+                    int64_t x_batch_stride, void* stream);
+
 /* Building block self-test / microbenchmark: D[M][N] = A[M][K] * B[K][N], row-major fp32, evaluated as a
  * 3xTF32 tcgen05 product with TMEM accumulation (the same code path as the gate contraction).  N <= 256. */
 int stc_tf32x3_gemm(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K, void* stream);

@@ -21,6 +21,7 @@ EXPORTED = (
     "stc_timing_enable", "stc_timing_collect", "stc_kernel_kind_name", "stc_tf32x3_gemm",
     "stc_cell_saved_layout", "stc_cell_fwd_stage", "stc_debug_trace_set",
     "stc_cell_bwd_scratch_layout", "stc_cell_bwd_stage",
+    "stc_support_apply_rows", "stc_halo_pack", "stc_halo_unpack",
 )
 STAGE_GATES, STAGE_CANDI = 0, 1
 SAVED_REGIONS = ("u", "r", "c", "Yr", "Yx", "Yh", "Q", "Pg", "Pc")
@@ -79,6 +80,13 @@ def load(build_if_missing: bool = True):
     lib.stc_support_apply.restype = c_int
     lib.stc_support_apply.argtypes = [POINTER(StcSupport), c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
                                       c_void_p, c_int64, c_void_p, c_float, c_float, c_void_p]
+    lib.stc_support_apply_rows.restype = c_int
+    lib.stc_support_apply_rows.argtypes = [POINTER(StcSupport), c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
+                                           c_void_p, c_int64, c_void_p, c_float, c_float, c_void_p, c_int32, c_void_p]
+    lib.stc_halo_pack.restype = c_int
+    lib.stc_halo_pack.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p]
+    lib.stc_halo_unpack.restype = c_int
+    lib.stc_halo_unpack.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]
     lib.stc_tf32x3_gemm.restype = c_int
     lib.stc_tf32x3_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     lib.stc_timing_enable.restype = c_int

@@ -280,6 +280,45 @@ int stc_support_apply(const StcSupport* gs, int32_t N, int32_t B, int32_t width,
                               beta, nullptr, 0.f, (cudaStream_t)stream);
 }
 
+int stc_support_apply_rows(const StcSupport* gs, int32_t N, int32_t B, int32_t width, int32_t transpose, const float* x,
+                           int64_t x_batch_stride, const float* z, int64_t z_batch_stride, float* y, float alpha,
+                           float beta, const int32_t* rows, int32_t n_rows, void* stream) {
+  reset_launch_count();
+  if (!gs || !x || !y || !rows) {
+    set_error("stc_support_apply_rows: NULL argument");
+    return STC_ERR_BAD_ARG;
+  }
+  if (n_rows < 0 || n_rows > N) {
+    set_error("stc_support_apply_rows: n_rows %d outside [0, N = %d]", n_rows, N);
+    return STC_ERR_BAD_ARG;
+  }
+  STC_TRY(check_arch());
+  return launch_support_apply(*gs, N, B, width, transpose != 0, x, x_batch_stride, z, z_batch_stride, y, alpha, beta,
+                              nullptr, 0.f, (cudaStream_t)stream, rows, n_rows);
+}
+
+int stc_halo_pack(const float* x_ext, int64_t x_batch_stride, int32_t width, int32_t B, const int32_t* idx, int32_t n_rows,
+                  float* send, void* stream) {
+  reset_launch_count();
+  if (n_rows > 0 && (!x_ext || !idx || !send)) {
+    set_error("stc_halo_pack: NULL argument");
+    return STC_ERR_BAD_ARG;
+  }
+  STC_TRY(check_arch());
+  return launch_halo_rows(true, const_cast<float*>(x_ext), x_batch_stride, width, B, idx, 0, n_rows, send, (cudaStream_t)stream);
+}
+
+int stc_halo_unpack(const float* recv, int32_t width, int32_t B, int32_t row0, int32_t n_rows, float* x_ext,
+                    int64_t x_batch_stride, void* stream) {
+  reset_launch_count();
+  if (n_rows > 0 && (!x_ext || !recv)) {
+    set_error("stc_halo_unpack: NULL argument");
+    return STC_ERR_BAD_ARG;
+  }
+  STC_TRY(check_arch());
+  return launch_halo_rows(false, x_ext, x_batch_stride, width, B, nullptr, row0, n_rows, const_cast<float*>(recv), (cudaStream_t)stream);
+}
+
 int stc_tf32x3_gemm(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K, void* stream) {
   reset_launch_count();
   if (!a || !b || !d) {

@@ -94,7 +94,11 @@ WsLayout make_layout(const StcDims& d);
 // ---- launchers implemented in the kernel TUs -----------------------------------------------------
 int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool transpose, const float* x,
                          int64_t x_bs, const float* z, int64_t z_bs, float* y, float alpha, float beta,
-                         float* axpy_out, float axpy_coef, cudaStream_t st);
+                         float* axpy_out, float axpy_coef, cudaStream_t st, const int32_t* row_list = nullptr,
+                         int n_list = 0);
+// halo rows of the row-partitioned path: pack (gather x_ext[b][idx[j]] -> buf[j][b]) or unpack (buf -> rows row0 + j)
+int launch_halo_rows(bool pack, float* x_ext, long long x_bs, int W, int B, const int32_t* idx, int row0, int n_rows,
+                     float* buf, cudaStream_t st);
 
 // tcgen05 versions (stc_support_tc.cu): STC_OK and *handled when they took the launch
 int try_launch_support_tc(const float* G, int N, int B, int width, bool transpose, const float* x, int64_t x_bs,

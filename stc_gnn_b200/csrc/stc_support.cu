@@ -109,14 +109,18 @@ __global__ void __launch_bounds__(256)
 support_csr_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                    const float* __restrict__ vals, int N, long long rows_total, const float* __restrict__ X,
                    long long x_bs, const float* Z, long long z_bs, float* Y, int W, float alpha, float beta,
-                   float* axpy_out, float axpy_coef) {
+                   float* axpy_out, float axpy_coef, const int32_t* __restrict__ row_list, int n_list) {
+  // row_list != nullptr: only the n_list output nodes it names are computed (rows_total = B * n_list); the other
+  // rows of Y are not touched (the row-partitioned path computes interior rows while the halo exchange is in flight)
   constexpr int U = 4;  // independent accumulators per lane per pass
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = warp0; row < rows_total; row += nwarps) {
-    const long long b = row / N;
-    const int m = (int)(row - b * N);
+    const int per_b = row_list ? n_list : N;
+    const long long b = row / per_b;
+    const int mi = (int)(row - b * per_b);
+    const int m = row_list ? row_list[mi] : mi;
     const int e0 = rowptr[m], e1 = rowptr[m + 1];
     const float* xb = X + b * x_bs;
     for (int j0 = 0; j0 < W; j0 += 32 * VEC * U) {
@@ -176,8 +180,15 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool transpose, const float* x,
                          int64_t x_bs, const float* z, int64_t z_bs, float* y, float alpha, float beta,
-                         float* axpy_out, float axpy_coef, cudaStream_t st) {
+                         float* axpy_out, float axpy_coef, cudaStream_t st, const int32_t* row_list, int n_list) {
   if (B <= 0 || N <= 0 || width <= 0) return STC_OK;
+  if (row_list) {
+    if (n_list <= 0) return STC_OK;
+    if (gs.kind != STC_SUPPORT_CSR) {
+      set_error("support_apply: a row list is only supported for a CSR support");
+      return STC_ERR_UNSUPPORTED;
+    }
+  }
   if (beta != 0.f && z == nullptr) {
     set_error("support_apply: beta != 0 needs z");
     return STC_ERR_BAD_ARG;
@@ -221,7 +232,7 @@ int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool tra
     set_error("CSR support needs both Gs and Gs^T (rowptr/col/vals and t_rowptr/t_col/t_vals)");
     return STC_ERR_BAD_ARG;
   }
-  long long rows_total = (long long)B * N;
+  long long rows_total = (long long)B * (row_list ? n_list : N);
   bool vec = (width % 4 == 0) && (x_bs % 4 == 0) && (z == nullptr || z_bs % 4 == 0) && aligned16(x) &&
              aligned16(y) && (z == nullptr || aligned16(z)) && (axpy_out == nullptr || aligned16(axpy_out));
   int warps_per_block = 8;
@@ -229,14 +240,63 @@ int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool tra
   int grid = (int)(want < (long long)device_sm_count() * 16 ? want : (long long)device_sm_count() * 16);
   if (grid < 1) grid = 1;
   ScopedKernelTimer _t(KK_SUPPORT_CSR, st,
-                       4.0 * B * N * width * (2 + (beta != 0.f ? 1 : 0) + (axpy_out ? 2 : 0)) + 8.0 * gs.nnz + 4.0 * (N + 1));
+                       4.0 * rows_total * width * (2 + (beta != 0.f ? 1 : 0) + (axpy_out ? 2 : 0)) + 8.0 * gs.nnz + 4.0 * (N + 1));
   if (vec)
     support_csr_kernel<4><<<grid, warps_per_block * 32, 0, st>>>(rp, ci, va, N, rows_total, x, x_bs, z, z_bs, y,
-                                                                  width, alpha, beta, axpy_out, axpy_coef);
+                                                                  width, alpha, beta, axpy_out, axpy_coef, row_list, n_list);
   else
     support_csr_kernel<1><<<grid, warps_per_block * 32, 0, st>>>(rp, ci, va, N, rows_total, x, x_bs, z, z_bs, y,
-                                                                  width, alpha, beta, axpy_out, axpy_coef);
+                                                                  width, alpha, beta, axpy_out, axpy_coef, row_list, n_list);
   STC_LAUNCH_OK("support_csr_kernel");
+  return STC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo rows of the row-partitioned path (stc_gnn_b200/halo.py): gather boundary-node slabs into the packed send buffer
+// of the all-to-all ([row j][b][W], rows grouped by destination rank) and scatter received slabs into the halo rows.
+// One warp per (j, b) slab; lanes sweep the contiguous width axis.
+// ------------------------------------------------------------------------------------------------
+template <int VEC, bool PACK>
+__global__ void __launch_bounds__(256)
+halo_rows_kernel(float* __restrict__ x_ext, long long x_bs, int W, int B, const int32_t* __restrict__ idx, int row0,
+                 int n_rows, float* __restrict__ buf) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)n_rows * B;
+  for (long long s = warp0; s < total; s += nwarps) {
+    const int j = (int)(s / B), b = (int)(s - (long long)j * B);
+    const int node = idx ? idx[j] : row0 + j;
+    float* xr = x_ext + b * x_bs + (long long)node * W;
+    float* br = buf + ((long long)j * B + b) * W;
+    for (int w = lane * VEC; w < W; w += 32 * VEC) {
+      if (VEC == 4) {
+        if (PACK) *reinterpret_cast<float4*>(br + w) = *reinterpret_cast<const float4*>(xr + w);
+        else *reinterpret_cast<float4*>(xr + w) = *reinterpret_cast<const float4*>(br + w);
+      } else {
+        if (PACK) br[w] = xr[w];
+        else xr[w] = br[w];
+      }
+    }
+  }
+}
+
+int launch_halo_rows(bool pack, float* x_ext, long long x_bs, int W, int B, const int32_t* idx, int row0, int n_rows,
+                     float* buf, cudaStream_t st) {
+  if (n_rows <= 0 || B <= 0 || W <= 0) return STC_OK;
+  const bool vec = (W % 4 == 0) && (x_bs % 4 == 0) && aligned16(x_ext) && aligned16(buf);
+  const long long slabs = (long long)n_rows * B;
+  long long want = (slabs + 7) / 8;
+  int grid = (int)(want < (long long)device_sm_count() * 8 ? want : (long long)device_sm_count() * 8);
+  if (grid < 1) grid = 1;
+  if (vec) {
+    if (pack) halo_rows_kernel<4, true><<<grid, 256, 0, st>>>(x_ext, x_bs, W, B, idx, row0, n_rows, buf);
+    else halo_rows_kernel<4, false><<<grid, 256, 0, st>>>(x_ext, x_bs, W, B, idx, row0, n_rows, buf);
+  } else {
+    if (pack) halo_rows_kernel<1, true><<<grid, 256, 0, st>>>(x_ext, x_bs, W, B, idx, row0, n_rows, buf);
+    else halo_rows_kernel<1, false><<<grid, 256, 0, st>>>(x_ext, x_bs, W, B, idx, row0, n_rows, buf);
+  }
+  STC_LAUNCH_OK("halo_rows_kernel");
   return STC_OK;
 }
 

@@ -208,19 +208,76 @@ class PartitionedSupport:
                               alpha=alpha, beta=beta, Z=Z_ext)
         return Y_ext[:, :plan.nloc].reshape(shape)
 
+    # -- device-side exchange state: packed index lists, interior / boundary row lists, persistent buffers --
+    def _device_state(self, direction: str, device):
+        key = ("xchg", direction, str(device))
+        st = self._dev.get(key)
+        if st is None:
+            plan = self.fwd if direction == "fwd" else self.bwd
+            send = torch.cat(plan.send_idx) if plan.send_idx else torch.empty(0, dtype=torch.long)
+            has_halo_col = torch.zeros(plan.nloc, dtype=torch.bool)
+            has_halo_col[plan.op_row[plan.op_col >= plan.nloc]] = True
+            interior = torch.nonzero(~has_halo_col).flatten()
+            # boundary pass: local rows that read a halo column + the halo rows themselves (empty operator rows: they
+            # come out as beta * Z, i.e. finite -- the node-local stages run over the extended node set)
+            boundary = torch.cat([torch.nonzero(has_halo_col).flatten(), torch.arange(plan.nloc, plan.next)])
+            st = self._dev[key] = {
+                "send_idx": send.to(torch.int32).to(device), "nsend": int(send.numel()),
+                "interior": interior.to(torch.int32).to(device), "boundary": boundary.to(torch.int32).to(device),
+                "buffers": {}, "side": torch.cuda.Stream(device=device), "ready": torch.cuda.Event(), "done": torch.cuda.Event(),
+            }
+        return st
+
+    def _buffers(self, st, plan, slab: int, device):
+        buf = st["buffers"].get(slab)
+        if buf is None:
+            if len(st["buffers"]) > 4:
+                st["buffers"].clear()
+            buf = st["buffers"][slab] = (torch.empty(st["nsend"], slab, dtype=torch.float32, device=device),
+                                         torch.empty(plan.nhalo, slab, dtype=torch.float32, device=device))
+        return buf
+
     def hop_ext(self, X_ext: torch.Tensor, out_ext: torch.Tensor, Z_ext: Optional[torch.Tensor] = None,
                 alpha: float = 1.0, beta: float = 0.0, direction: str = "fwd") -> None:
-        """One hop on EXTENDED tensors [B, nloc + nhalo, ...] (CUDA): the halo rows of `X_ext` are refreshed in place
-        from their owners, then `out_ext = alpha * A X_ext + beta * Z_ext` with the local operator (square over the
-        extended index set, empty rows for the halo nodes -- their output rows are meaningless and get overwritten
-        by the next exchange).  No tensor is copied or sliced."""
+        """One hop on EXTENDED tensors [B, nloc + nhalo, ...] (CUDA): `out_ext = alpha * A X_ext + beta * Z_ext` with the
+        local operator (square over the extended index set; the halo nodes have empty operator rows).
+
+        The halo rows of `X_ext` are refreshed in place from their owners ON A SIDE STREAM -- `stc_halo_pack` of the
+        boundary rows into a persistent send buffer, one NCCL all-to-all of packed rows, `stc_halo_unpack` into the halo
+        rows -- while the main stream already computes the INTERIOR output rows (those whose neighbours are all local,
+        `stc_support_apply_rows`); the main stream then waits for the exchange and computes the boundary rows.  No
+        tensor is copied, sliced or allocated per hop."""
+        from . import _lib
         from .support import support_apply
         plan = self.fwd if direction == "fwd" else self.bwd
         B = X_ext.shape[0]
-        exchange_into(plan, X_ext.view(B, plan.next, -1), self.group)
-        support_apply(self.device_support(direction, X_ext.device), X_ext.view(B, plan.next, -1),
-                      transpose=(direction == "fwd"), alpha=alpha, beta=beta,
-                      Z=None if Z_ext is None else Z_ext.view(B, plan.next, -1), out=out_ext.view(B, plan.next, -1))
+        X3 = X_ext.view(B, plan.next, -1)
+        W = X3.shape[-1]
+        out3 = out_ext.view(B, plan.next, -1)
+        Z3 = None if Z_ext is None else Z_ext.view(B, plan.next, -1)
+        sup = self.device_support(direction, X_ext.device)
+        tr = direction == "fwd"
+        if plan.world == 1:
+            support_apply(sup, X3, transpose=tr, alpha=alpha, beta=beta, Z=Z3, out=out3)
+            return
+        lib = _lib.load()
+        st = self._device_state(direction, X_ext.device)
+        send, recv = self._buffers(st, plan, B * W, X_ext.device)
+        main, side = torch.cuda.current_stream(), st["side"]
+        st["ready"].record(main)                     # X_ext's local rows are final once the main stream gets here
+        with torch.cuda.stream(side):
+            side.wait_event(st["ready"])
+            _lib.check(lib.stc_halo_pack(X3.data_ptr(), plan.next * W, W, B, st["send_idx"].data_ptr(), st["nsend"],
+                                         send.data_ptr(), side.cuda_stream), "stc_halo_pack")
+            dist.all_to_all_single(recv, send, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts,
+                                   group=self.group)
+            _lib.check(lib.stc_halo_unpack(recv.data_ptr(), W, B, plan.nloc, plan.nhalo, X3.data_ptr(), plan.next * W,
+                                           side.cuda_stream), "stc_halo_unpack")
+            st["done"].record(side)
+        if st["interior"].numel():
+            support_apply(sup, X3, transpose=tr, alpha=alpha, beta=beta, Z=Z3, out=out3, rows=st["interior"])
+        main.wait_event(st["done"])
+        support_apply(sup, X3, transpose=tr, alpha=alpha, beta=beta, Z=Z3, out=out3, rows=st["boundary"])
 
     def spatial_terms(self, X_local: torch.Tensor, Ks: int, apply_fn=None) -> List[torch.Tensor]:
         """Feature-side Chebyshev terms Y_0..Y_{Ks-1} of this rank's block (Y_1 = Gs^T Y_0, Y_k = 2 Gs^T Y_{k-1} - Y_{k-2};

@@ -60,9 +60,10 @@ def dense_struct(G: torch.Tensor) -> _lib.StcSupport:
 
 
 def support_apply(Gs, X: torch.Tensor, transpose: bool = True, alpha: float = 1.0, beta: float = 0.0,
-                  Z: torch.Tensor = None, out: torch.Tensor = None) -> torch.Tensor:
+                  Z: torch.Tensor = None, out: torch.Tensor = None, rows: torch.Tensor = None) -> torch.Tensor:
     """Y[b,m,...] = alpha * sum_n A(m,n) X[b,n,...] + beta * Z  with A = Gs^T (transpose) or Gs. CUDA only.
-    `out` (contiguous, X's shape) receives the result in place of a fresh tensor."""
+    `out` (contiguous, X's shape) receives the result in place of a fresh tensor.  `rows` (int32 CUDA tensor, CSR
+    supports only): compute just those output nodes and leave every other row of `out` untouched."""
     lib = _lib.load()
     if not X.is_cuda or X.dtype != torch.float32:
         raise RuntimeError("support_apply needs a float32 CUDA tensor (there is no CPU path)")
@@ -82,6 +83,18 @@ def support_apply(Gs, X: torch.Tensor, transpose: bool = True, alpha: float = 1.
         keep = Gs.detach().contiguous()
         st = dense_struct(keep)
     zc = Z.contiguous() if Z is not None else None
+    if rows is not None:
+        if rows.dtype != torch.int32 or not rows.is_cuda or not rows.is_contiguous():
+            raise RuntimeError("support_apply: `rows` must be a contiguous int32 CUDA tensor")
+        if out is None:
+            raise RuntimeError("support_apply: `rows` needs `out` (the other rows keep their contents)")
+        status = lib.stc_support_apply_rows(st, N, B, width, 1 if transpose else 0, Xc.data_ptr(), N * width,
+                                            zc.data_ptr() if zc is not None else None, N * width, Y.data_ptr(),
+                                            float(alpha), float(beta), rows.data_ptr(), rows.numel(),
+                                            torch.cuda.current_stream().cuda_stream)
+        _lib.check(status, "stc_support_apply_rows")
+        del keep
+        return Y
     status = lib.stc_support_apply(st, N, B, width, 1 if transpose else 0, Xc.data_ptr(), N * width,
                                    zc.data_ptr() if zc is not None else None, N * width, Y.data_ptr(),
                                    float(alpha), float(beta), torch.cuda.current_stream().cuda_stream)

@@ -136,3 +136,47 @@ def test_halo_cell_two_ranks_nccl():
         p.join(timeout=60)
     errs = [f"rank {r}:\n{e}" for r, e in results if e]
     assert not errs, "\n".join(errs)
+
+
+def test_row_subset_apply_and_halo_pack_unpack_kernels():
+    """The two device pieces of the overlapped hop, on one GPU: `stc_support_apply_rows` computes exactly the listed
+    output nodes (the rest of `out` keeps its contents), `stc_halo_pack` / `stc_halo_unpack` move packed row slabs."""
+    import stc_gnn_b200 as S
+    from stc_gnn_b200 import _lib
+    from stc_gnn_b200.support import support_apply
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(17)
+    N, B, W = 90, 3, 40
+    G = (torch.rand(N, N, generator=g) * (torch.rand(N, N, generator=g) > 0.8)).float().to(dev)
+    csr = S.CsrSupport.from_dense(G)
+    X = torch.randn(B, N, W, generator=g).to(dev)
+    Z = torch.randn(B, N, W, generator=g).to(dev)
+    rows = torch.tensor([0, 3, 4, 17, 50, 89], dtype=torch.int32, device=dev)
+    for transpose in (True, False):
+        full = support_apply(csr, X, transpose=transpose, alpha=2.0, beta=-1.0, Z=Z)
+        out = torch.full((B, N, W), 7.0, device=dev)
+        support_apply(csr, X, transpose=transpose, alpha=2.0, beta=-1.0, Z=Z, out=out, rows=rows)
+        keep = torch.ones(N, dtype=torch.bool, device=dev)
+        keep[rows.long()] = False
+        assert torch.equal(out[:, rows.long()], full[:, rows.long()])
+        assert torch.equal(out[:, keep], torch.full_like(out[:, keep], 7.0))
+        # in-place accumulation form used by the adjoint chain (out aliases Z), split over two row lists
+        acc = Z.clone()
+        rest = torch.nonzero(keep).flatten().to(torch.int32)
+        support_apply(csr, X, transpose=transpose, alpha=2.0, beta=1.0, Z=acc, out=acc, rows=rows)
+        support_apply(csr, X, transpose=transpose, alpha=2.0, beta=1.0, Z=acc, out=acc, rows=rest)
+        want = support_apply(csr, X, transpose=transpose, alpha=2.0, beta=1.0, Z=Z)
+        assert torch.equal(acc, want)
+    with pytest.raises(RuntimeError):
+        support_apply(G, X, out=torch.empty_like(X), rows=rows)          # dense supports have no row-list form
+    for Wq in (40, 7):                                                   # vectorised and scalar widths
+        Xe = torch.randn(B, N, Wq, generator=g).to(dev)
+        idx = torch.tensor([5, 6, 30, 2], dtype=torch.int32, device=dev)
+        send = torch.empty(idx.numel(), B * Wq, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.stc_halo_pack(Xe.data_ptr(), N * Wq, Wq, B, idx.data_ptr(), idx.numel(), send.data_ptr(), st), "pack")
+        assert torch.equal(send.view(-1, B, Wq), Xe[:, idx.long()].permute(1, 0, 2))
+        before = Xe.clone()
+        _lib.check(lib.stc_halo_unpack(send.data_ptr(), Wq, B, N - 4, 4, Xe.data_ptr(), N * Wq, st), "unpack")
+        assert torch.equal(Xe[:, N - 4:], before[:, idx.long()]) and torch.equal(Xe[:, :N - 4], before[:, :N - 4])

@@ -7,11 +7,22 @@ libstc_b200.so per direction (include/stc_b200.h).  CUDA fp32 only -- anything e
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
 from . import _lib
 from .support import CsrSupport, dense_struct
+
+# Gradients of LEAF tensors (the cell's parameters; Gs / Gc when they are leaves) are accumulated by the backward
+# kernels straight into `.grad` (the ABI's accumulate mode) instead of being returned to autograd: a cell is applied
+# T times per sequence and the supports feed all 24 cell steps, so the returned form costs one freshly zeroed buffer
+# set (6 memsets) per cell backward plus one elementwise add per tensor and step (~250 tiny launches per SF step,
+# profiles/r1q_launches.txt).  Semantics are those of `loss.backward()` (gradients add into `.grad`);
+# `torch.autograd.grad(...)` w.r.t. these leaves needs the returned form: set STC_INPLACE_GRADS=0 or
+# `stc_gnn_b200.cell.INPLACE_LEAF_GRADS = False`.
+INPLACE_LEAF_GRADS = os.environ.get("STC_INPLACE_GRADS", "1") != "0"
 
 _ACT_CODES = {None: _lib.ACT_NONE, nn.ReLU: _lib.ACT_RELU}
 _ACT_NAMES = {_lib.ACT_NONE: None, _lib.ACT_RELU: "relu"}
@@ -99,6 +110,12 @@ class _CellFunction(torch.autograd.Function):
         ctx.cfg, ctx.dims_tuple, ctx.xbs, ctx.csr = cfg, (B, N, C, Din, h), xbs, csr
         ctx.gs_obj = Gs if csr else None
         ctx.has_bias = bg is not None
+        # leaves whose gradient the backward adds into `.grad` directly (index = position among forward's inputs)
+        ctx.sinks = {}
+        if INPLACE_LEAF_GRADS:
+            for i, t in ((0, None if csr else Gs), (1, Gc), (4, Wg), (5, bg), (6, Wc), (7, bc)):
+                if t is not None and ctx.needs_input_grad[i] and t.is_leaf and t.is_contiguous():
+                    ctx.sinks[i] = t
         ctx.save_for_backward(*( [] if csr else [gs_keep] ), Gc_c, Xt_c, H_c, Wg_c, Wc_c, saved)
         return Hn
 
@@ -124,24 +141,42 @@ class _CellFunction(torch.autograd.Function):
         new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
         dXt = new(B, N, C, Din) if need[2] else None
         dH = new(B, N, C, h)
-        dWg, dWc = new(P * L, 2 * h), new(P * L, h)
-        dbg, dbc = (new(2 * h), new(h)) if ctx.has_bias else (None, None)
-        dGs = new(N, N) if (need[0] and not ctx.csr) else None
-        dGc = new(C, C) if need[1] else None
+        returned = [None] * 9
+
+        def target(i, shape, wanted=True):
+            """Buffer the kernels ADD input i's gradient into: the leaf's own `.grad` (created zeroed on first use in a
+            step; nothing is returned to autograd), else a fresh zeroed tensor that is returned."""
+            if not wanted:
+                return None
+            leaf = ctx.sinks.get(i)
+            if leaf is not None and need[i]:
+                if leaf.grad is None:
+                    leaf.grad = torch.zeros(shape, dtype=torch.float32, device=dev)
+                if leaf.grad.is_contiguous() and leaf.grad.dtype == torch.float32 and leaf.grad.shape == torch.Size(shape):
+                    return leaf.grad
+            buf = torch.zeros(shape, dtype=torch.float32, device=dev)
+            returned[i] = buf
+            return buf
+
+        dWg, dWc = target(4, (P * L, 2 * h)), target(6, (P * L, h))
+        dbg, dbc = target(5, (2 * h,), ctx.has_bias), target(7, (h,), ctx.has_bias)
+        dGs = target(0, (N, N), need[0] and not ctx.csr)
+        dGc = target(1, (C, C), need[1])
+        returned[2], returned[3] = dXt, dH
+        if B == 0:  # empty batch: every parameter gradient is zero (the targets are zeroed or untouched), nothing to launch
+            return tuple(returned)
         scratch = torch.empty(lib.stc_cell_bwd_scratch_bytes(dims) // 4, dtype=torch.float32, device=dev)
-        if B == 0:  # empty batch: every parameter gradient is zero, nothing to launch
-            for g_ in (dWg, dWc, dbg, dbc, dGs, dGc):
-                if g_ is not None:
-                    g_.zero_()
-            return dGs, dGc, dXt, dH, dWg, dbg, dWc, dbc, None
         status = lib.stc_cell_bwd(dims, gs_struct, Gc.data_ptr(), Xt.data_ptr(), ctx.xbs, H.data_ptr(), Wg.data_ptr(),
                                   Wc.data_ptr(), dHn.data_ptr(), _ptr(dXt), dH.data_ptr(), dWg.data_ptr(), _ptr(dbg),
-                                  dWc.data_ptr(), _ptr(dbc), _ptr(dGs), _ptr(dGc), 0, saved.data_ptr(),
+                                  dWc.data_ptr(), _ptr(dbc), _ptr(dGs), _ptr(dGc), 1, saved.data_ptr(),
                                   saved.numel() * 4, scratch.data_ptr(), scratch.numel() * 4,
                                   torch.cuda.current_stream().cuda_stream)
         _lib.check(status, "stc_cell_bwd")
         _lib.note_launches()
-        return dGs, dGc, dXt, dH, dWg, dbg, dWc, dbc, None
+        for i in (0, 1, 4, 5, 6, 7):       # inputs that need no gradient get none, whatever was computed for them
+            if not need[i]:
+                returned[i] = None
+        return tuple(returned)
 
 
 def stc_cell_forward(Gs, Gc, Xt, Ht_1, Wg, bg, Wc, bc, Ks: int, Kc: int, activation=None) -> torch.Tensor:

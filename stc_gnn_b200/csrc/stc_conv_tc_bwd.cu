@@ -610,24 +610,40 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
   }
   if (a.dbias && !db_fast && tid < db_groups * Hout) atomicAdd(&a.dbias[db_col], db_acc);
   __syncthreads();   // every tile is done: Dsm is free and serves as the reduction scratch
+  // End-of-kernel reductions.  Shared-memory float atomics are compare-and-swap loops: with every thread of the CTA
+  // adding into the same few addresses at once (the first version) the loops serialise -- ~100 us per launch, at any batch
+  // size (profiles/r3b_launches_b32.txt: 110 us per dx launch at B = 32 against 10 us for the forward).  Lanes that
+  // share an address are therefore summed with warp shuffles first; one lane per warp and address touches memory.
   if (db_fast) {
     for (int i = tid; i < Hout; i += CV_THREADS) Dsm[i] = 0.f;
     __syncthreads();
-    const int j = (tid % (h >> 2)) << 2;
-    atomicAdd(&Dsm[j + 0], dbs0.x); atomicAdd(&Dsm[j + 1], dbs0.y); atomicAdd(&Dsm[j + 2], dbs0.z); atomicAdd(&Dsm[j + 3], dbs0.w);
-    if (a.phase == 0) {
-      atomicAdd(&Dsm[h + j + 0], dbs1.x); atomicAdd(&Dsm[h + j + 1], dbs1.y);
-      atomicAdd(&Dsm[h + j + 2], dbs1.z); atomicAdd(&Dsm[h + j + 3], dbs1.w);
+    const int cprw = h >> 2;                         // lanes l and l + cprw (mod 32) hold the same column chunk
+    float v[8] = {dbs0.x, dbs0.y, dbs0.z, dbs0.w, dbs1.x, dbs1.y, dbs1.z, dbs1.w};
+    for (int off = cprw; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+    }
+    if (lane < cprw || cprw >= 32) {
+      const int j = (tid % cprw) << 2;
+      atomicAdd(&Dsm[j + 0], v[0]); atomicAdd(&Dsm[j + 1], v[1]); atomicAdd(&Dsm[j + 2], v[2]); atomicAdd(&Dsm[j + 3], v[3]);
+      if (a.phase == 0) {
+        atomicAdd(&Dsm[h + j + 0], v[4]); atomicAdd(&Dsm[h + j + 1], v[5]);
+        atomicAdd(&Dsm[h + j + 2], v[6]); atomicAdd(&Dsm[h + j + 3], v[7]);
+      }
     }
     __syncthreads();
     for (int i = tid; i < Hout; i += CV_THREADS) atomicAdd(&a.dbias[i], Dsm[i]);
   }
-  if (dq_fast && tid < p.npt * dq_chunks) {
+  if (dq_fast) {   // CTA-uniform: every lane takes part in the shuffles (threads without a node slot hold zeros)
 #pragma unroll
     for (int cp = 0; cp < DQ_C; ++cp)
 #pragma unroll
-      for (int d = 0; d < DQ_C; ++d)
-        if (cp < C && d < C) atomicAdd(&dQacc[cp * C + d], dq[cp * DQ_C + d]);
+      for (int d = 0; d < DQ_C; ++d) {
+        float s = dq[cp * DQ_C + d];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0 && cp < C && d < C) atomicAdd(&dQacc[cp * C + d], s);
+      }
   }
   __syncthreads();
   if (want_dQ)

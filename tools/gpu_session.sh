@@ -10,6 +10,7 @@
 #   g4096[:N[:B]]    bench.py --workload g4096             sweep      config 2 batch sweep (tools/bench_configs.py)
 #   launches[:B]     ncu launch list of one bench step     ncu[:REGEX[:SKIP[:COUNT]]]  one ncu --set full capture
 #   support|config3|config4|config5   tools/bench_configs.py side workloads
+#   full:N:CFG:B[:stock|adam]  reference STCGNN + installed cell, DP over N GPUs (CFG = sf | longc)
 #   halo:N[:train]   tools/bench_halo.py on N GPUs         trace      clock64 phase trace of the gate convolutions
 #   memcheck         compute-sanitizer over the smallest parity case of every kernel family
 #   probe            what the box has (GPU, host cores / memory, reference probe)
@@ -63,8 +64,15 @@ for stage in "$@"; do
       timeout 900 python tools/bench_configs.py $S > gpurun_out/${S}_$T.jsonl 2> gpurun_out/${S}_$T.err; cut -c1-260 gpurun_out/${S}_$T.jsonl; tail -2 gpurun_out/${S}_$T.err ;;
     halo)
       N=${A1:-2}
-      timeout 900 bash -c "$(declare -f RUN); RUN $N tools/bench_halo.py $N ${A2:+--$A2}" 2>> gpurun_out/halo_${N}gpu_$T.err | tee -a gpurun_out/halo_${N}gpu_$T.jsonl | cut -c1-400
+      IFS=: read -r _ _ _ HB <<< "$stage"
+      timeout 900 bash -c "$(declare -f RUN); RUN $N tools/bench_halo.py ${HB:-2} ${A2:+--$A2}" 2>> gpurun_out/halo_${N}gpu_$T.err | tee -a gpurun_out/halo_${N}gpu_$T.jsonl | cut -c1-400
       tail -3 gpurun_out/halo_${N}gpu_$T.err ;;
+    full)   # full:N:CONFIG:BATCH[:stock]  -- the unmodified reference STCGNN with the cell installed (tools/bench_full_model.py)
+      N=${A1:-1}; CFG=${A2:-sf}; IFS=: read -r _ _ _ B EXTRA <<< "$stage"; B=${B:-32}
+      FLAGS="--config $CFG --batch $B"; [ "$EXTRA" = stock ] && FLAGS="$FLAGS --stock"; [ "$EXTRA" = adam ] && FLAGS="$FLAGS --adam"
+      if [ "$N" = 1 ]; then timeout 900 python tools/bench_full_model.py $FLAGS 2>> gpurun_out/full_$T.err | tee -a gpurun_out/full_$T.jsonl
+      else timeout 900 bash -c "$(declare -f RUN); RUN $N tools/bench_full_model.py $FLAGS" 2>> gpurun_out/full_$T.err | tee -a gpurun_out/full_$T.jsonl; fi
+      tail -2 gpurun_out/full_$T.err ;;
     trace) timeout 200 python tools/trace_conv.py 2048 16 > gpurun_out/trace_$T.txt 2>&1; tail -5 gpurun_out/trace_$T.txt ;;
     memcheck)
       P=tests/test_cell_gpu.py

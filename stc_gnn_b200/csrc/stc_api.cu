@@ -456,12 +456,6 @@ int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
   if (d.B == 0) return STC_OK;
   STC_TRY(check_arch());
   const WsLayout w = make_layout(d);
-  if (cell_fused_eligible(d, *gs)) {   // SF-class shape: the whole cell in one launch (plus the C x C Chebyshev terms)
-    float* ws = (float*)wsv;
-    STC_TRY(launch_cheby_small(gc, d.C, d.Kc, ws + w.Q, (cudaStream_t)stream));
-    return launch_cell_fwd_fused(d, *gs, ws + w.Q, xt, xt_batch_stride, h_prev, Wg, d.has_bias ? bg : nullptr, Wc,
-                                 d.has_bias ? bc : nullptr, h_out, ws, w, (cudaStream_t)stream);
-  }
   const FwdCtx f{d, w, gs, gc, xt, xt_batch_stride, h_prev, (float*)wsv, (cudaStream_t)stream};
   STC_TRY(fwd_terms_xh(f));
   STC_TRY(fwd_gates(f, Wg, bg));

@@ -159,11 +159,6 @@ enum { OPT_L2_PREFETCH = 1, OPT_GENERIC_EPILOGUE = 4 /* diagnostic: force the ge
 constexpr int TRACE_SLOTS = 16;
 int conv_opt_flags();                                  // cached STC_OPT (default: OPT_L2_PREFETCH)
 void conv_trace_target(long long** buf, int* tiles);   // what stc_debug_trace_set registered (null when off)
-// fused forward cell (stc_cell_fused.cu): dense support that fits one tile, Ks = Kc = 2, h = 16
-bool cell_fused_eligible(const StcDims& d, const StcSupport& gs);
-int launch_cell_fwd_fused(const StcDims& d, const StcSupport& gs, const float* Q, const float* xt, long long xt_bs,
-                          const float* h_prev, const float* Wg, const float* bg, const float* Wc, const float* bc,
-                          float* h_out, float* ws, const WsLayout& w, cudaStream_t st);
 int launch_tf32x3_gemm(const float* A, const float* Bm, float* D, int M, int N, int K, cudaStream_t st);
 int launch_conv_fwd(const ConvArgs& a, cudaStream_t st);
 // wide hidden states (h >= 32, Kc = 2): streamed-weight tcgen05 forward (stc_conv_tc_big.cu)

@@ -353,13 +353,14 @@ def check_dp_parity(stack, leaves, Gs, Gc, bucket, rank, world, dev, b_small=4):
         (loss_fn(stack(Gs, Gc, X), y) * scale).backward()
 
     grads_of(Xg, yg, 1.0)                                   # single process, concatenated batch (mean over world*b)
-    want = [p.grad.detach().clone() for p in leaves]
+    want = [p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p) for p in leaves]   # unused cells: no grad
     s, e = rank * b_small, (rank + 1) * b_small
     grads_of(Xg[s:e], yg[s:e], 1.0 / world)                 # shard loss is a mean over b: scale so that the sum is the global mean
     bucket.allreduce()
     ok = True
     for p, w in zip(leaves, want):
-        err = (p.grad.double() - w.double()).abs()
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        err = (got.double() - w.double()).abs()
         tol = 1e-4 * w.double().abs() + 5e-5 * w.double().abs().mean()
         ok = ok and bool((err <= tol).all())
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)

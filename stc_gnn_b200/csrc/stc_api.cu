@@ -124,6 +124,85 @@ void conv_trace_target(long long** buf, int* tiles) {
   *tiles = g_trace_tiles;
 }
 
+// ---- small-problem concurrency: independent kernels of one cell call on side streams ---------------------------------
+// At the reference's own batch size (32 windows -> 128 row tiles) no kernel fills the 148 SMs and a cell backward is a
+// chain of ten ~10 us launches.  Several of them are independent (dW needs only dx's output, the three dGs outer
+// products and the adjoint hops of Xt / H touch disjoint buffers), so they are forked onto side streams with events and
+// joined back before anything they read is overwritten: the critical path of a backward call drops from 10 to 4
+// kernels.  Everything stays ordered after prior work on the caller's stream and is complete, as seen from that stream,
+// when the call's last event wait has been enqueued; event fork/join is also what CUDA-graph capture expects.
+// Large problems (every kernel fills the device) keep the single-stream order.  STC_CONCURRENCY=0 / 1 forces it off / on.
+struct SidePool {
+  int dev = -1;
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[16] = {};
+  int next_ev = 0;
+  bool ok = false;
+};
+static thread_local SidePool g_pool;
+
+static SidePool* side_pool() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  SidePool& p = g_pool;
+  if (p.dev != dev) {   // first use on this thread / device (streams of another device are simply left behind)
+    p = SidePool();
+    p.dev = dev;
+    p.ok = true;
+    for (auto& s_ : p.side) p.ok = p.ok && cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& e : p.ev) p.ok = p.ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    if (!p.ok) cudaGetLastError();
+  }
+  return p.ok ? &p : nullptr;
+}
+
+static int concurrency_mode() {   // -1 auto, 0 off, 1 on
+  static int cached = -2;
+  if (cached == -2) {
+    const char* e = getenv("STC_CONCURRENCY");
+    cached = (e && e[0]) ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }
+  return cached;
+}
+
+// Fork / join helper of one cell call.  Inactive (every stream() is the caller's stream, fork / join are no-ops) when the
+// problem is large or the pool could not be created.
+struct Lanes {
+  cudaStream_t main;
+  SidePool* pool;
+  bool forked[4] = {false, false, false, false};
+  Lanes(cudaStream_t st, const StcDims& d) : main(st), pool(nullptr) {
+    const int mode = concurrency_mode();
+    const long long rows = (long long)d.B * d.N * d.C;
+    const bool small = rows * (d.Din + 2 * d.h) < (long long)device_sm_count() * 2 * 128 * 48 * 2;   // < ~2 waves of 128-row tiles
+    if (mode == 1 || (mode == -1 && small)) pool = side_pool();
+  }
+  bool active() const { return pool != nullptr; }
+  cudaStream_t stream(int i) const { return pool ? pool->side[i] : main; }
+  cudaEvent_t next_event() { cudaEvent_t e = pool->ev[pool->next_ev]; pool->next_ev = (pool->next_ev + 1) & 15; return e; }
+  int fork_from(cudaStream_t src, int i) {   // side[i] additionally waits for everything queued on src so far
+    if (!pool || src == pool->side[i]) return STC_OK;
+    cudaEvent_t e = next_event();
+    STC_CUDA_OK(cudaEventRecord(e, src));
+    STC_CUDA_OK(cudaStreamWaitEvent(pool->side[i], e, 0));
+    forked[i] = true;
+    return STC_OK;
+  }
+  int fork(int i) { return fork_from(main, i); }   // side[i] continues from the caller's stream's current position
+  int join(int i) {          // the caller's stream waits for everything queued on side[i]
+    if (!pool || !forked[i]) return STC_OK;
+    cudaEvent_t e = next_event();
+    STC_CUDA_OK(cudaEventRecord(e, pool->side[i]));
+    STC_CUDA_OK(cudaStreamWaitEvent(main, e, 0));
+    forked[i] = false;
+    return STC_OK;
+  }
+  int join_all() {
+    for (int i = 0; i < 4; ++i) STC_TRY(join(i));
+    return STC_OK;
+  }
+};
+
 WsLayout make_layout(const StcDims& d) {
   WsLayout w;
   const size_t A = 64;  // 256-byte alignment of every region
@@ -341,6 +420,7 @@ struct FwdCtx {
   const float* h_prev;
   float* ws;
   cudaStream_t st;
+  Lanes* lanes = nullptr;   // set by stc_cell_fwd: the Xt-side terms and the Gc terms may run beside the H-side terms
 };
 
 // spatial Chebyshev terms of Xt and H:  Y_1 = Gs^T Y_0,  Y_k = 2 Gs^T Y_{k-1} - Y_{k-2}
@@ -351,6 +431,12 @@ static int fwd_terms_xh(const FwdCtx& f) {
   const size_t Rh = w.R * d.h, Rx = w.R * d.Din;
   const int CD = d.C * d.Din, CH = d.C * d.h;
   const long long nbs_h = (long long)d.N * CH;
+  // the two recurrences are independent of each other: Xt's on side stream 0 (when lanes are active), H's on the caller's
+  cudaStream_t sx = f.st;
+  if (f.lanes && f.lanes->active() && d.Ks > 1) {
+    STC_TRY(f.lanes->fork(0));
+    sx = f.lanes->stream(0);
+  }
   for (int k = 1; k < d.Ks; ++k) {
     const float alpha = k == 1 ? 1.f : 2.f, beta = k == 1 ? 0.f : -1.f;
     const float* xin = k == 1 ? f.xt : ws + w.Yx + (size_t)(k - 2) * Rx;
@@ -358,12 +444,16 @@ static int fwd_terms_xh(const FwdCtx& f) {
     const float* xz = k == 1 ? nullptr : (k == 2 ? f.xt : ws + w.Yx + (size_t)(k - 3) * Rx);
     const int64_t xz_bs = k == 2 ? f.xt_bs : (int64_t)d.N * CD;
     STC_TRY(launch_support_apply(*f.gs, d.N, d.B, CD, true, xin, xin_bs, xz, xz_bs, ws + w.Yx + (size_t)(k - 1) * Rx,
-                                 alpha, beta, nullptr, 0.f, f.st));
+                                 alpha, beta, nullptr, 0.f, sx));
+  }
+  for (int k = 1; k < d.Ks; ++k) {
+    const float alpha = k == 1 ? 1.f : 2.f, beta = k == 1 ? 0.f : -1.f;
     const float* hin = k == 1 ? f.h_prev : ws + w.Yh + (size_t)(k - 2) * Rh;
     const float* hz = k == 1 ? nullptr : (k == 2 ? f.h_prev : ws + w.Yh + (size_t)(k - 3) * Rh);
     STC_TRY(launch_support_apply(*f.gs, d.N, d.B, CH, true, hin, nbs_h, hz, nbs_h, ws + w.Yh + (size_t)(k - 1) * Rh,
                                  alpha, beta, nullptr, 0.f, f.st));
   }
+  if (f.lanes) STC_TRY(f.lanes->join(0));
   return STC_OK;
 }
 
@@ -456,7 +546,9 @@ int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
   if (d.B == 0) return STC_OK;
   STC_TRY(check_arch());
   const WsLayout w = make_layout(d);
-  const FwdCtx f{d, w, gs, gc, xt, xt_batch_stride, h_prev, (float*)wsv, (cudaStream_t)stream};
+  Lanes lanes((cudaStream_t)stream, d);
+  FwdCtx f{d, w, gs, gc, xt, xt_batch_stride, h_prev, (float*)wsv, (cudaStream_t)stream};
+  f.lanes = &lanes;
   STC_TRY(fwd_terms_xh(f));
   STC_TRY(fwd_gates(f, Wg, bg));
   STC_TRY(fwd_terms_rh(f));
@@ -497,7 +589,7 @@ int stc_cell_fwd_stage(const StcDims* dp, int32_t stage, const float* gc, const 
 //   ybar[k-1] += (k>=2 ? 2 : 1) * Gs * ybar[k];  ybar[k-2] -= ybar[k];  dGs += coef * Y_{k-1} (x) ybar[k]
 static int adjoint_chain(const StcDims& d, const StcSupport& gs, int width, const float* y0, int64_t y0_bs,
                          const float* yk /* terms k>=1, contiguous */, float* ybar0, float* ybark /* k>=1 */,
-                         float* dGs, cudaStream_t st) {
+                         float* dGs, cudaStream_t st, Lanes* lanes = nullptr, int outer_lane = 1) {
   const size_t Rw = (size_t)d.B * d.N * width;
   const int64_t nbs = (int64_t)d.N * width;
   for (int k = d.Ks - 1; k >= 1; --k) {
@@ -507,7 +599,14 @@ static int adjoint_chain(const StcDims& d, const StcSupport& gs, int width, cons
     if (dGs) {
       const float* yprev = k == 1 ? y0 : yk + (size_t)(k - 2) * Rw;
       const int64_t yprev_bs = k == 1 ? y0_bs : nbs;
-      STC_TRY(launch_support_outer(d.N, d.B, width, yprev, yprev_bs, yb_k, coef, dGs, st));
+      // the outer product only READS ybar[k] (final once the previous hop on `st` is queued) and Y[k-1]; nothing later in
+      // the chain writes either, so it runs beside the hops on the outer lane and is joined at the end of the call
+      cudaStream_t so = st;
+      if (lanes && lanes->active()) {
+        STC_TRY(lanes->fork_from(st, outer_lane));
+        so = lanes->stream(outer_lane);
+      }
+      STC_TRY(launch_support_outer(d.N, d.B, width, yprev, yprev_bs, yb_k, coef, dGs, so));
     }
     float* axpy = nullptr;
     if (k >= 2) axpy = k == 2 ? ybar0 : ybark + (size_t)(k - 3) * Rw;
@@ -533,6 +632,7 @@ struct BwdCtx {
   float* sv;          // saved (read-only here)
   float* sc;          // scratch
   cudaStream_t st;
+  Lanes* lanes = nullptr;   // set by stc_cell_bwd: dW runs beside the adjoint hops on side stream 0
   bool want_dGc() const { return dGc != nullptr && d.Kc > 1; }
   float* dYx0() const { return d_xt ? d_xt : sc + w.dYx0; }
 };
@@ -578,6 +678,15 @@ static int bwd_begin(const BwdCtx& b, float* dWg, float* dbg, float* dWc, float*
   return STC_OK;
 }
 
+// dW = Y_k^T [Ds | Dm_c] needs only what dx just wrote (dpre) and forward's saved terms: side stream 0 when lanes are active
+static int launch_dw_beside(const BwdCtx& b, const ConvArgs& a) {
+  if (b.lanes && b.lanes->active()) {
+    STC_TRY(b.lanes->fork(0));
+    return launch_conv_bwd_dw(a, b.lanes->stream(0));
+  }
+  return launch_conv_bwd_dw(a, b.st);
+}
+
 // candidate conv adjoint: leaves d(r*H terms) in scratch dYr[0..Ks-1], the x-part adjoint in dYx0 / scratch dYx
 static int bwd_candi(const BwdCtx& b, const float* Wc, float* dWc, float* dbc) {
   const StcDims& d = b.d;
@@ -602,7 +711,7 @@ static int bwd_candi(const BwdCtx& b, const float* Wc, float* dWc, float* dbc) {
   a.Psave = b.sv + w.Pc;
   a.Wimg = (w.saved_total > w.Wimg_c && w.scratch_total > w.Wimg_dx) ? b.sc + w.Wimg_dx : nullptr;   // wide forward ran
   STC_TRY(launch_conv_bwd_dx(a, b.st));
-  return launch_conv_bwd_dw(a, b.st);
+  return launch_dw_beside(b, a);
 }
 
 // GRU elementwise adjoint + gates conv adjoint (reads d(r*H) = scratch dYr[0]); then dGc from the dT_k(Gc) partials
@@ -629,8 +738,9 @@ static int bwd_gates(const BwdCtx& b, const float* Wg, float* dWg, float* dbg) {
   a.dW = dWg;
   a.Psave = b.sv + w.Pg;
   a.Wimg = (w.Wimg_c > w.Wimg_g && w.scratch_total > w.Wimg_dx) ? b.sc + w.Wimg_dx : nullptr;   // wide forward ran
+  if (b.lanes) STC_TRY(b.lanes->join(0));   // the candidate's dW reads dpre, which this dx overwrites
   STC_TRY(launch_conv_bwd_dx(a, b.st));
-  STC_TRY(launch_conv_bwd_dw(a, b.st));
+  STC_TRY(launch_dw_beside(b, a));
   if (b.want_dGc()) STC_TRY(launch_cheby_small_bwd(b.gc, b.sv + w.Q, b.sc + w.dQ, d.C, d.Kc, b.dGc, b.st));
   return STC_OK;
 }
@@ -655,21 +765,33 @@ int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
   const WsLayout w = make_layout(d);
   STC_TRY(check_arch());
   cudaStream_t st = (cudaStream_t)stream;
-  const BwdCtx b{d, w, gc, xt, xt_batch_stride, h_prev, d_h_out, d_xt, d_h_prev, dGc,
-                 const_cast<float*>((const float*)savedv), (float*)scratchv, st};
+  Lanes lanes(st, d);
+  BwdCtx b{d, w, gc, xt, xt_batch_stride, h_prev, d_h_out, d_xt, d_h_prev, dGc,
+           const_cast<float*>((const float*)savedv), (float*)scratchv, st};
+  b.lanes = &lanes;
   STC_TRY(bwd_begin(b, dWg, dbg, dWc, dbc, dGs, accumulate_params));
   if (d.B == 0) return STC_OK;
   const size_t Rh = w.R * d.h;
   const int CD = d.C * d.Din, CH = d.C * d.h;
 
+  // Lanes (small problems only; otherwise everything below is one stream in program order):
+  //   caller's stream   dx_c -> hops of d(rH) -> dx_g -> Gc chain -> hops of dH
+  //   side 0            dW_c (joined before dx_g rewrites dpre), then dW_g
+  //   side 1            the dGs outer products of all three chains (atomics into dGs)
+  //   side 2            hops of dXt
   STC_TRY(bwd_candi(b, Wc, dWc, dbc));
   // d(rH) through the spatial recurrence
   STC_TRY(adjoint_chain(d, *gs, CH, b.sv + w.Yr, (int64_t)d.N * CH, b.sv + w.Yr + Rh, b.sc + w.dYr, b.sc + w.dYr + Rh,
-                        dGs, st));
+                        dGs, st, &lanes, 1));
   STC_TRY(bwd_gates(b, Wg, dWg, dbg));
-  STC_TRY(adjoint_chain(d, *gs, CD, xt, xt_batch_stride, b.sv + w.Yx, b.dYx0(), b.sc + w.dYx, dGs, st));
-  STC_TRY(adjoint_chain(d, *gs, CH, h_prev, (int64_t)d.N * CH, b.sv + w.Yh, d_h_prev, b.sc + w.dYh, dGs, st));
-  return STC_OK;
+  cudaStream_t sx = st;
+  if (lanes.active() && d.Ks > 1) {
+    STC_TRY(lanes.fork(2));
+    sx = lanes.stream(2);
+  }
+  STC_TRY(adjoint_chain(d, *gs, CD, xt, xt_batch_stride, b.sv + w.Yx, b.dYx0(), b.sc + w.dYx, dGs, sx, &lanes, 1));
+  STC_TRY(adjoint_chain(d, *gs, CH, h_prev, (int64_t)d.N * CH, b.sv + w.Yh, d_h_prev, b.sc + w.dYh, dGs, st, &lanes, 1));
+  return lanes.join_all();
 }
 
 int stc_cell_bwd_scratch_layout(const StcDims* dp, int64_t* offsets, int32_t n_offsets) {

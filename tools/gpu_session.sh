@@ -6,7 +6,7 @@
 #   tests            pytest -m gpu (whole suite)           tests2     the multi-rank NCCL tests only
 #   tests:EXPR       pytest -m gpu -k EXPR                 smoke      __graft_entry__.smoke()
 #   bench[:N]        headline bench line (torchrun for N>1) refarm    bench.py --impl reference
-#   bench_b:B        headline bench at batch B (no baselines)
+#   bench_b:B        headline bench at batch B (no baselines)   bench_g:B  the same step replayed from a CUDA graph
 #   g4096[:N[:B]]    bench.py --workload g4096             sweep      config 2 batch sweep (tools/bench_configs.py)
 #   launches[:B]     ncu launch list of one bench step     ncu[:REGEX[:SKIP[:COUNT]]]  one ncu --set full capture
 #   support|config3|config4|config5   tools/bench_configs.py side workloads
@@ -43,6 +43,9 @@ for stage in "$@"; do
     bench_b)
       O=gpurun_out/bench_b${A1}_$T
       timeout 600 python bench.py --batch "$A1" --no-cpu-baseline --no-eager-baseline 2> $O.err > $O.json; tail -2 $O.err; cut -c1-300 $O.json ;;
+    bench_g)   # CUDA-graph replay of the whole step at batch A1
+      O=gpurun_out/bench_graph_b${A1}_$T
+      timeout 600 python bench.py --batch "$A1" --cuda-graph --no-cpu-baseline --no-eager-baseline --no-roofline 2> $O.err > $O.json; tail -2 $O.err; cut -c1-300 $O.json ;;
     refarm) timeout 600 python bench.py --impl reference 2> gpurun_out/ref_$T.err > gpurun_out/ref_$T.json; cut -c1-300 gpurun_out/ref_$T.json ;;
     g4096)
       N=${A1:-1}; B=${A2:-4}; O=gpurun_out/g4096_${N}gpu_b${B}_$T

@@ -54,6 +54,20 @@ def _dims(B, N, C, Din, h, Ks, Kc, act, has_bias) -> _lib.StcDims:
     return _lib.StcDims(B, N, C, Din, h, Ks, Kc, act, 1 if has_bias else 0)
 
 
+_SIZES = {}
+
+
+def _buffer_floats(lib, dims: _lib.StcDims, key):
+    """(saved, scratch) buffer sizes in floats of a cell call, cached per shape: at the reference's batch size a training
+    step is bound by host-side call overhead (48 cell calls), so the two size queries are not repeated."""
+    hit = _SIZES.get(key)
+    if hit is None:
+        if len(_SIZES) > 256:
+            _SIZES.clear()
+        hit = _SIZES[key] = (lib.stc_cell_saved_bytes(dims) // 4, lib.stc_cell_bwd_scratch_bytes(dims) // 4)
+    return hit
+
+
 def _ptr(t):
     return t.data_ptr() if t is not None else None
 
@@ -99,7 +113,8 @@ class _CellFunction(torch.autograd.Function):
         Xt_c = Xt if (B == 0 or Xt[0].is_contiguous()) else Xt.contiguous()
         xbs = Xt_c.stride(0) if B > 1 else N * C * Din
         dims = _dims(B, N, C, Din, h, Ks, Kc, act, bg is not None)
-        saved = torch.empty(lib.stc_cell_saved_bytes(dims) // 4, dtype=torch.float32, device=Xt.device)
+        ctx.size_key = (B, N, C, Din, h, Ks, Kc, act, bg is not None)
+        saved = torch.empty(_buffer_floats(lib, dims, ctx.size_key)[0], dtype=torch.float32, device=Xt.device)
         Hn = torch.empty((B, N, C, h), dtype=torch.float32, device=Xt.device)
         stream = torch.cuda.current_stream().cuda_stream
         status = 0 if B == 0 else lib.stc_cell_fwd(dims, gs_struct, Gc_c.data_ptr(), Xt_c.data_ptr(), xbs, H_c.data_ptr(),
@@ -165,7 +180,7 @@ class _CellFunction(torch.autograd.Function):
         returned[2], returned[3] = dXt, dH
         if B == 0:  # empty batch: every parameter gradient is zero (the targets are zeroed or untouched), nothing to launch
             return tuple(returned)
-        scratch = torch.empty(lib.stc_cell_bwd_scratch_bytes(dims) // 4, dtype=torch.float32, device=dev)
+        scratch = torch.empty(_buffer_floats(lib, dims, ctx.size_key)[1], dtype=torch.float32, device=dev)
         status = lib.stc_cell_bwd(dims, gs_struct, Gc.data_ptr(), Xt.data_ptr(), ctx.xbs, H.data_ptr(), Wg.data_ptr(),
                                   Wc.data_ptr(), dHn.data_ptr(), _ptr(dXt), dH.data_ptr(), dWg.data_ptr(), _ptr(dbg),
                                   dWc.data_ptr(), _ptr(dbc), _ptr(dGs), _ptr(dGc), 1, saved.data_ptr(),

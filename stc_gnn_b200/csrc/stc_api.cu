@@ -174,7 +174,8 @@ struct Lanes {
   Lanes(cudaStream_t st, const StcDims& d) : main(st), pool(nullptr) {
     const int mode = concurrency_mode();
     const long long rows = (long long)d.B * d.N * d.C;
-    const bool small = rows * (d.Din + 2 * d.h) < (long long)device_sm_count() * 2 * 128 * 48 * 2;   // < ~2 waves of 128-row tiles
+    // measured on the SF stack (profiles/r3g_*): +4 % at B = 512 (256 K rows), -1 % at B = 4096; threshold ~ B = 600
+    const bool small = rows * (d.Din + 2 * d.h) < (long long)device_sm_count() * 2 * 128 * 48 * 8;
     if (mode == 1 || (mode == -1 && small)) pool = side_pool();
   }
   bool active() const { return pool != nullptr; }

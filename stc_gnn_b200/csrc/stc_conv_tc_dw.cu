@@ -213,7 +213,8 @@ tc_conv_bwd_dw_kernel(const ConvArgs a, const TcDwPlan p) {
     fence_before_sync();   // the reads above are ordered before the MMAs issued after the next __syncthreads
   }
 
-  // ---- one atomicAdd per owned element ----
+  // ---- one (vector) atomic per owned element group ----
+  const bool dw_v4 = (Hout & 3) == 0 && (col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dW) & 15) == 0;
   if (own && mrow < p.M1) {
     const int k = mrow / p.KBL, kb = mrow - k * p.KBL;
     const int l = kb < h ? Din + kb : (kb - h < Din ? kb - h : -1);
@@ -222,11 +223,19 @@ tc_conv_bwd_dw_kernel(const ConvArgs a, const TcDwPlan p) {
       for (int i = 0; i < NCH; ++i) {
         if (i * 8 >= ncols_half) break;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8; j += 4) {
           const int n = col0 + i * 8 + j;
-          if (n < p.N1) {
-            const int c = n / Hout, o = n - c * Hout;
-            atomicAdd(&a.dW[((size_t)(k * a.Kc + c) * L + l) * Hout + o], acc[i][j]);
+          const int c = n / Hout, o = n - c * Hout;
+          float* dst = &a.dW[((size_t)(k * a.Kc + c) * L + l) * Hout + o];
+          if (dw_v4 && n + 3 < p.N1) {
+            red_add_v4(dst, acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N1) {
+                const int ce = (n + e) / Hout, oe = (n + e) - ce * Hout;
+                atomicAdd(&a.dW[((size_t)(k * a.Kc + ce) * L + l) * Hout + oe], acc[i][j + e]);
+              }
           }
         }
       }
@@ -455,7 +464,8 @@ tc_conv_bwd_dw_pipe_kernel(const ConvArgs a, const TcDwPipePlan p) {
         }
       }
     }
-    // ---- one atomicAdd per owned element ----
+    // ---- one (vector) atomic per owned element group ----
+    const bool dw_v4 = (Hout & 3) == 0 && (col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dW) & 15) == 0;
     if (own && mrow < p.M1) {
       const int k = mrow / p.KBL, kb = mrow - k * p.KBL;
       const int l = kb < h ? Din + kb : (kb - h < Din ? kb - h : -1);
@@ -464,11 +474,20 @@ tc_conv_bwd_dw_pipe_kernel(const ConvArgs a, const TcDwPipePlan p) {
         for (int i = 0; i < NCH; ++i) {
           if (i * 8 >= ncols_half) break;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 8; j += 4) {
             const int n = col0 + i * 8 + j;
-            if (n < p.N1) {
-              const int c = n / Hout, o = n - c * Hout;
-              atomicAdd(&a.dW[((size_t)(k * a.Kc + c) * L + l) * Hout + o], acc[i][j]);
+            const int c = n / Hout, o = n - c * Hout;
+            float* dst = &a.dW[((size_t)(k * a.Kc + c) * L + l) * Hout + o];
+            // Hout % 4 == 0 and n % 4 == 0: the four columns stay inside one categorical block and one 16-byte slot
+            if (dw_v4 && n + 3 < p.N1) {
+              red_add_v4(dst, acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n + e < p.N1) {
+                  const int ce = (n + e) / Hout, oe = (n + e) - ce * Hout;
+                  atomicAdd(&a.dW[((size_t)(k * a.Kc + ce) * L + l) * Hout + oe], acc[i][j + e]);
+                }
             }
           }
         }

@@ -483,13 +483,21 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
   if (since_drain > 0) drain();
 
   if (nrow < N) {
+    const bool v4 = (N & 3) == 0 && (col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(dG) & 15) == 0;
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
       if (ch * 8 < ncols_half) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; i += 4) {
           const int m = col0 + ch * 8 + i;
-          if (m < N) atomicAdd(&dG[(size_t)nrow * N + m], coef * acc[ch][i]);
+          float* dst = &dG[(size_t)nrow * N + m];
+          if (v4 && m + 3 < N) {
+            red_add_v4(dst, coef * acc[ch][i], coef * acc[ch][i + 1], coef * acc[ch][i + 2], coef * acc[ch][i + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (m + e < N) atomicAdd(dst + e, coef * acc[ch][i + e]);
+          }
         }
       }
     }

@@ -268,6 +268,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// ---- vector reduction into global memory ----------------------------------------------------------------
+// red.global.add.v4.f32 (sm_90+): one L2 atomic transaction for four consecutive floats.  The end-of-kernel
+// accumulations (dW, dGs: every CTA adds its partial sums into the same few thousand addresses) are bound by the
+// number of atomic operations the L2 slices retire, not by bytes -- a quarter of the operations is a quarter of that
+// fixed per-launch cost.  p must be 16-byte aligned.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

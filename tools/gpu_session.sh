@@ -63,6 +63,13 @@ for stage in "$@"; do
       ncu -i gpurun_out/prof_$T.ncu-rep --page raw --csv > gpurun_out/prof_${T}_raw.csv 2>/dev/null
       SZ=$(stat -c %s gpurun_out/prof_$T.ncu-rep 2>/dev/null || echo 0); echo "report bytes $SZ"
       if [ "$SZ" -gt 40000000 ]; then rm gpurun_out/prof_$T.ncu-rep; echo "report too large for gpurun_out: kept the raw csv only"; fi ;;
+    ncucfg)   # ncucfg:CONFIG:REGEX:SKIP:COUNT -- one ncu --set full capture of a side workload of tools/bench_configs.py
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"${A2:-big}" -s ${A3:-20} -c 12 \
+        -o gpurun_out/prof_${A1}_$T -f python tools/bench_configs.py $A1 > gpurun_out/ncu_${A1}_$T.log 2>&1
+      tail -2 gpurun_out/ncu_${A1}_$T.log
+      ncu -i gpurun_out/prof_${A1}_$T.ncu-rep --page raw --csv > gpurun_out/prof_${A1}_${T}_raw.csv 2>/dev/null
+      SZ=$(stat -c %s gpurun_out/prof_${A1}_$T.ncu-rep 2>/dev/null || echo 0); echo "report bytes $SZ"
+      if [ "$SZ" -gt 40000000 ]; then rm gpurun_out/prof_${A1}_$T.ncu-rep; echo "kept the raw csv only"; fi ;;
     support|config3|config4|config5|sweep)
       timeout 900 python tools/bench_configs.py $S > gpurun_out/${S}_$T.jsonl 2> gpurun_out/${S}_$T.err; cut -c1-260 gpurun_out/${S}_$T.jsonl; tail -2 gpurun_out/${S}_$T.err ;;
     halo)

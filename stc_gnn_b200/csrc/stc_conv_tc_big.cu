@@ -969,14 +969,23 @@ tc_conv_bwd_dw_big_kernel(const ConvArgs a, const BigDwPlan p) {
   if (nchunks > 0 && mrow < p.KBL) {
     const int l = mrow < h ? Din + mrow : (mrow - h < Din ? mrow - h : -1);
     if (l >= 0) {
+      const bool v4 = (Hout & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dW) & 15) == 0;   // 16-byte vector reductions
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8; j += 4) {
           const int n = nh * 128 + 32 * qtr + 8 * i + j;
-          if (n < p.N1) {
-            const int c = n / Hout, o = n - c * Hout;
-            atomicAdd(&a.dW[((size_t)(k * a.Kc + c) * L + l) * Hout + o], acc[i][j]);
+          const int c = n / Hout, o = n - c * Hout;
+          float* dst = &a.dW[((size_t)(k * a.Kc + c) * L + l) * Hout + o];
+          if (v4 && n + 3 < p.N1) {
+            red_add_v4(dst, acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N1) {
+                const int ce = (n + e) / Hout, oe = (n + e) - ce * Hout;
+                atomicAdd(&a.dW[((size_t)(k * a.Kc + ce) * L + l) * Hout + oe], acc[i][j + e]);
+              }
           }
         }
     }

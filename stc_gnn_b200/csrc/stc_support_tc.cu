@@ -315,7 +315,9 @@ int try_launch_support_tc(const float* G, int N, int B, int width, bool transpos
 //      the 3xTF32 cross terms; every TO_DRAIN atoms they are drained into fp32 registers (bounded chains, see
 //      profiles/r1_tc_precision.txt); one atomicAdd per element per CTA at the end.
 // ------------------------------------------------------------------------------------------------
-constexpr int TO_DRAIN = 48;
+constexpr int TO_DRAIN = 32;          // atoms per accumulation chain set (two slots: 16 atoms = 64 K-steps per accumulator)
+constexpr int TO_STAGES = 3;          // shared-memory operand ring
+constexpr int TO_THREADS = CV_THREADS + 32;   // 8 producer / drain warps + 1 MMA-issue warp
 
 struct TcOuterPlan {
   int N, Npad, W, B, atoms_per_sample;
@@ -323,7 +325,13 @@ struct TcOuterPlan {
   uint32_t imgA, imgB, off_bar, smem_bytes;
 };
 
-__global__ void __launch_bounds__(CV_THREADS, 1)
+// Warp-specialised since round 2: with the MMA issue inside the producers' barrier-coupled loop one atom cost
+// stage + block barrier + 12 MMA issues (~3.2 K cycles, 0.33 of HBM).  Now warp 8 only issues MMAs, fed through a
+// 3-stage ring with full / empty mbarriers, and the hi/lo images of the B operand are adjacent so that
+// A_hi x [B_hi ; B_lo] is ONE N = 2 Npad MMA filling the main and the cross-term accumulator of a slot together:
+// 2 MMAs per K-step instead of 3.  TMEM: two slots of [main | cross] (4 Npad columns), used round-robin and drained
+// into fp32 registers every TO_DRAIN atoms (bounded chains: the tensor core truncates on accumulate).
+__global__ void __launch_bounds__(TO_THREADS, 1)
 tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __restrict__ Bm, float coef, float* dG,
                 const TcOuterPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -331,15 +339,20 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, W = p.W;
   const uint32_t bufsz = 2 * p.imgA + 2 * p.imgB;    // [A hi | A lo | B hi | B lo]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [TO_STAGES] producers -> MMA warp
+  uint64_t* empty = full + TO_STAGES;                                // [TO_STAGES] MMA commit -> producers
+  uint64_t* drained = empty + TO_STAGES;                             // producers have read the accumulators
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int i = 0; i < TO_STAGES; ++i) {
+      mbar_init(&full[i], CV_THREADS / 32);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(drained, CV_THREADS / 32);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  for (uint32_t i = tid * 16u; i < 2 * bufsz; i += CV_THREADS * 16u)   // rows >= N stay zero for good
+  for (uint32_t i = tid * 16u; i < TO_STAGES * bufsz; i += TO_THREADS * 16u)   // rows >= N stay zero for good
     *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_async_smem();
   fence_before_sync();
@@ -347,161 +360,164 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
   fence_after_sync();
   const int warp_u = uniform_warp_index();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
-  const uint32_t idesc = make_idesc_tf32(128, p.Npad);
-  const uint32_t d_small = tmem_base + (uint32_t)(3 * p.Npad);
-
-  // staging map: chunk q of rows r0 + 32 i of either operand
-  const int q = tid & 7, r0 = tid >> 3;
-  uint32_t soff[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) soff[i] = atom_chunk_offset(r0 + 32 * i, q);
-  // two register sets: the operands of atom seq + 2 are requested right after atom seq has been staged, so two atoms
-  // (2 x 25 KB per SM) are always in flight -- one was not enough to cover the HBM latency (Little's law)
-  float4 ra0[4], rb0[4], ra1[4], rb1[4];
-  auto fetch = [&](int s, int at, float4 (&ra)[4], float4 (&rb)[4]) {   // s-th sample of this CTA, atom `at` within the sample
-    const long long b = blockIdx.x + s * (long long)gridDim.x;
-    const int j = at * ATOM_K + q * 4;
-    const bool ok = j < W;               // W % 4 == 0
-    const float* pa = A + b * a_bs + j;
-    const float* pb = Bm + b * (long long)N * W + j;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + 32 * i;
-      const bool live = ok && r < N;
-      ra[i] = live ? __ldg(reinterpret_cast<const float4*>(pa + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      rb[i] = live ? __ldg(reinterpret_cast<const float4*>(pb + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto stage = [&](int buf, const float4 (&ra)[4], const float4 (&rb)[4]) {
-    uint8_t* base = smem + (size_t)buf * bufsz;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (r0 + 32 * i < N) {
-        store_split4(base, base + p.imgA, soff[i], ra[i]);
-        store_split4(base + 2 * p.imgA, base + 2 * p.imgA + p.imgB, soff[i], rb[i]);
-      }
-    }
-  };
-
   const int nsamples = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const long long natoms = (long long)nsamples * p.atoms_per_sample;
 
-  // accumulators: thread (sub-partition sp, half) owns row 32 sp + lane and Npad/2 columns
-  const int sp = warp & 3, half = warp >> 2;
-  const int nrow = sp * 32 + lane;
-  const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
-  const int ncols_half = p.Npad >> 1, col0 = half * ncols_half;
-  float acc[8][8];   // Npad <= 128 -> at most 64 columns per thread
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-  bool pend[2] = {false, false};
-  uint32_t ph[2] = {0u, 0u};
-  bool acc_main[3] = {false, false, false}, acc_small = false;
-  int since_drain = 0;
-  auto drain = [&]() {
-#pragma unroll
-    for (int b = 0; b < 2; ++b)
-      if (pend[b]) {
-        mbar_wait(&bars[b], ph[b]);
-        ph[b] ^= 1u;
-        pend[b] = false;
+  if (warp_u == CV_THREADS / 32) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc2 = make_idesc_tf32(128, 2 * p.Npad), idesc1 = make_idesc_tf32(128, p.Npad);
+    int at = 0, in_set = 0;
+    uint32_t drain_parity = 0;
+    for (long long seq = 0; seq < natoms; ++seq) {
+      const int buf = (int)(seq % TO_STAGES);
+      const uint32_t use = (uint32_t)(seq / TO_STAGES);
+      mbar_wait(&full[buf], use & 1u);
+      if (seq > 0 && in_set == 0) {   // first atom of a new chain set: the producers must have drained the accumulators
+        mbar_wait(drained, drain_parity);
+        drain_parity ^= 1u;
       }
-    fence_after_sync();
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      if (ch * 8 < ncols_half) {
-        float v[8], t[8];
-        const uint32_t cc = (uint32_t)(col0 + ch * 8);
-        tmem_ld8(tl + (uint32_t)(3 * p.Npad) + cc, v);
-#pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          if (acc_main[m]) {
-            tmem_ld8(tl + (uint32_t)(m * p.Npad) + cc, t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += t[i];
-          }
+      const int kleft = W - at * ATOM_K;
+      const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
+      const int slot = in_set & 1;
+      const bool fresh = in_set < 2;  // first atom into this slot since the drain
+      if (elect_one_sync()) {
+        fence_after_sync();
+        const uint32_t base = smem_u32(smem + (size_t)buf * bufsz);
+        const uint32_t a_hi = base, a_lo = base + p.imgA, b_hi = base + 2 * p.imgA;   // b_lo follows b_hi directly
+        const uint32_t d_main = tmem_base + (uint32_t)(slot * 2 * p.Npad), d_cross = d_main + (uint32_t)p.Npad;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t o = ks * 32;
+          const uint64_t ah = make_smem_desc_sw128(a_hi + o), al = make_smem_desc_sw128(a_lo + o);
+          const uint64_t bh = make_smem_desc_sw128(b_hi + o);
+          mma_tf32(d_main, ah, bh, idesc2, (fresh && ks == 0) ? 0u : 1u);   // [main | cross] (+)= A_hi x [B_hi ; B_lo]
+          mma_tf32(d_cross, al, bh, idesc1, 1u);                            // cross += A_lo x B_hi
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[ch][i] += v[i];
+        mma_commit(&empty[buf]);
       }
+      __syncwarp();
+      if (++at == p.atoms_per_sample) at = 0;
+      if (++in_set == TO_DRAIN) in_set = 0;
     }
-    fence_before_sync();
-    acc_main[0] = acc_main[1] = acc_main[2] = false;
-    acc_small = false;
-    since_drain = 0;
-  };
+  } else {
+    // =============================== producers / drain / epilogue ===============================
+    // staging map: chunk q of rows r0 + 32 i of either operand
+    const int q = tid & 7, r0 = tid >> 3;
+    uint32_t soff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) soff[i] = atom_chunk_offset(r0 + 32 * i, q);
+    // two register sets: the operands of atom seq + 2 are requested right after atom seq has been staged, so two atoms
+    // are always in flight from HBM on top of the staged ring
+    float4 ra0[4], rb0[4], ra1[4], rb1[4];
+    auto fetch = [&](int s_, int at_, float4 (&ra)[4], float4 (&rb)[4]) {   // s_-th sample of this CTA, atom at_ of it
+      const long long b = blockIdx.x + s_ * (long long)gridDim.x;
+      const int j = at_ * ATOM_K + q * 4;
+      const bool ok = j < W;               // W % 4 == 0
+      const float* pa = A + b * a_bs + j;
+      const float* pb = Bm + b * (long long)N * W + j;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
+        const bool live = ok && r < N;
+        ra[i] = live ? __ldg(reinterpret_cast<const float4*>(pa + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rb[i] = live ? __ldg(reinterpret_cast<const float4*>(pb + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto stage = [&](int buf, const float4 (&ra)[4], const float4 (&rb)[4]) {
+      uint8_t* base = smem + (size_t)buf * bufsz;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (r0 + 32 * i < N) {
+          store_split4(base, base + p.imgA, soff[i], ra[i]);
+          store_split4(base + 2 * p.imgA, base + 2 * p.imgA + p.imgB, soff[i], rb[i]);
+        }
+      }
+    };
+    // accumulators: thread (sub-partition sp, half) owns row 32 sp + lane and Npad/2 columns
+    const int sp = warp & 3, half = warp >> 2;
+    const int nrow = sp * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(sp * 32) << 16);
+    const int ncols_half = p.Npad >> 1, col0 = half * ncols_half;
+    float acc[8][8];   // Npad <= 128 -> at most 64 columns per thread
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  int at = 0;                           // atom of `seq` within its sample
-  int pf_s = 0, pf_at = 0;              // (sample, atom) the next fetch targets: runs two atoms ahead, no divisions
-  auto advance_pf = [&]() {
-    if (++pf_at == p.atoms_per_sample) {
-      pf_at = 0;
-      ++pf_s;
-    }
-  };
-  auto step = [&](long long seq, float4 (&ra)[4], float4 (&rb)[4]) {
-    const int buf = (int)(seq & 1);
-    if (pend[buf]) {   // the MMAs that read this buffer two atoms ago
-      mbar_wait(&bars[buf], ph[buf]);
-      ph[buf] ^= 1u;
-      pend[buf] = false;
-    }
-    stage(buf, ra, rb);
-    if (seq + 2 < natoms) fetch(pf_s, pf_at, ra, rb);
-    advance_pf();
-    fence_async_smem();
-    __syncthreads();
-    const int kleft = W - at * ATOM_K;
-    const int ksteps = kleft >= ATOM_K ? 4 : (kleft + 7) / 8;
-    const int mi = since_drain % 3;
-    if (warp_u == 0 && elect_one_sync()) {   // uniform issue path, see stc_tc.cuh
+    int in_set = 0;
+    auto drain = [&](long long last_seq) {   // every atom up to last_seq has been handed to the MMA warp
+      const int lb = (int)(last_seq % TO_STAGES);
+      mbar_wait(&empty[lb], (uint32_t)(last_seq / TO_STAGES) & 1u);   // commits complete in order: this one covers all
       fence_after_sync();
-      const uint32_t base = smem_u32(smem + (size_t)buf * bufsz);
-      bool am = acc_main[mi], as = acc_small;
-      mma_atom_3x_split(tmem_base + (uint32_t)(mi * p.Npad), d_small, base, base + p.imgA, base + 2 * p.imgA,
-                        base + 2 * p.imgA + p.imgB, ksteps, idesc, am, as);
-      mma_commit(&bars[buf]);
-    }
-    acc_main[mi] = true;
-    acc_small = true;
-    pend[buf] = true;
-    ++since_drain;
-    if (++at == p.atoms_per_sample) at = 0;
-    if (since_drain >= TO_DRAIN) drain();
-  };
-  if (natoms > 0) fetch(pf_s, pf_at, ra0, rb0);
-  advance_pf();
-  if (natoms > 1) fetch(pf_s, pf_at, ra1, rb1);
-  advance_pf();
-  for (long long seq = 0; seq < natoms; seq += 2) {
-    step(seq, ra0, rb0);
-    if (seq + 1 < natoms) step(seq + 1, ra1, rb1);
-  }
-  if (since_drain > 0) drain();
+      const int slots = in_set >= 2 ? 2 : in_set;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        if (ch * 8 < ncols_half) {
+          const uint32_t cc = (uint32_t)(col0 + ch * 8);
+          for (int sl = 0; sl < slots; ++sl) {
+            float v[8], t[8];
+            tmem_ld8(tl + (uint32_t)(sl * 2 * p.Npad + p.Npad) + cc, v);
+            tmem_ld8(tl + (uint32_t)(sl * 2 * p.Npad) + cc, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[ch][i] += v[i] + t[i];
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(drained);
+      in_set = 0;
+    };
 
-  if (nrow < N) {
-    const bool v4 = (N & 3) == 0 && (col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(dG) & 15) == 0;
+    int pf_s = 0, pf_at = 0;              // (sample, atom) the next fetch targets: runs two atoms ahead, no divisions
+    auto advance_pf = [&]() {
+      if (++pf_at == p.atoms_per_sample) {
+        pf_at = 0;
+        ++pf_s;
+      }
+    };
+    auto step = [&](long long seq, float4 (&ra)[4], float4 (&rb)[4]) {
+      const int buf = (int)(seq % TO_STAGES);
+      const uint32_t use = (uint32_t)(seq / TO_STAGES);
+      if (use > 0) mbar_wait(&empty[buf], (use - 1u) & 1u);   // the MMAs of this buffer's previous fill have read it
+      stage(buf, ra, rb);
+      if (seq + 2 < natoms) fetch(pf_s, pf_at, ra, rb);
+      advance_pf();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[buf]);
+      if (++in_set == TO_DRAIN || seq == natoms - 1) drain(seq);
+    };
+    if (natoms > 0) fetch(pf_s, pf_at, ra0, rb0);
+    advance_pf();
+    if (natoms > 1) fetch(pf_s, pf_at, ra1, rb1);
+    advance_pf();
+    for (long long seq = 0; seq < natoms; seq += 2) {
+      step(seq, ra0, rb0);
+      if (seq + 1 < natoms) step(seq + 1, ra1, rb1);
+    }
+
+    if (nrow < N) {
+      const bool v4 = (N & 3) == 0 && (col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(dG) & 15) == 0;
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      if (ch * 8 < ncols_half) {
+      for (int ch = 0; ch < 8; ++ch) {
+        if (ch * 8 < ncols_half) {
 #pragma unroll
-        for (int i = 0; i < 8; i += 4) {
-          const int m = col0 + ch * 8 + i;
-          float* dst = &dG[(size_t)nrow * N + m];
-          if (v4 && m + 3 < N) {
-            red_add_v4(dst, coef * acc[ch][i], coef * acc[ch][i + 1], coef * acc[ch][i + 2], coef * acc[ch][i + 3]);
-          } else {
+          for (int i = 0; i < 8; i += 4) {
+            const int m = col0 + ch * 8 + i;
+            float* dst = &dG[(size_t)nrow * N + m];
+            if (v4 && m + 3 < N) {
+              red_add_v4(dst, coef * acc[ch][i], coef * acc[ch][i + 1], coef * acc[ch][i + 2], coef * acc[ch][i + 3]);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (m + e < N) atomicAdd(dst + e, coef * acc[ch][i + e]);
+              for (int e = 0; e < 4; ++e)
+                if (m + e < N) atomicAdd(dst + e, coef * acc[ch][i + e]);
+            }
           }
         }
       }
     }
   }
+  fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
@@ -522,13 +538,13 @@ int try_launch_outer_tc(int N, int B, int width, const float* a, int64_t a_bs, c
   p.imgA = 128 * ATOM_ROW_BYTES;
   p.imgB = (uint32_t)round_up((size_t)p.Npad * ATOM_ROW_BYTES, 1024);
   const uint32_t bufsz = 2 * p.imgA + 2 * p.imgB;
-  p.off_bar = 2 * bufsz;
-  p.smem_bytes = p.off_bar + 32;
+  p.off_bar = TO_STAGES * bufsz;
+  p.smem_bytes = p.off_bar + 8 * (2 * TO_STAGES + 1) + 16;
   STC_TRY(set_smem(tc_outer_kernel, p.smem_bytes));
   int grid = device_sm_count();
   if (grid > B) grid = B;
   ScopedKernelTimer _t(KK_TC_OUTER, st, 4.0 * B * N * width * 2 + 4.0 * N * N);
-  tc_outer_kernel<<<grid, CV_THREADS, p.smem_bytes, st>>>(a, a_bs, bmat, coef, dG, p);
+  tc_outer_kernel<<<grid, TO_THREADS, p.smem_bytes, st>>>(a, a_bs, bmat, coef, dG, p);
   STC_LAUNCH_OK("tc_outer_kernel");
   *handled = true;
   return STC_OK;

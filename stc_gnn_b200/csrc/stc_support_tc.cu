@@ -101,6 +101,11 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
     const uint32_t tG = tmem_base + TS_ACC_COLS;
     if (elect_one_sync()) {
       const uint32_t idesc = make_idesc_tf32_atmem_bmn(128, TS_NT);
+      // the hi and lo images of an X stage are adjacent with one column-block pitch, and so are the main and the
+      // cross-term accumulator: G_hi x [X_hi | X_lo] is ONE N = 2 TS_NT MMA.  The kernel is bound by MMA issue (13
+      // K-steps x 3 MMAs of N = 64 ~ 3.5 K cycles per tile against 2.3 K cycles of HBM time at the SM's fair share),
+      // so 2 MMAs per K-step instead of 3 is a direct gain.
+      const uint32_t idesc2 = make_idesc_tf32_atmem_bmn(128, 2 * TS_NT);
       int it = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
         const int st = it % p.stages, ab = it & 1;
@@ -109,15 +114,13 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
         fence_after_sync();
         const uint32_t xhi = smem_u32(Xbuf + (size_t)st * 2 * p.imgX);
         const uint64_t xh0 = make_smem_desc_mn32(xhi, colblk, MN32_GROUP_BYTES);
-        const uint64_t xl0 = make_smem_desc_mn32(xhi + p.imgX, colblk, MN32_GROUP_BYTES);
         const uint32_t d_main = tmem_base + (uint32_t)(ab * 2 * TS_NT), d_small = d_main + TS_NT;
 #pragma unroll 1
         for (int ks = 0; ks < Kp / 8; ++ks) {
           const uint64_t o = (uint64_t)(ks * ((2 * MN32_GROUP_BYTES) >> 4));   // K = 8 rows further down
           const uint32_t gh = tG + (uint32_t)(ks * 8), gl = gh + (uint32_t)Kp;
-          mma_tf32_atmem(d_small, gl, xh0 + o, idesc, ks > 0 ? 1u : 0u);
-          mma_tf32_atmem(d_small, gh, xl0 + o, idesc, 1u);
-          mma_tf32_atmem(d_main, gh, xh0 + o, idesc, ks > 0 ? 1u : 0u);
+          mma_tf32_atmem(d_main, gh, xh0 + o, idesc2, ks > 0 ? 1u : 0u);   // [main | cross] (+)= G_hi x [X_hi | X_lo]
+          mma_tf32_atmem(d_small, gl, xh0 + o, idesc, 1u);                  // cross += G_lo x X_hi
         }
         mma_commit(&empty[st]);       // X stage may be refilled once these MMAs have read it
         mma_commit(&accfull[ab]);     // ... and the accumulators are complete
@@ -322,6 +325,7 @@ constexpr int TO_THREADS = CV_THREADS + 32;   // 8 producer / drain warps + 1 MM
 struct TcOuterPlan {
   int N, Npad, W, B, atoms_per_sample;
   int tmem_cols;
+  int drain, unstacked;   // atoms per chain set; diagnostic: 3 MMAs of N = Npad per K-step instead of 2 (N = 2 Npad, Npad)
   uint32_t imgA, imgB, off_bar, smem_bytes;
 };
 
@@ -389,14 +393,21 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
           const uint32_t o = ks * 32;
           const uint64_t ah = make_smem_desc_sw128(a_hi + o), al = make_smem_desc_sw128(a_lo + o);
           const uint64_t bh = make_smem_desc_sw128(b_hi + o);
-          mma_tf32(d_main, ah, bh, idesc2, (fresh && ks == 0) ? 0u : 1u);   // [main | cross] (+)= A_hi x [B_hi ; B_lo]
-          mma_tf32(d_cross, al, bh, idesc1, 1u);                            // cross += A_lo x B_hi
+          const uint32_t accf = (fresh && ks == 0) ? 0u : 1u;
+          if (p.unstacked) {
+            mma_tf32(d_cross, al, bh, idesc1, accf);
+            mma_tf32(d_cross, ah, make_smem_desc_sw128(b_hi + p.imgB + o), idesc1, 1u);
+            mma_tf32(d_main, ah, bh, idesc1, accf);
+          } else {
+            mma_tf32(d_main, ah, bh, idesc2, accf);          // [main | cross] (+)= A_hi x [B_hi ; B_lo]
+            mma_tf32(d_cross, al, bh, idesc1, 1u);           // cross += A_lo x B_hi
+          }
         }
         mma_commit(&empty[buf]);
       }
       __syncwarp();
       if (++at == p.atoms_per_sample) at = 0;
-      if (++in_set == TO_DRAIN) in_set = 0;
+      if (++in_set == p.drain) in_set = 0;
     }
   } else {
     // =============================== producers / drain / epilogue ===============================
@@ -485,7 +496,7 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[buf]);
-      if (++in_set == TO_DRAIN || seq == natoms - 1) drain(seq);
+      if (++in_set == p.drain || seq == natoms - 1) drain(seq);
     };
     if (natoms > 0) fetch(pf_s, pf_at, ra0, rb0);
     advance_pf();
@@ -533,6 +544,17 @@ int try_launch_outer_tc(int N, int B, int width, const float* a, int64_t a_bs, c
   p.W = width;
   p.B = B;
   p.atoms_per_sample = (width + ATOM_K - 1) / ATOM_K;
+  {
+    static int v_drain = -1, v_unst = 0;
+    if (v_drain < 0) {
+      const char* e = getenv("STC_OUTER_DRAIN");
+      v_drain = (e && atoi(e) > 1) ? atoi(e) : TO_DRAIN;
+      const char* u = getenv("STC_OUTER_UNSTACKED");
+      v_unst = (u && u[0] == '1') ? 1 : 0;
+    }
+    p.drain = v_drain;
+    p.unstacked = v_unst;
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < 4 * p.Npad) p.tmem_cols *= 2;
   p.imgA = 128 * ATOM_ROW_BYTES;

@@ -319,22 +319,31 @@ int try_launch_support_tc(const float* G, int N, int B, int width, bool transpos
 //      profiles/r1_tc_precision.txt); one atomicAdd per element per CTA at the end.
 // ------------------------------------------------------------------------------------------------
 constexpr int TO_DRAIN = 32;          // atoms per accumulation chain set (two slots: 16 atoms = 64 K-steps per accumulator)
-constexpr int TO_STAGES = 3;          // shared-memory operand ring
+constexpr int TO_SH = 5;              // ring of raw -> hi operand images (cp.async landing zones)
+constexpr int TO_SL = 2;              // ring of lo images
 constexpr int TO_THREADS = CV_THREADS + 32;   // 8 producer / drain warps + 1 MMA-issue warp
 
 struct TcOuterPlan {
   int N, Npad, W, B, atoms_per_sample;
   int tmem_cols;
-  int drain, unstacked;   // atoms per chain set; diagnostic: 3 MMAs of N = Npad per K-step instead of 2 (N = 2 Npad, Npad)
-  uint32_t imgA, imgB, off_bar, smem_bytes;
+  int drain;      // atoms per chain set
+  uint32_t imgA, imgB, off_lo, off_bar, smem_bytes;
 };
 
-// Warp-specialised since round 2: with the MMA issue inside the producers' barrier-coupled loop one atom cost
-// stage + block barrier + 12 MMA issues (~3.2 K cycles, 0.33 of HBM).  Now warp 8 only issues MMAs, fed through a
-// 3-stage ring with full / empty mbarriers, and the hi/lo images of the B operand are adjacent so that
-// A_hi x [B_hi ; B_lo] is ONE N = 2 Npad MMA filling the main and the cross-term accumulator of a slot together:
-// 2 MMAs per K-step instead of 3.  TMEM: two slots of [main | cross] (4 Npad columns), used round-robin and drained
-// into fp32 registers every TO_DRAIN atoms (bounded chains: the tensor core truncates on accumulate).
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Round-2 structure (profiles/r3l_outer_support_ncu.txt): with 16-byte loads into registers two atoms ahead the
+// compiler's register reuse serialised every fetch behind the previous one (long-scoreboard stalls on address
+// arithmetic, 0.27-0.35 of HBM whatever the MMA count).  Now the operand chunks travel global -> shared with cp.async
+// (no registers held, TO_SH - 2 = 3 atoms = 77 KB in flight per SM); every producer thread converts the chunks IT
+// requested in place (raw -> hi in the landing zone, lo into a second, shorter ring), so no block-wide barrier is needed
+// between the copy and the conversion; warp 8 only issues MMAs, paced by full / done mbarriers.  TMEM: two slots of
+// [main | cross] used round-robin, drained into fp32 registers every `drain` atoms (bounded chains).
 __global__ void __launch_bounds__(TO_THREADS, 1)
 tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __restrict__ Bm, float coef, float* dG,
                 const TcOuterPlan p) {
@@ -342,21 +351,23 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, W = p.W;
-  const uint32_t bufsz = 2 * p.imgA + 2 * p.imgB;    // [A hi | A lo | B hi | B lo]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [TO_STAGES] producers -> MMA warp
-  uint64_t* empty = full + TO_STAGES;                                // [TO_STAGES] MMA commit -> producers
-  uint64_t* drained = empty + TO_STAGES;                             // producers have read the accumulators
+  const uint32_t hsz = p.imgA + p.imgB;              // one stage of either ring: [A image | B image]
+  uint8_t* Hring = smem;                             // [TO_SH][A raw->hi | B raw->hi]
+  uint8_t* Lring = smem + p.off_lo;                  // [TO_SL][A lo | B lo]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [TO_SH] producers -> MMA warp
+  uint64_t* done = full + TO_SH;                                     // [TO_SH] MMA commit -> producers
+  uint64_t* drained = done + TO_SH;                                  // producers have read the accumulators
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
   if (tid == 0) {
-    for (int i = 0; i < TO_STAGES; ++i) {
+    for (int i = 0; i < TO_SH; ++i) {
       mbar_init(&full[i], CV_THREADS / 32);
-      mbar_init(&empty[i], 1);
+      mbar_init(&done[i], 1);
     }
     mbar_init(drained, CV_THREADS / 32);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  for (uint32_t i = tid * 16u; i < TO_STAGES * bufsz; i += TO_THREADS * 16u)   // rows >= N stay zero for good
+  for (uint32_t i = tid * 16u; i < (TO_SH + TO_SL) * hsz; i += TO_THREADS * 16u)   // rows >= N stay zero for good
     *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_async_smem();
   fence_before_sync();
@@ -369,13 +380,12 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
 
   if (warp_u == CV_THREADS / 32) {
     // =============================== MMA issuer ===============================
-    const uint32_t idesc2 = make_idesc_tf32(128, 2 * p.Npad), idesc1 = make_idesc_tf32(128, p.Npad);
+    const uint32_t idesc = make_idesc_tf32(128, p.Npad);
     int at = 0, in_set = 0;
     uint32_t drain_parity = 0;
     for (long long seq = 0; seq < natoms; ++seq) {
-      const int buf = (int)(seq % TO_STAGES);
-      const uint32_t use = (uint32_t)(seq / TO_STAGES);
-      mbar_wait(&full[buf], use & 1u);
+      const int hb = (int)(seq % TO_SH), lb = (int)(seq % TO_SL);
+      mbar_wait(&full[hb], (uint32_t)(seq / TO_SH) & 1u);
       if (seq > 0 && in_set == 0) {   // first atom of a new chain set: the producers must have drained the accumulators
         mbar_wait(drained, drain_parity);
         drain_parity ^= 1u;
@@ -386,24 +396,19 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
       const bool fresh = in_set < 2;  // first atom into this slot since the drain
       if (elect_one_sync()) {
         fence_after_sync();
-        const uint32_t base = smem_u32(smem + (size_t)buf * bufsz);
-        const uint32_t a_hi = base, a_lo = base + p.imgA, b_hi = base + 2 * p.imgA;   // b_lo follows b_hi directly
+        const uint32_t a_hi = smem_u32(Hring + (size_t)hb * hsz), b_hi = a_hi + p.imgA;
+        const uint32_t a_lo = smem_u32(Lring + (size_t)lb * hsz), b_lo = a_lo + p.imgA;
         const uint32_t d_main = tmem_base + (uint32_t)(slot * 2 * p.Npad), d_cross = d_main + (uint32_t)p.Npad;
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint32_t o = ks * 32;
           const uint64_t ah = make_smem_desc_sw128(a_hi + o), al = make_smem_desc_sw128(a_lo + o);
-          const uint64_t bh = make_smem_desc_sw128(b_hi + o);
+          const uint64_t bh = make_smem_desc_sw128(b_hi + o), bl = make_smem_desc_sw128(b_lo + o);
           const uint32_t accf = (fresh && ks == 0) ? 0u : 1u;
-          if (p.unstacked) {
-            mma_tf32(d_cross, al, bh, idesc1, accf);
-            mma_tf32(d_cross, ah, make_smem_desc_sw128(b_hi + p.imgB + o), idesc1, 1u);
-            mma_tf32(d_main, ah, bh, idesc1, accf);
-          } else {
-            mma_tf32(d_main, ah, bh, idesc2, accf);          // [main | cross] (+)= A_hi x [B_hi ; B_lo]
-            mma_tf32(d_cross, al, bh, idesc1, 1u);           // cross += A_lo x B_hi
-          }
+          mma_tf32(d_cross, al, bh, idesc, accf);
+          mma_tf32(d_cross, ah, bl, idesc, 1u);
+          mma_tf32(d_main, ah, bh, idesc, accf);
         }
-        mma_commit(&empty[buf]);
+        mma_commit(&done[hb]);
       }
       __syncwarp();
       if (++at == p.atoms_per_sample) at = 0;
@@ -411,37 +416,35 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
     }
   } else {
     // =============================== producers / drain / epilogue ===============================
-    // staging map: chunk q of rows r0 + 32 i of either operand
+    // copy / conversion map: chunk q of rows r0 + 32 i of either operand -- a thread converts exactly what it copied
     const int q = tid & 7, r0 = tid >> 3;
     uint32_t soff[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) soff[i] = atom_chunk_offset(r0 + 32 * i, q);
-    // two register sets: the operands of atom seq + 2 are requested right after atom seq has been staged, so two atoms
-    // are always in flight from HBM on top of the staged ring
-    float4 ra0[4], rb0[4], ra1[4], rb1[4];
-    auto fetch = [&](int s_, int at_, float4 (&ra)[4], float4 (&rb)[4]) {   // s_-th sample of this CTA, atom at_ of it
-      const long long b = blockIdx.x + s_ * (long long)gridDim.x;
-      const int j = at_ * ATOM_K + q * 4;
-      const bool ok = j < W;               // W % 4 == 0
-      const float* pa = A + b * a_bs + j;
-      const float* pb = Bm + b * (long long)N * W + j;
+    int cs = 0, cat = 0;                  // (sample, atom) of the next copy to issue
+    auto issue_copy = [&](long long seq) {   // atom seq -> H ring (nothing for seq >= natoms: the group is still committed)
+      if (seq < natoms) {
+        const long long b = blockIdx.x + cs * (long long)gridDim.x;
+        const int j = cat * ATOM_K + q * 4;
+        if (j < W) {                       // W % 4 == 0; chunks past W are never read (the MMAs stop at ceil(kleft / 8))
+          const float* pa = A + b * a_bs + j;
+          const float* pb = Bm + b * (long long)N * W + j;
+          const uint32_t base = smem_u32(Hring + (size_t)(seq % TO_SH) * hsz);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = r0 + 32 * i;
-        const bool live = ok && r < N;
-        ra[i] = live ? __ldg(reinterpret_cast<const float4*>(pa + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        rb[i] = live ? __ldg(reinterpret_cast<const float4*>(pb + (long long)r * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto stage = [&](int buf, const float4 (&ra)[4], const float4 (&rb)[4]) {
-      uint8_t* base = smem + (size_t)buf * bufsz;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (r0 + 32 * i < N) {
-          store_split4(base, base + p.imgA, soff[i], ra[i]);
-          store_split4(base + 2 * p.imgA, base + 2 * p.imgA + p.imgB, soff[i], rb[i]);
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + 32 * i;
+            if (r < N) {
+              cp_async16(base + soff[i], pa + (long long)r * W);
+              cp_async16(base + p.imgA + soff[i], pb + (long long)r * W);
+            }
+          }
+        }
+        if (++cat == p.atoms_per_sample) {
+          cat = 0;
+          ++cs;
         }
       }
+      cp_async_commit();
     };
     // accumulators: thread (sub-partition sp, half) owns row 32 sp + lane and Npad/2 columns
     const int sp = warp & 3, half = warp >> 2;
@@ -456,8 +459,7 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
 
     int in_set = 0;
     auto drain = [&](long long last_seq) {   // every atom up to last_seq has been handed to the MMA warp
-      const int lb = (int)(last_seq % TO_STAGES);
-      mbar_wait(&empty[lb], (uint32_t)(last_seq / TO_STAGES) & 1u);   // commits complete in order: this one covers all
+      mbar_wait(&done[last_seq % TO_SH], (uint32_t)(last_seq / TO_SH) & 1u);   // commits complete in order
       fence_after_sync();
       const int slots = in_set >= 2 ? 2 : in_set;
 #pragma unroll
@@ -479,33 +481,37 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
       in_set = 0;
     };
 
-    int pf_s = 0, pf_at = 0;              // (sample, atom) the next fetch targets: runs two atoms ahead, no divisions
-    auto advance_pf = [&]() {
-      if (++pf_at == p.atoms_per_sample) {
-        pf_at = 0;
-        ++pf_s;
+    for (int k = 0; k < TO_SH - 2; ++k) issue_copy(k);      // the ring starts empty: no waits
+    int at = 0;
+    for (long long seq = 0; seq < natoms; ++seq) {
+      // (a) Once the MMAs of atom seq - 2 are complete, its H stage can take the copy of atom seq + TO_SH - 2 and its L
+      //     stage (TO_SL = 2: the same index parity as seq) the lo image of atom seq.  Waiting for seq - 2 rather than
+      //     seq - 1 lets this conversion run beside the MMAs of atom seq - 1; TO_SH - 2 = 3 atoms (77 KB) stay in flight.
+      if (seq >= 2) mbar_wait(&done[(seq - 2) % TO_SH], (uint32_t)((seq - 2) / TO_SH) & 1u);
+      issue_copy(seq + TO_SH - 2);
+      // (b) this thread's chunks of atom seq have landed
+      cp_async_wait<TO_SH - 2>();
+      const int j = at * ATOM_K + q * 4;
+      if (j < W) {
+        uint8_t* hb = Hring + (size_t)(seq % TO_SH) * hsz;
+        uint8_t* lbp = Lring + (size_t)(seq % TO_SL) * hsz;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (r0 + 32 * i < N) {
+            const float4 va = *reinterpret_cast<const float4*>(hb + soff[i]);
+            const float4 vb = *reinterpret_cast<const float4*>(hb + p.imgA + soff[i]);
+            store_split4(hb, lbp, soff[i], va);
+            store_split4(hb + p.imgA, lbp + p.imgA, soff[i], vb);
+          }
+        }
       }
-    };
-    auto step = [&](long long seq, float4 (&ra)[4], float4 (&rb)[4]) {
-      const int buf = (int)(seq % TO_STAGES);
-      const uint32_t use = (uint32_t)(seq / TO_STAGES);
-      if (use > 0) mbar_wait(&empty[buf], (use - 1u) & 1u);   // the MMAs of this buffer's previous fill have read it
-      stage(buf, ra, rb);
-      if (seq + 2 < natoms) fetch(pf_s, pf_at, ra, rb);
-      advance_pf();
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[buf]);
+      if (lane == 0) mbar_arrive(&full[seq % TO_SH]);
+      if (++at == p.atoms_per_sample) at = 0;
       if (++in_set == p.drain || seq == natoms - 1) drain(seq);
-    };
-    if (natoms > 0) fetch(pf_s, pf_at, ra0, rb0);
-    advance_pf();
-    if (natoms > 1) fetch(pf_s, pf_at, ra1, rb1);
-    advance_pf();
-    for (long long seq = 0; seq < natoms; seq += 2) {
-      step(seq, ra0, rb0);
-      if (seq + 1 < natoms) step(seq + 1, ra1, rb1);
     }
+    cp_async_wait<0>();
 
     if (nrow < N) {
       const bool v4 = (N & 3) == 0 && (col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(dG) & 15) == 0;
@@ -545,23 +551,22 @@ int try_launch_outer_tc(int N, int B, int width, const float* a, int64_t a_bs, c
   p.B = B;
   p.atoms_per_sample = (width + ATOM_K - 1) / ATOM_K;
   {
-    static int v_drain = -1, v_unst = 0;
+    static int v_drain = -1;
     if (v_drain < 0) {
       const char* e = getenv("STC_OUTER_DRAIN");
       v_drain = (e && atoi(e) > 1) ? atoi(e) : TO_DRAIN;
-      const char* u = getenv("STC_OUTER_UNSTACKED");
-      v_unst = (u && u[0] == '1') ? 1 : 0;
     }
     p.drain = v_drain;
-    p.unstacked = v_unst;
   }
   p.tmem_cols = 32;
   while (p.tmem_cols < 4 * p.Npad) p.tmem_cols *= 2;
   p.imgA = 128 * ATOM_ROW_BYTES;
   p.imgB = (uint32_t)round_up((size_t)p.Npad * ATOM_ROW_BYTES, 1024);
-  const uint32_t bufsz = 2 * p.imgA + 2 * p.imgB;
-  p.off_bar = TO_STAGES * bufsz;
-  p.smem_bytes = p.off_bar + 8 * (2 * TO_STAGES + 1) + 16;
+  const uint32_t hsz = p.imgA + p.imgB;
+  p.off_lo = TO_SH * hsz;
+  p.off_bar = (TO_SH + TO_SL) * hsz;
+  p.smem_bytes = p.off_bar + 8 * (2 * TO_SH + 1) + 16;
+  if (p.smem_bytes > 227 * 1024) return STC_OK;
   STC_TRY(set_smem(tc_outer_kernel, p.smem_bytes));
   int grid = device_sm_count();
   if (grid > B) grid = B;

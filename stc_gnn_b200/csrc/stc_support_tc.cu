@@ -19,19 +19,11 @@ namespace stc {
 
 using namespace tc;
 
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 constexpr int TS_NT = 64;                    // (b,j) columns per tile = GEMM N
 constexpr int TS_PROD_WARPS = 8, TS_EPI_WARPS = 4;
 constexpr int TS_THREADS = 32 * (1 + TS_PROD_WARPS + TS_EPI_WARPS);
 constexpr int TS_SLOTS = 8;                  // 16-byte chunks per producer thread per tile (Kp <= 128)
-constexpr int TS_MAX_STAGES = 6;             // ring of raw -> hi X images (cp.async landing zones), as many as fit
-constexpr int TS_LO_STAGES = 2;              // ring of lo images
+constexpr int TS_MAX_STAGES = 4;             // X ring depth (as many as fit)
 constexpr int TS_ACC_COLS = 4 * TS_NT;       // 2 accumulator buffers x (main + cross-term)
 constexpr int TS_OLD = TS_NT + 4;            // row stride (floats) of the output staging tile: conflict-free both ways
 
@@ -39,7 +31,7 @@ struct TcSupPlan {
   int N, Kp, W, transpose, stages;
   long long total_cols, ntiles;
   int tmem_cols;
-  uint32_t off_x, off_lo, off_o, off_bar, smem_bytes, imgX;
+  uint32_t off_x, off_o, off_bar, smem_bytes, imgX;
 };
 
 __global__ void __launch_bounds__(TS_THREADS, 1)
@@ -49,8 +41,7 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, Kp = p.Kp, W = p.W;
-  uint8_t* Xbuf = smem + p.off_x;               // [stages][2 column blocks][Kp][128 B]: cp.async landing zone, then the hi image
-  uint8_t* Lbuf = smem + p.off_lo;              // [TS_LO_STAGES] lo images
+  uint8_t* Xbuf = smem + p.off_x;               // [stages][hi | lo][2 column blocks][Kp][128 B]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bar);   // [stages] producers -> MMA
   uint64_t* empty = full + TS_MAX_STAGES;                           // [stages] MMA -> producers
   uint64_t* accfull = empty + TS_MAX_STAGES;                        // [2] MMA -> epilogue
@@ -71,8 +62,8 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
   }
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   // rows N..Kp-1 of the X images are never written by the producers: zero them once
-  for (uint32_t i = tid * 16u; i < (uint32_t)(p.stages + TS_LO_STAGES) * p.imgX; i += TS_THREADS * 16u)
-    *reinterpret_cast<float4*>(Xbuf + i) = make_float4(0.f, 0.f, 0.f, 0.f);   // Lbuf follows Xbuf directly
+  for (uint32_t i = tid * 16u; i < 2u * (uint32_t)p.stages * p.imgX; i += TS_THREADS * 16u)
+    *reinterpret_cast<float4*>(Xbuf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -110,22 +101,26 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
     const uint32_t tG = tmem_base + TS_ACC_COLS;
     if (elect_one_sync()) {
       const uint32_t idesc = make_idesc_tf32_atmem_bmn(128, TS_NT);
+      // the hi and lo images of an X stage are adjacent with one column-block pitch, and so are the main and the
+      // cross-term accumulator: G_hi x [X_hi | X_lo] is ONE N = 2 TS_NT MMA.  The kernel is bound by MMA issue (13
+      // K-steps x 3 MMAs of N = 64 ~ 3.5 K cycles per tile against 2.3 K cycles of HBM time at the SM's fair share),
+      // so 2 MMAs per K-step instead of 3 is a direct gain.
+      const uint32_t idesc2 = make_idesc_tf32_atmem_bmn(128, 2 * TS_NT);
       int it = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
         const int st = it % p.stages, ab = it & 1;
         mbar_wait(&accempty[ab], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator pair
         mbar_wait(&full[st], (uint32_t)(it / p.stages) & 1u);        // the producers staged this X tile
         fence_after_sync();
-        const uint64_t xh0 = make_smem_desc_mn32(smem_u32(Xbuf + (size_t)st * p.imgX), colblk, MN32_GROUP_BYTES);
-        const uint64_t xl0 = make_smem_desc_mn32(smem_u32(Lbuf + (size_t)(it % TS_LO_STAGES) * p.imgX), colblk, MN32_GROUP_BYTES);
+        const uint32_t xhi = smem_u32(Xbuf + (size_t)st * 2 * p.imgX);
+        const uint64_t xh0 = make_smem_desc_mn32(xhi, colblk, MN32_GROUP_BYTES);
         const uint32_t d_main = tmem_base + (uint32_t)(ab * 2 * TS_NT), d_small = d_main + TS_NT;
 #pragma unroll 1
         for (int ks = 0; ks < Kp / 8; ++ks) {
           const uint64_t o = (uint64_t)(ks * ((2 * MN32_GROUP_BYTES) >> 4));   // K = 8 rows further down
           const uint32_t gh = tG + (uint32_t)(ks * 8), gl = gh + (uint32_t)Kp;
-          mma_tf32_atmem(d_small, gl, xh0 + o, idesc, ks > 0 ? 1u : 0u);
-          mma_tf32_atmem(d_small, gh, xl0 + o, idesc, 1u);
-          mma_tf32_atmem(d_main, gh, xh0 + o, idesc, ks > 0 ? 1u : 0u);
+          mma_tf32_atmem(d_main, gh, xh0 + o, idesc2, ks > 0 ? 1u : 0u);   // [main | cross] (+)= G_hi x [X_hi | X_lo]
+          mma_tf32_atmem(d_small, gl, xh0 + o, idesc, 1u);                  // cross += G_lo x X_hi
         }
         mma_commit(&empty[st]);       // X stage may be refilled once these MMAs have read it
         mma_commit(&accfull[ab]);     // ... and the accumulators are complete
@@ -136,51 +131,42 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
     const int pt = tid - 32;
     const int c0 = (pt & 15) << 2, r0 = pt >> 4;       // chunk column of the 64-wide tile, rows r0 + 16 i
     const uint32_t soff0 = (uint32_t)(c0 >> 5) * colblk + mn32_chunk_offset(r0, (c0 & 31) >> 2);
-    // Round 2: the X chunks travel global -> shared with cp.async (no registers held; with 16-byte loads into two
-    // register sets the fetch of tile i + 2 queued behind the loads of tile i + 1 -- long-scoreboard stalls on address
-    // arithmetic, profiles/r3l_outer_support_ncu.txt).  `stages - 2` tiles are in flight per SM; every producer thread
-    // converts the chunks IT requested in place (raw -> hi in the landing zone, lo into a 2-deep ring).
-    auto issue_copy = [&](int it, long long tile) {   // tile -> landing zone it % stages (a group is committed either way)
+    float4 ra[2][TS_SLOTS];
+    auto fetch = [&](long long tile, float4 (&r)[TS_SLOTS]) {
       const long long cg = tile * TS_NT + c0;
-      if (tile < p.ntiles && cg < p.total_cols) {      // W % 4 == 0: a chunk never straddles samples
-        const long long b = cg / W;
-        const float* src = X + b * x_bs + (cg - b * W);
-        const uint32_t base = smem_u32(Xbuf + (size_t)(it % p.stages) * p.imgX) + soff0;
+      const bool ok = tile < p.ntiles && cg < p.total_cols;     // W % 4 == 0: a chunk never straddles samples
+      const long long b = ok ? cg / W : 0;
+      const float* src = X + b * x_bs + (cg - b * W);
 #pragma unroll
-        for (int i = 0; i < TS_SLOTS; ++i) {
-          const int n = r0 + 16 * i;
-          if (n < N) cp_async16(base + (uint32_t)(16 * i) * ATOM_ROW_BYTES, src + (long long)n * W);
-        }
+      for (int i = 0; i < TS_SLOTS; ++i) {
+        const int n = r0 + 16 * i;
+        r[i] = (ok && n < N) ? __ldg(reinterpret_cast<const float4*>(src + (long long)n * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      cp_async_commit();
     };
-    const int ahead = p.stages - 2;                   // tiles in flight
-    {
-      long long t = blockIdx.x;
-      for (int k = 0; k < ahead; ++k, t += stride) issue_copy(k, t);
-    }
-    long long tile = blockIdx.x;
-    for (int it = 0; tile < p.ntiles; ++it, tile += stride) {
-      // the MMAs of tile it - 2 are complete: its landing zone can take tile it + ahead, its lo image (same parity) tile it
-      if (it >= 2) mbar_wait(&empty[(it - 2) % p.stages], (uint32_t)((it - 2) / p.stages) & 1u);
-      issue_copy(it + ahead, tile + (long long)ahead * stride);
-      if (ahead == 4) cp_async_wait<4>(); else if (ahead == 3) cp_async_wait<3>(); else if (ahead == 2) cp_async_wait<2>();
-      else if (ahead == 1) cp_async_wait<1>(); else cp_async_wait<0>();
-      uint8_t* hi = Xbuf + (size_t)(it % p.stages) * p.imgX;
-      uint8_t* lo = Lbuf + (size_t)(it % TS_LO_STAGES) * p.imgX;
-      const bool ok = tile * TS_NT + c0 < p.total_cols;   // past the last column: zeros (the epilogue does not store them)
+    auto stage = [&](int it, const float4 (&r)[TS_SLOTS]) {
+      const int st = it % p.stages;
+      mbar_wait(&empty[st], ((uint32_t)(it / p.stages) & 1u) ^ 1u);   // MMAs of the tile `stages` back have read it
+      uint8_t* hi = Xbuf + (size_t)st * 2 * p.imgX;
+      uint8_t* lo = hi + p.imgX;
 #pragma unroll
       for (int i = 0; i < TS_SLOTS; ++i)
-        if (r0 + 16 * i < N) {
-          const uint32_t off = soff0 + (uint32_t)(16 * i) * ATOM_ROW_BYTES;
-          const float4 v = ok ? *reinterpret_cast<const float4*>(hi + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-          store_split4(hi, lo, off, v);
-        }
+        if (r0 + 16 * i < N) store_split4(hi, lo, soff0 + (uint32_t)(16 * i) * ATOM_ROW_BYTES, r[i]);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[it % p.stages]);
+      if (lane == 0) mbar_arrive(&full[st]);
+    };
+    long long tile = blockIdx.x;
+    fetch(tile, ra[0]);
+    fetch(tile + stride, ra[1]);
+    for (int it = 0; tile < p.ntiles; it += 2) {
+      stage(it, ra[0]);
+      fetch(tile + 2 * stride, ra[0]);
+      tile += stride;
+      if (tile >= p.ntiles) break;
+      stage(it + 1, ra[1]);
+      fetch(tile + 2 * stride, ra[1]);
+      tile += stride;
     }
-    cp_async_wait<0>();
   } else {
     // =========================== epilogue: TMEM -> staging tile -> coalesced rows ===========================
     // A thread can only read its own TMEM lane (= output node m), but writing Y one node-row per thread makes every
@@ -306,10 +292,9 @@ int try_launch_support_tc(const float* G, int N, int B, int width, bool transpos
   const size_t obytes = (size_t)128 * TS_OLD * sizeof(float);
   const size_t fixed = 8 * (2 * TS_MAX_STAGES + 4) + 32 + obytes;
   p.stages = TS_MAX_STAGES;
-  while (p.stages > 3 && (size_t)(p.stages + TS_LO_STAGES) * p.imgX + fixed > 227 * 1024) --p.stages;
+  while (p.stages > 2 && 2 * (size_t)p.stages * p.imgX + fixed > 227 * 1024) --p.stages;
   size_t o = 0;
-  p.off_x = (uint32_t)o; o += (size_t)p.stages * p.imgX;
-  p.off_lo = (uint32_t)o; o += (size_t)TS_LO_STAGES * p.imgX;
+  p.off_x = (uint32_t)o; o += 2 * (size_t)p.stages * p.imgX;
   o = round_up(o, 16);
   p.off_o = (uint32_t)o; o += obytes;
   p.off_bar = (uint32_t)o; o += 8 * (2 * TS_MAX_STAGES + 4) + 16;
@@ -344,6 +329,13 @@ struct TcOuterPlan {
   int drain;      // atoms per chain set
   uint32_t imgA, imgB, off_lo, off_bar, smem_bytes;
 };
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Round-2 structure (profiles/r3l_outer_support_ncu.txt): with 16-byte loads into registers two atoms ahead the
 // compiler's register reuse serialised every fetch behind the previous one (long-scoreboard stalls on address

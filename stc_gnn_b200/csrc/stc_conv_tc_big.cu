@@ -569,9 +569,45 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
       }
     }
     // ---- 3. per spatial term: streamed-weight GEMM + epilogue ----
+    // my 8 columns of [Ds | Dm_1] for chunk kc: K range [32 kc + 8 qtr, +8).  Terms k > 0 reload Dm_1 from dpre (this
+    // thread left it there during term 0): that global load is issued ONE CHUNK AHEAD (`nx`), so its latency travels
+    // under the current chunk's split / TMEM store / barrier instead of being exposed 3 x nkc times per tile
+    // (profiles/r3o_config3_wide_ncu.txt: 13 % of the kernel's stall samples sat on the first use of that load).
+    auto reload_ok = [&](int k_, int kc_) {
+      return k_ > 0 && kc_ < p.nkc && (32 * kc_ + 8 * qtr) >= Hout && valid && a.dpre_ld >= 2 * Hout;
+    };
+    float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
     for (int k = 0; k < a.Ks; ++k) {
+      // prior contents the epilogue of this term adds to (direct dH terms / the other convolution's x-part adjoint):
+      // requested here, consumed after nkc chunks of work
+      float4 prev[4][2];
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        prev[gi][0] = prev[gi][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c0 = 8 * qtr + 32 * gi;
+        if (c0 < Nb && valid) {
+          if (c0 < h) {
+            if (k == 0 && a.phase == 0) {
+              const float4* src = reinterpret_cast<const float4*>(a.dYh0 + gr * h + c0);
+              prev[gi][0] = src[0];
+              prev[gi][1] = src[1];
+            }
+          } else {
+            const int xi = c0 - h;
+            if (xi < Din && xvec && a.accum_x) {
+              const float* src = (k == 0 ? a.dYx0 : a.dYx + (size_t)(k - 1) * R * Din) + gr * Din + xi;
+              prev[gi][0] = *reinterpret_cast<const float4*>(src);
+              if (xi + 4 < Din) prev[gi][1] = *reinterpret_cast<const float4*>(src + 4);
+            }
+          }
+        }
+      }
+      if (reload_ok(k, 0)) {
+        const float4* dp = reinterpret_cast<const float4*>(a.dpre + gr * a.dpre_ld + 8 * qtr);
+        nx0 = dp[0];
+        nx1 = dp[1];
+      }
       for (int kc = 0; kc < p.nkc; ++kc, ++g) {
-        // my 8 columns of [Ds | Dm_1]: K range [32 kc + 8 qtr, +8)
         const int kk0 = 32 * kc + 8 * qtr;
         float av[8];
         if (kk0 < Hout) {
@@ -579,10 +615,8 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
           const float4 x1 = *reinterpret_cast<const float4*>(Dsm + erow * DP + kk0 + 4);
           av[0] = x0.x; av[1] = x0.y; av[2] = x0.z; av[3] = x0.w; av[4] = x1.x; av[5] = x1.y; av[6] = x1.z; av[7] = x1.w;
         } else if (k > 0 && valid && a.dpre_ld >= 2 * Hout) {
-          // Dm_1 does not depend on the spatial term: this thread left these 8 values in dpre during term 0
-          const float4* dp = reinterpret_cast<const float4*>(a.dpre + gr * a.dpre_ld + kk0);
-          const float4 x0 = dp[0], x1 = dp[1];
-          av[0] = x0.x; av[1] = x0.y; av[2] = x0.z; av[3] = x0.w; av[4] = x1.x; av[5] = x1.y; av[6] = x1.z; av[7] = x1.w;
+          // Dm_1 does not depend on the spatial term: requested one chunk ago
+          av[0] = nx0.x; av[1] = nx0.y; av[2] = nx0.z; av[3] = nx0.w; av[4] = nx1.x; av[5] = nx1.y; av[6] = nx1.z; av[7] = nx1.w;
         } else {
           const float* spm = Dsm + (enode * C) * DP + (kk0 - Hout);
 #pragma unroll
@@ -597,6 +631,11 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
               av[4] = fmaf(w, x1.x, av[4]); av[5] = fmaf(w, x1.y, av[5]); av[6] = fmaf(w, x1.z, av[6]); av[7] = fmaf(w, x1.w, av[7]);
             }
           }
+        }
+        if (reload_ok(k, kc + 1)) {   // next chunk's Dm_1 piece
+          const float4* dp = reinterpret_cast<const float4*>(a.dpre + gr * a.dpre_ld + kk0 + 32);
+          nx0 = dp[0];
+          nx1 = dp[1];
         }
         if (k == 0 && kk0 >= Hout && valid && a.dpre_ld >= 2 * Hout) {   // the wide dW kernel contracts Y_k^T with [Ds | Dm_1]
           float4* dp = reinterpret_cast<float4*>(a.dpre + gr * a.dpre_ld + kk0);
@@ -654,7 +693,10 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
       mbar_wait(acc_full, acc_phase);
       acc_phase ^= 1u;
       fence_after_sync();
-      for (int c0 = 8 * qtr; c0 < Nb; c0 += 32) {
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        const int c0 = 8 * qtr + 32 * gi;
+        if (c0 >= Nb) break;
         float v[8];
         {
           uint32_t t0[8], t1[8], t2[8];
@@ -667,32 +709,18 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
           for (int i = 0; i < 8; ++i) v[i] = (__uint_as_float(t2[i]) + __uint_as_float(t0[i])) + __uint_as_float(t1[i]);
         }
         if (!valid) continue;
+        const float4 p0 = prev[gi][0], p1 = prev[gi][1];   // zeros unless this group accumulates (requested before the chunks)
         if (c0 < h) {
           float* dst = (k == 0 ? a.dYh0 : a.dYh + (size_t)(k - 1) * R * h) + gr * h + c0;
-          float4 o0 = make_float4(v[0], v[1], v[2], v[3]), o1 = make_float4(v[4], v[5], v[6], v[7]);
-          if (k == 0 && a.phase == 0) {   // the prologue left the direct dH terms there
-            const float4 p0 = reinterpret_cast<const float4*>(dst)[0], p1 = reinterpret_cast<const float4*>(dst)[1];
-            o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
-            o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
-          }
-          reinterpret_cast<float4*>(dst)[0] = o0;
-          reinterpret_cast<float4*>(dst)[1] = o1;
+          reinterpret_cast<float4*>(dst)[0] = make_float4(v[0] + p0.x, v[1] + p0.y, v[2] + p0.z, v[3] + p0.w);
+          reinterpret_cast<float4*>(dst)[1] = make_float4(v[4] + p1.x, v[5] + p1.y, v[6] + p1.z, v[7] + p1.w);
         } else {
           const int xi = c0 - h;
           if (xi >= Din) continue;
           float* dst = (k == 0 ? a.dYx0 : a.dYx + (size_t)(k - 1) * R * Din) + gr * Din + xi;
           if (xvec) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              if (xi + 4 * i < Din) {
-                float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                if (a.accum_x) {
-                  const float4 pv = reinterpret_cast<const float4*>(dst)[i];
-                  o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
-                }
-                reinterpret_cast<float4*>(dst)[i] = o;
-              }
-            }
+            reinterpret_cast<float4*>(dst)[0] = make_float4(v[0] + p0.x, v[1] + p0.y, v[2] + p0.z, v[3] + p0.w);
+            if (xi + 4 < Din) reinterpret_cast<float4*>(dst)[1] = make_float4(v[4] + p1.x, v[5] + p1.y, v[6] + p1.z, v[7] + p1.w);
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i)

@@ -409,6 +409,22 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
       }
     }
     STC_TRACE(3);
+    // x-part adjoint this pass adds to (the other convolution's contribution): requested now, consumed in the epilogue --
+    // the read-modify-write latency travels under the MMAs and the dQ pass instead of sitting at the end of every tile
+    float4 xprev[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xprev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (FAST) {
+      if (a.accum_x && p.x_vec && erow < rows_valid) {
+        const float* dbase_pf = (half == 0 ? a.dYx0 : a.dYx);
+        if (dbase_pf != nullptr) {
+          const float* src = dbase_pf + (row0 + erow) * Din;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (4 * i < Din) xprev[i] = *reinterpret_cast<const float4*>(src + 4 * i);
+        }
+      }
+    }
     // ---- 4 (overlaps the MMAs). dQ_c[c'][d] += sum_{node,o} P_c[(node,c')][o] * Ds[(node,d)][o] ----
     if (want_dQ) {
       mbar_wait(load_bar, load_phase);
@@ -526,13 +542,9 @@ tc_conv_bwd_dx_kernel(const ConvArgs a, const TcDxPlan p) {
                                  __uint_as_float(sm[4 * i + 2]) + __uint_as_float(mn[4 * i + 2]),
                                  __uint_as_float(sm[4 * i + 3]) + __uint_as_float(mn[4 * i + 3]));
             if (a.accum_x) {
-              float4 pv[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                if (4 * i < Din) pv[i] = *reinterpret_cast<const float4*>(dst + 4 * i);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (4 * i < Din) { o[i].x += pv[i].x; o[i].y += pv[i].y; o[i].z += pv[i].z; o[i].w += pv[i].w; }
+                if (4 * i < Din) { o[i].x += xprev[i].x; o[i].y += xprev[i].y; o[i].z += xprev[i].z; o[i].w += xprev[i].w; }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)

@@ -48,9 +48,17 @@ def launches(src, dst):
     print(open(dst).read())
 
 
-def full(src, dst):
+def _raw_rows(src):
+    """rows of `ncu --page raw --csv`: from a report, or from a csv the GPU session already exported (large reports
+    are not brought back)."""
+    if src.endswith(".csv"):
+        return list(csv.reader(open(src)))
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
+    return list(csv.reader(io.StringIO(out)))
+
+
+def full(src, dst):
+    rows = _raw_rows(src)
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     with open(dst, "w") as f:
@@ -66,8 +74,7 @@ def full(src, dst):
 def traffic(src, dst, batch="4096"):
     """profiles/traffic.json: mean dram bytes (read + write) per launch of each captured kernel kind."""
     import json
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
+    rows = _raw_rows(src)
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

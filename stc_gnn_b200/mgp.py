@@ -34,17 +34,21 @@ def _active(group) -> bool:
 
 class _SumForward(torch.autograd.Function):
     """y = sum over ranks of x; the incoming gradient is already the global dL/dy on every rank (see `_ReduceGrad`),
-    and dy/dx_rank = I, so backward is the identity."""
+    and dy/dx_rank = I, so backward is the identity -- times `grad_scale`: what flows on from here are the shard-
+    dependent generator parameters (`params_S/C`), whose full gradient is the SUM of the per-rank pieces; when the
+    job averages its gradient bucket (per-rank losses are shard means), the pieces are pre-multiplied by the world size
+    so that the average is that sum."""
 
     @staticmethod
-    def forward(ctx, x, group):
+    def forward(ctx, x, group, grad_scale):
+        ctx.grad_scale = grad_scale
         y = x.detach().clone()
         dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        return dy, None
+        return (dy * ctx.grad_scale if ctx.grad_scale != 1.0 else dy), None, None
 
 
 class _ReduceGrad(torch.autograd.Function):
@@ -64,8 +68,10 @@ class _ReduceGrad(torch.autograd.Function):
         return g, None, None
 
 
-def sum_forward(x, group=None):
-    return _SumForward.apply(x, group) if _active(group) else x
+def sum_forward(x, group=None, average=False):
+    if not _active(group):
+        return x
+    return _SumForward.apply(x, group, float(dist.get_world_size(group)) if average else 1.0)
 
 
 def reduce_grad(x, group=None, average=False):
@@ -86,11 +92,13 @@ def pair_scores(X: torch.Tensor, Wu: torch.Tensor, Wv: torch.Tensor, alpha: floa
 def mgp_forward_dp(self, X_seq: torch.Tensor, As: torch.Tensor, Ac: torch.Tensor,
                    group: Optional[dist.ProcessGroup] = None, average: bool = False):
     """Drop-in body for `MGP_Gen.forward` with the batch-coupled sums made global over `group`.
-    `average`: the per-rank losses are means over equal shards and the job's loss is their mean."""
-    Ss = sum_forward(pair_scores(X_seq, self.params_S["Wu"], self.params_S["Wv"], self.alpha), group)
+    `average`: the per-rank losses are means over equal shards, the job's loss is their mean, and the gradient bucket of
+    `dp_bucket_parameters` is AVERAGED over the ranks (`GradBucket.allreduce(average=True)`); without it per-rank losses
+    add up and the bucket is summed."""
+    Ss = sum_forward(pair_scores(X_seq, self.params_S["Wu"], self.params_S["Wv"], self.alpha), group, average)
     Gs = self.aggreg_S(As, torch.softmax(torch.relu(Ss), dim=-1))
     Xc = X_seq.transpose(2, 3)
-    Sc = sum_forward(pair_scores(Xc, self.params_C["Wu"], self.params_C["Wv"], self.alpha), group)
+    Sc = sum_forward(pair_scores(Xc, self.params_C["Wu"], self.params_C["Wv"], self.alpha), group, average)
     Gc = self.aggreg_C(Ac, torch.softmax(torch.relu(Sc), dim=-1))
     return reduce_grad(Gs, group, average), reduce_grad(Gc, group, average)
 

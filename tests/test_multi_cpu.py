@@ -303,31 +303,38 @@ def _mgp_setup():
 
 def _mgp_dp_case(rank, world):
     """Sharded batch + patched generator: supports and EVERY generator gradient equal the single-process global-batch
-    ones; the fusion-layer gradients come out complete on every rank without being communicated."""
+    ones; the fusion-layer gradients come out complete on every rank without being communicated.  Both conventions:
+    per-rank losses add up (bucket summed) and per-rank losses are shard means whose mean is the job's loss (bucket
+    averaged)."""
     from stc_gnn_b200 import mgp
     ref, gen, X, As, Ac, wS, wC = _mgp_setup()
     loss = lambda Gs, Gc, a, b: (Gs * a.sum(0)).sum() + (Gc * b.sum(0)).sum()     # sum of per-sample losses
-    Gs_f, Gc_f = gen(X, As, Ac)                                                  # stock forward, whole batch
-    loss(Gs_f, Gc_f, wS, wC).backward()
-    full = {n: p.grad.clone() for n, p in gen.named_parameters()}
-    for p in gen.parameters():
-        p.grad = None
-    mgp.patch_generator(ref, group=None)
-    try:
-        sl = slice(*dp.shard_bounds(X.shape[0], rank, world))
-        Gs_r, Gc_r = gen(X[sl], As, Ac)
-        O.assert_close(Gs_r, Gs_f, f"Gs from a shard (rank {rank})", 1e-10, 1e-12)
-        O.assert_close(Gc_r, Gc_f, f"Gc from a shard (rank {rank})", 1e-10, 1e-12)
-        loss(Gs_r, Gc_r, wS[sl], wC[sl]).backward()
-    finally:
-        mgp.unpatch_generator(ref)
-    shard_params = mgp.dp_bucket_parameters(gen)
-    assert len(shard_params) == 4 and all(".aggreg_" not in n for n, p in gen.named_parameters()
-                                          if any(p is q for q in shard_params))
-    for p in shard_params:                                                        # the usual DP gradient sum
-        dist.all_reduce(p.grad)
-    for n, p in gen.named_parameters():
-        O.assert_close(p.grad, full[n], f"generator d{n} (rank {rank})", 1e-8, 1e-10)
+    for average in (False, True):
+        for p in gen.parameters():
+            p.grad = None
+        Gs_f, Gc_f = gen(X, As, Ac)                                              # stock forward, whole batch
+        (loss(Gs_f, Gc_f, wS, wC) / (world if average else 1)).backward()
+        full = {n: p.grad.clone() for n, p in gen.named_parameters()}
+        for p in gen.parameters():
+            p.grad = None
+        mgp.patch_generator(ref, group=None, average=average)
+        try:
+            sl = slice(*dp.shard_bounds(X.shape[0], rank, world))
+            Gs_r, Gc_r = gen(X[sl], As, Ac)
+            O.assert_close(Gs_r, Gs_f, f"Gs from a shard (rank {rank})", 1e-10, 1e-12)
+            O.assert_close(Gc_r, Gc_f, f"Gc from a shard (rank {rank})", 1e-10, 1e-12)
+            loss(Gs_r, Gc_r, wS[sl], wC[sl]).backward()
+        finally:
+            mgp.unpatch_generator(ref)
+        shard_params = mgp.dp_bucket_parameters(gen)
+        assert len(shard_params) == 4 and all(".aggreg_" not in n for n, p in gen.named_parameters()
+                                              if any(p is q for q in shard_params))
+        for p in shard_params:                                                    # the usual DP gradient sum / mean
+            dist.all_reduce(p.grad)
+            if average:
+                p.grad.div_(world)
+        for n, p in gen.named_parameters():
+            O.assert_close(p.grad, full[n], f"generator d{n} (rank {rank}, average={average})", 1e-8, 1e-10)
 
 
 def test_generator_restatement_matches_reference_single_process():

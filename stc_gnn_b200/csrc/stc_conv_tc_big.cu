@@ -552,7 +552,33 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
       db_acc += sacc;
     }
     // ---- 2. dT_1(Gc)[c'][d] += sum_{node,o} P_1[(node,c')][o] * Ds[(node,d)][o]  (P_1 saved by the forward kernel) ----
-    if (want_dQ) {
+    if (want_dQ && (C & 7) == 0) {
+      // Register-blocked form (C % 8 == 0; C = 64 of config 5: one (c', 8 d's) item per thread).  One 16-byte piece of
+      // P_1[(node,c')] serves eight pairs: 9 loads per 32 FMAs instead of 2 per 4, and the eight Ds rows d = dblk + 8 j a
+      // warp reads at a time are eight CONSECUTIVE rows (row pitch DP = Hout + 4 words: conflict-free 16-byte reads).
+      const int nblk = C >> 3;
+      for (int item = tid; item < C * nblk; item += BG_THREADS) {
+        const int cp = item / nblk, dblk = item - cp * nblk;
+        float sacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sacc[j] = 0.f;
+        for (int node = 0; node < nodes_valid; ++node) {
+          const float* pp = a.Psave + (row0 + node * C + cp) * (long long)Hout;
+          const float* dd = Dsm + (node * C + dblk) * DP;
+          for (int o = 0; o < Hout; o += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(pp + o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 y = *reinterpret_cast<const float4*>(dd + (size_t)(j * nblk) * DP + o);
+              sacc[j] = fmaf(x.x, y.x, sacc[j]); sacc[j] = fmaf(x.y, y.y, sacc[j]);
+              sacc[j] = fmaf(x.z, y.z, sacc[j]); sacc[j] = fmaf(x.w, y.w, sacc[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dQacc[cp * C + dblk + j * nblk] += sacc[j];   // each pair has exactly one owner thread
+      }
+    } else if (want_dQ) {
       for (int pr = tid; pr < C * C; pr += BG_THREADS) {
         const int cp = pr / C, d = pr - cp * C;
         float sacc = 0.f;

@@ -38,28 +38,6 @@ struct BigPlan {
   uint32_t off_b, off_pm, off_q, off_bias, off_bar, smem_bytes;
 };
 
-
-// one lane: pull the operand rows of tile `tile` towards L2 while the current tile is being worked on (the wide-state
-// kernels read their rows with per-thread 32-byte loads one chunk ahead: from L2 the first use waits ~1/3 as long as from
-// HBM).  Ranges: the node-major row slabs are contiguous per tile; Xt carries a batch stride, so it goes per sample.
-__device__ __forceinline__ void big_prefetch_rows(const float* base, long long row0, int rows, int width) {
-  if (base != nullptr && rows > 0) l2_prefetch(base + row0 * width, (uint32_t)(rows * width * 4) & ~15u);
-}
-__device__ __forceinline__ void big_prefetch_xt(const ConvArgs& a, long long g0, int nv) {
-  const int CD = a.C * a.Din;
-  if ((CD & 3) != 0 || (a.x0_bs & 3) != 0) return;
-  long long g = g0;
-  int left = nv;
-  while (left > 0) {
-    const long long b = g / a.N;
-    const int m = (int)(g - b * a.N);
-    const int seg = min(left, a.N - m);
-    l2_prefetch(a.x0 + b * a.x0_bs + (long long)m * CD, (uint32_t)(seg * CD * 4));
-    g += seg;
-    left -= seg;
-  }
-}
-
 // img[(cb, ch)][hi | lo][o][kb]  <-  W[((k*Kc + cb)*L + l(kb))*Hout + o],  k = ch / nchk, kb = 32 (ch % nchk) + ...
 __global__ void tc_big_prep_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int Din, int h, int Ks, int Kc,
                                    int Hout, int KBL, int nchk) {
@@ -153,20 +131,6 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
     const int rows_valid = nodes_valid * C;
     const bool valid = erow < rows_valid;
     const long long gr = g0 * C + erow;
-    if ((a.opt & OPT_L2_PREFETCH) && warp_u == 2 && tile + (int)gridDim.x < p.ntiles && elect_one_sync()) {
-      const long long n0 = (long long)(tile + gridDim.x) * p.npt;
-      const int nv = (int)min((long long)p.npt, total_nodes - n0);
-      const long long r0n = n0 * C;
-      const int rows = nv * C;
-      big_prefetch_rows(a.h0, r0n, rows, h);
-      for (int k = 1; k < a.Ks; ++k) big_prefetch_rows(a.yh + (size_t)(k - 1) * R * h, r0n, rows, h);
-      if ((Din & 3) == 0) {
-        for (int k = 1; k < a.Ks; ++k) big_prefetch_rows(a.yx + (size_t)(k - 1) * R * Din, r0n, rows, Din);
-        big_prefetch_xt(a, n0, nv);
-      }
-      if (a.Hprev != a.h0) big_prefetch_rows(a.Hprev, r0n, rows, h);
-      if (a.phase != 0) big_prefetch_rows(a.u, r0n, rows, h);
-    }
     // x-part source of my row for spatial term 0 (Xt carries a batch stride)
     const float* xs0 = a.x0;
     if (valid) {
@@ -532,20 +496,6 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
     const long long row0 = g0 * C;
     const bool valid = erow < rows_valid;
     const long long gr = row0 + erow;
-    if ((a.opt & OPT_L2_PREFETCH) && warp_u == 2 && tile + (int)gridDim.x < p.ntiles && elect_one_sync()) {
-      const long long n0 = (long long)(tile + gridDim.x) * p.npt;
-      const int rows = (int)min((long long)p.npt, total_nodes - n0) * C;
-      const long long r0n = n0 * C;
-      big_prefetch_rows(a.dHn, r0n, rows, h);
-      big_prefetch_rows(a.u, r0n, rows, h);
-      big_prefetch_rows(a.c, r0n, rows, h);
-      if (a.phase == 0) {
-        big_prefetch_rows(a.Hprev, r0n, rows, h);
-        big_prefetch_rows(a.r, r0n, rows, h);
-        big_prefetch_rows(a.drH, r0n, rows, h);
-      }
-      if (want_dQ) big_prefetch_rows(a.Psave, r0n, rows, Hout);
-    }
     // ---- 1. elementwise adjoint: one float4 of hidden channels per item ----
     const int cpr = h >> 2;
     for (int it = tid; it < 128 * cpr; it += BG_THREADS) {

@@ -25,6 +25,7 @@ using namespace tc;
 
 constexpr int BG_STAGES = 3;
 constexpr int BG_THREADS = 512;   // 16 warps: four threads per tile row (one per 8 K-values of a chunk / per quarter of the output columns)
+constexpr int BG_FWD_THREADS = BG_THREADS + 32;   // forward: + one warp that only issues MMAs and refills the weight ring
 constexpr int BG_ACOL = 384;   // first TMEM column of the A buffers: buffer b = [hi 32 | lo 32] at BG_ACOL + 64 b
 
 struct BigPlan {
@@ -63,7 +64,15 @@ __global__ void tc_big_prep_kernel(const float* __restrict__ W, uint8_t* __restr
   }
 }
 
-__global__ void __launch_bounds__(BG_THREADS, 1)
+// Round 2: the MMA issue moved out of the producers' loop.  Before, every chunk ended in a block barrier behind warp 0,
+// which both staged its rows AND issued the chunk's 12 MMAs (tensor-execution-paced, ~800 cycles): a chunk cost
+// staging + issue in series (ncu: 20 % barrier stalls, tensor pipe 13-21 %).  Now warp 16 only waits for "A staged"
+// (a_full, one arrive per producer warp) and "weights landed" (b_full), issues, commits, and refills the weight ring;
+// the 16 producer warps run ahead by the two TMEM A buffers and meet the issuer only through mbarriers (a_free,
+// acc_full, acc_empty).  Producer-only block syncs use named barrier 1.
+__device__ __forceinline__ void bg_producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BG_THREADS) : "memory"); }
+
+__global__ void __launch_bounds__(BG_FWD_THREADS, 1)
 tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restrict__ img) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -77,7 +86,9 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
   uint64_t* b_free = b_full + BG_STAGES;
   uint64_t* a_free = b_free + BG_STAGES;
   uint64_t* acc_full = a_free + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* a_full = acc_full + 1;                               // [2] producers -> issuer: A buffer staged in TMEM
+  uint64_t* acc_empty = a_full + 2;                              // producers -> issuer: the block's epilogue has read the accumulators
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   if (tid == 0) {
     for (int i = 0; i < BG_STAGES; ++i) {
@@ -87,12 +98,15 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
     mbar_init(&a_free[0], 1);
     mbar_init(&a_free[1], 1);
     mbar_init(acc_full, 1);
+    mbar_init(&a_full[0], BG_THREADS / 32);
+    mbar_init(&a_full[1], BG_THREADS / 32);
+    mbar_init(acc_empty, BG_THREADS / 32);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512u);
-  for (int i = tid; i < C * C; i += BG_THREADS) Qs[i] = a.Q[C * C + i];
-  for (int i = tid; i < Hout; i += BG_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
-  for (int i = tid; i < (128 + C) * p.PS; i += BG_THREADS) Pm[i] = 0.f;
+  for (int i = tid; i < C * C; i += BG_FWD_THREADS) Qs[i] = a.Q[C * C + i];
+  for (int i = tid; i < Hout; i += BG_FWD_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
+  for (int i = tid; i < (128 + C) * p.PS; i += BG_FWD_THREADS) Pm[i] = 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -116,13 +130,55 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
     const uint32_t cbi = w / (uint32_t)p.nch, ch = w - cbi * (uint32_t)p.nch;
     return img + (size_t)((1u - cbi) * (uint32_t)p.nch + ch) * p.stage_bytes;   // c = 1 first, then c = 0
   };
-  if (warp_u == 1 && elect_one_sync()) {               // ring prologue: the first BG_STAGES - 1 chunks
-    for (uint32_t g = 0; g < (uint32_t)(BG_STAGES - 1) && g < total_chunks; ++g) {
-      mbar_arrive_expect_tx(&b_full[g], p.stage_bytes);
-      bulk_g2s(Bring + (size_t)g * p.stage_bytes, img_of(g), p.stage_bytes, &b_full[g]);
+  if (warp_u == BG_THREADS / 32) {
+    // =============================== issuer: MMAs + weight ring ===============================
+    if (elect_one_sync()) {
+      for (uint32_t g = 0; g < (uint32_t)(BG_STAGES - 1) && g < total_chunks; ++g) {   // ring prologue
+        mbar_arrive_expect_tx(&b_full[g], p.stage_bytes);
+        bulk_g2s(Bring + (size_t)g * p.stage_bytes, img_of(g), p.stage_bytes, &b_full[g]);
+      }
+      uint32_t g = 0, blocks = 0;
+      for (int t_ = 0; t_ < my_tiles; ++t_) {
+        for (int cbi = 0; cbi < 2; ++cbi, ++blocks) {
+          for (int ch = 0; ch < p.nch; ++ch, ++g) {
+            const int buf = (int)(g & 1u), st = (int)(g % (uint32_t)BG_STAGES);
+            if (ch == 0 && blocks > 0) mbar_wait(acc_empty, (blocks - 1u) & 1u);   // previous block's epilogue is done
+            mbar_wait(&a_full[buf], (g >> 1) & 1u);
+            mbar_wait(&b_full[st], (g / (uint32_t)BG_STAGES) & 1u);
+            fence_after_sync();
+            const int j = ch % p.nchk;
+            const int kleft = p.KBL - 32 * j;
+            const int ksteps = kleft >= 32 ? 4 : (kleft + 7) / 8;
+            const uint32_t a_hi0 = tmem_base + (uint32_t)(BG_ACOL + 64 * buf);
+            const uint64_t dBh = make_smem_desc_sw128(smem_u32(Bring + (size_t)st * p.stage_bytes));
+            const uint64_t dBl = dBh + (uint64_t)(((uint32_t)Hout * ATOM_ROW_BYTES) >> 4);
+            // consecutive MMAs never touch the same accumulator twice in a row: the main product alternates between the
+            // two main accumulators per K-step and sits between the two cross-term products
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t ko = (uint64_t)(ks * 2);
+              const uint32_t ah = a_hi0 + (uint32_t)(ks * 8), al = ah + 32u;
+              const uint32_t d_main = tmem_base + (uint32_t)((ks & 1) * Hout);
+              mma_tf32_atmem(d_small, al, dBh + ko, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+              mma_tf32_atmem(d_main, ah, dBh + ko, idesc, (ch > 0 || ks >= 2) ? 1u : 0u);
+              mma_tf32_atmem(d_small, ah, dBl + ko, idesc, 1u);
+            }
+            mma_commit(&a_free[buf]);                     // A buffer and weight stage are free once these MMAs have read them
+            mma_commit(&b_free[st]);
+            if (ch == p.nch - 1) mma_commit(acc_full);    // ... and the block's accumulators are complete
+            const uint32_t t = g + (uint32_t)(BG_STAGES - 1);   // refill the ring BG_STAGES - 1 chunks ahead
+            if (t < total_chunks) {
+              const uint32_t ts = t % (uint32_t)BG_STAGES, tu = t / (uint32_t)BG_STAGES;
+              if (tu >= 1u) mbar_wait(&b_free[ts], (tu - 1u) & 1u);
+              mbar_arrive_expect_tx(&b_full[ts], p.stage_bytes);
+              bulk_g2s(Bring + (size_t)ts * p.stage_bytes, img_of(t), p.stage_bytes, &b_full[ts]);
+            }
+          }
+        }
+      }
     }
-  }
-
+    __syncwarp();
+  } else {
+  // =============================== producers + epilogue (16 warps) ===============================
   uint32_t g = 0;                                      // running chunk counter of this CTA
   uint32_t acc_phase = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -188,40 +244,8 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
         }
         tmem_st_wait();
         fence_before_sync();
-        __syncthreads();
-        const int st = (int)(g % (uint32_t)BG_STAGES);
-        if (warp_u == 0 && elect_one_sync()) {
-          mbar_wait(&b_full[st], (g / (uint32_t)BG_STAGES) & 1u);
-          fence_after_sync();
-          const int j = ch % p.nchk;
-          const int kleft = p.KBL - 32 * j;
-          const int ksteps = kleft >= 32 ? 4 : (kleft + 7) / 8;
-          const uint32_t a_hi0 = tmem_base + (uint32_t)(BG_ACOL + 64 * buf);
-          const uint64_t dBh = make_smem_desc_sw128(smem_u32(Bring + (size_t)st * p.stage_bytes));
-          const uint64_t dBl = dBh + (uint64_t)(((uint32_t)Hout * ATOM_ROW_BYTES) >> 4);
-          // consecutive MMAs never touch the same accumulator twice in a row: the main product alternates between the
-          // two main accumulators per K-step and sits between the two cross-term products
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t ko = (uint64_t)(ks * 2);
-            const uint32_t ah = a_hi0 + (uint32_t)(ks * 8), al = ah + 32u;
-            const uint32_t d_main = tmem_base + (uint32_t)((ks & 1) * Hout);
-            mma_tf32_atmem(d_small, al, dBh + ko, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
-            mma_tf32_atmem(d_main, ah, dBh + ko, idesc, (ch > 0 || ks >= 2) ? 1u : 0u);
-            mma_tf32_atmem(d_small, ah, dBl + ko, idesc, 1u);
-          }
-          mma_commit(&a_free[buf]);                     // A buffer and weight stage are free once these MMAs have read them
-          mma_commit(&b_free[st]);
-          if (ch == p.nch - 1) mma_commit(acc_full);    // ... and the block's accumulators are complete
-        }
-        if (warp_u == 1 && elect_one_sync()) {          // refill the ring BG_STAGES - 1 chunks ahead
-          const uint32_t t = g + (uint32_t)(BG_STAGES - 1);
-          if (t < total_chunks) {
-            const uint32_t ts = t % (uint32_t)BG_STAGES, tu = t / (uint32_t)BG_STAGES;
-            if (tu >= 1u) mbar_wait(&b_free[ts], (tu - 1u) & 1u);
-            mbar_arrive_expect_tx(&b_full[ts], p.stage_bytes);
-            bulk_g2s(Bring + (size_t)ts * p.stage_bytes, img_of(t), p.stage_bytes, &b_full[ts]);
-          }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[buf]);       // one arrive per producer warp: the issuer takes it from here
         cur[0] = nxt[0];
         cur[1] = nxt[1];
       }
@@ -307,9 +331,12 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
         }
       }
       fence_before_sync();   // accumulator reads precede the next block's overwriting MMAs; P_1 is complete / consumed
-      __syncthreads();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      bg_producer_sync();    // the P_1 tile is rewritten by the next block's epilogue
     }
   }
+  }   // producers
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512u);
 }
@@ -360,7 +387,7 @@ int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled) {
   p.off_pm = (uint32_t)o; o += round_up((size_t)(128 + a.C) * p.PS * sizeof(float), 16);
   p.off_q = (uint32_t)o; o += round_up((size_t)a.C * a.C * sizeof(float), 16);
   p.off_bias = (uint32_t)o; o += round_up((size_t)a.Hout * sizeof(float), 16);
-  p.off_bar = (uint32_t)o; o += 8 * (2 * BG_STAGES + 3) + 16;
+  p.off_bar = (uint32_t)o; o += 8 * (2 * BG_STAGES + 6) + 16;
   p.smem_bytes = (uint32_t)o;
   if (p.smem_bytes > 226 * 1024) return STC_OK;
   {
@@ -376,7 +403,7 @@ int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled) {
   const double R = (double)total_nodes * a.C;
   ScopedKernelTimer _t(KK_TC_CONV_FWD, st,
                        4.0 * R * (a.Ks * L + (a.phase == 0 ? 3 * a.h : 4 * a.h)) + 4.0 * P * L * a.Hout);
-  tc_conv_fwd_big_kernel<<<grid, BG_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
+  tc_conv_fwd_big_kernel<<<grid, BG_FWD_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
   STC_LAUNCH_OK("tc_conv_fwd_big_kernel");
   *handled = true;
   return STC_OK;

@@ -225,7 +225,7 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
       float4 cur[2], nxt[2];
       load_chunk(0, cur);
       for (int ch = 0; ch < p.nch; ++ch, ++g) {
-        if (ch + 1 < p.nch) load_chunk(ch + 1, nxt);   // next chunk's loads travel under this chunk's work
+        if (ch + 1 < p.nch) load_chunk(ch + 1, nxt);   // next chunk's loads travel under this chunk's work (two chunks ahead measured slower)
         const int buf = (int)(g & 1u);
         const uint32_t ua = g >> 1;
         if (ua >= 1u) {                                // the MMAs that read this A buffer two chunks ago are done
@@ -451,7 +451,9 @@ __global__ void tc_big_dx_prep_kernel(const float* __restrict__ W, uint8_t* __re
   }
 }
 
-__global__ void __launch_bounds__(BG_THREADS, 1)
+// (same role split as the forward kernel: warp 16 issues the MMAs and refills the weight ring, the 16 producer warps
+//  meet it only through mbarriers)
+__global__ void __launch_bounds__(BG_FWD_THREADS, 1)
 tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __restrict__ img) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -466,7 +468,9 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
   uint64_t* b_free = b_full + BG_STAGES;   // (arrays sized for the deepest ring)
   uint64_t* a_free = b_free + BG_STAGES;
   uint64_t* acc_full = a_free + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* a_full = acc_full + 1;                               // [2] producers -> issuer: A buffer staged in TMEM
+  uint64_t* acc_empty = a_full + 2;                              // producers -> issuer: a term's epilogue has read the accumulators
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   if (tid == 0) {
     for (int i = 0; i < BG_STAGES; ++i) {
@@ -476,14 +480,17 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
     mbar_init(&a_free[0], 1);
     mbar_init(&a_free[1], 1);
     mbar_init(acc_full, 1);
+    mbar_init(&a_full[0], BG_THREADS / 32);
+    mbar_init(&a_full[1], BG_THREADS / 32);
+    mbar_init(acc_empty, BG_THREADS / 32);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512u);
-  for (int i = tid; i < C * C; i += BG_THREADS) {
+  for (int i = tid; i < C * C; i += BG_FWD_THREADS) {
     Qs[i] = a.Q[C * C + i];
     dQacc[i] = 0.f;
   }
-  for (int i = tid; i < (128 + C) * DP; i += BG_THREADS) Dsm[i] = 0.f;
+  for (int i = tid; i < (128 + C) * DP; i += BG_FWD_THREADS) Dsm[i] = 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -507,13 +514,51 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
   const uint32_t per_tile = (uint32_t)(a.Ks * p.nkc);
   const uint32_t total_chunks = (uint32_t)my_tiles * per_tile;
   auto img_of = [&](uint32_t g) { return img + (size_t)(g % per_tile) * p.stage_bytes; };   // (k, kc) order = issue order
-  if (warp_u == 1 && elect_one_sync()) {
-    for (uint32_t g = 0; g < (uint32_t)(p.stages - 1) && g < total_chunks; ++g) {
-      mbar_arrive_expect_tx(&b_full[g], p.stage_bytes);
-      bulk_g2s(Bring + (size_t)g * p.stage_bytes, img_of(g), p.stage_bytes, &b_full[g]);
+  if (warp_u == BG_THREADS / 32) {
+    // =============================== issuer: MMAs + weight ring ===============================
+    if (elect_one_sync()) {
+      for (uint32_t g = 0; g < (uint32_t)(p.stages - 1) && g < total_chunks; ++g) {
+        mbar_arrive_expect_tx(&b_full[g], p.stage_bytes);
+        bulk_g2s(Bring + (size_t)g * p.stage_bytes, img_of(g), p.stage_bytes, &b_full[g]);
+      }
+      uint32_t g = 0, terms = 0;
+      for (int t_ = 0; t_ < my_tiles; ++t_) {
+        for (int k = 0; k < a.Ks; ++k, ++terms) {
+          for (int kc = 0; kc < p.nkc; ++kc, ++g) {
+            const int buf = (int)(g & 1u), st = (int)(g % (uint32_t)p.stages);
+            if (kc == 0 && terms > 0) mbar_wait(acc_empty, (terms - 1u) & 1u);   // previous term's epilogue is done
+            mbar_wait(&a_full[buf], (g >> 1) & 1u);
+            mbar_wait(&b_full[st], (g / (uint32_t)p.stages) & 1u);
+            fence_after_sync();
+            const uint32_t a_hi0 = tmem_base + (uint32_t)(BG_ACOL + 64 * buf);
+            const uint64_t dBh = make_smem_desc_sw128(smem_u32(Bring + (size_t)st * p.stage_bytes));
+            const uint64_t dBl = dBh + (uint64_t)(((uint32_t)Nb * ATOM_ROW_BYTES) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ko = (uint64_t)(ks * 2);
+              const uint32_t ah = a_hi0 + (uint32_t)(ks * 8), al = ah + 32u;
+              const uint32_t d_main = tmem_base + (uint32_t)((ks & 1) * Nb);
+              mma_tf32_atmem(d_small, al, dBh + ko, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+              mma_tf32_atmem(d_main, ah, dBh + ko, idesc, (kc > 0 || ks >= 2) ? 1u : 0u);
+              mma_tf32_atmem(d_small, ah, dBl + ko, idesc, 1u);
+            }
+            mma_commit(&a_free[buf]);
+            mma_commit(&b_free[st]);
+            if (kc == p.nkc - 1) mma_commit(acc_full);
+            const uint32_t t = g + (uint32_t)(p.stages - 1);
+            if (t < total_chunks) {
+              const uint32_t ts = t % (uint32_t)p.stages, tu = t / (uint32_t)p.stages;
+              if (tu >= 1u) mbar_wait(&b_free[ts], (tu - 1u) & 1u);
+              mbar_arrive_expect_tx(&b_full[ts], p.stage_bytes);
+              bulk_g2s(Bring + (size_t)ts * p.stage_bytes, img_of(t), p.stage_bytes, &b_full[ts]);
+            }
+          }
+        }
+      }
     }
-  }
-
+    __syncwarp();
+  } else {
+  // =============================== producers + epilogue (16 warps) ===============================
   uint32_t g = 0;
   uint32_t acc_phase = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -572,7 +617,7 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
       *reinterpret_cast<float4*>(Dsm + row * DP + j) = g0v;
       if (a.phase == 0) *reinterpret_cast<float4*>(Dsm + row * DP + h + j) = g1v;
     }
-    __syncthreads();
+    bg_producer_sync();
     if (a.dbias && tid < Hout) {
       float sacc = 0.f;
       for (int row = 0; row < rows_valid; ++row) sacc += Dsm[row * DP + tid];
@@ -711,36 +756,8 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
         }
         tmem_st_wait();
         fence_before_sync();
-        __syncthreads();
-        const int st = (int)(g % (uint32_t)p.stages);
-        if (warp_u == 0 && elect_one_sync()) {
-          mbar_wait(&b_full[st], (g / (uint32_t)p.stages) & 1u);
-          fence_after_sync();
-          const uint32_t a_hi0 = tmem_base + (uint32_t)(BG_ACOL + 64 * buf);
-          const uint64_t dBh = make_smem_desc_sw128(smem_u32(Bring + (size_t)st * p.stage_bytes));
-          const uint64_t dBl = dBh + (uint64_t)(((uint32_t)Nb * ATOM_ROW_BYTES) >> 4);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ko = (uint64_t)(ks * 2);
-            const uint32_t ah = a_hi0 + (uint32_t)(ks * 8), al = ah + 32u;
-            const uint32_t d_main = tmem_base + (uint32_t)((ks & 1) * Nb);
-            mma_tf32_atmem(d_small, al, dBh + ko, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-            mma_tf32_atmem(d_main, ah, dBh + ko, idesc, (kc > 0 || ks >= 2) ? 1u : 0u);
-            mma_tf32_atmem(d_small, ah, dBl + ko, idesc, 1u);
-          }
-          mma_commit(&a_free[buf]);
-          mma_commit(&b_free[st]);
-          if (kc == p.nkc - 1) mma_commit(acc_full);
-        }
-        if (warp_u == 1 && elect_one_sync()) {
-          const uint32_t t = g + (uint32_t)(p.stages - 1);
-          if (t < total_chunks) {
-            const uint32_t ts = t % (uint32_t)p.stages, tu = t / (uint32_t)p.stages;
-            if (tu >= 1u) mbar_wait(&b_free[ts], (tu - 1u) & 1u);
-            mbar_arrive_expect_tx(&b_full[ts], p.stage_bytes);
-            bulk_g2s(Bring + (size_t)ts * p.stage_bytes, img_of(t), p.stage_bytes, &b_full[ts]);
-          }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[buf]);       // one arrive per producer warp: the issuer takes it from here
       }
       // ---- epilogue of spatial term k: columns [0,h) -> h-part adjoint, [h, h+Din) -> x-part adjoint ----
       mbar_wait(acc_full, acc_phase);
@@ -782,12 +799,15 @@ tc_conv_bwd_dx_big_kernel(const ConvArgs a, const BigDxPlan p, const uint8_t* __
         }
       }
       fence_before_sync();
-      __syncthreads();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      bg_producer_sync();    // the Ds tile is rewritten by the next tile's prologue
     }
   }
   if (a.dbias && tid < Hout) atomicAdd(&a.dbias[tid], db_acc);
   if (want_dQ)
     for (int i = tid; i < C * C; i += BG_THREADS) atomicAdd(&a.dQ[C * C + i], dQacc[i]);
+  }   // producers
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512u);
 }
@@ -838,7 +858,7 @@ int try_launch_conv_bwd_dx_big(const ConvArgs& a, cudaStream_t st, bool* handled
   p.off_ds = (uint32_t)o; o += round_up((size_t)(128 + a.C) * p.DP * sizeof(float), 16);
   p.off_q = (uint32_t)o; o += round_up((size_t)a.C * a.C * sizeof(float), 16);
   p.off_qacc = (uint32_t)o; o += round_up((size_t)a.C * a.C * sizeof(float), 16);
-  p.off_bar = (uint32_t)o; o += 8 * (2 * BG_STAGES + 3) + 16;
+  p.off_bar = (uint32_t)o; o += 8 * (2 * BG_STAGES + 6) + 16;
   p.smem_bytes = (uint32_t)o;
   if (p.smem_bytes > 226 * 1024) return STC_OK;
   {
@@ -855,7 +875,7 @@ int try_launch_conv_bwd_dx_big(const ConvArgs& a, cudaStream_t st, bool* handled
   ScopedKernelTimer _t(KK_TC_CONV_BWD_DX, st,
                        4.0 * R * ((a.phase == 0 ? 6 * a.h + a.Ks * a.Din : 3 * a.h) + a.Hout + a.Ks * L +
                                   (a.dQ ? a.Hout : 0)) + 4.0 * a.Ks * a.Kc * L * a.Hout);
-  tc_conv_bwd_dx_big_kernel<<<grid, BG_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
+  tc_conv_bwd_dx_big_kernel<<<grid, BG_FWD_THREADS, p.smem_bytes, st>>>(a, p, reinterpret_cast<const uint8_t*>(a.Wimg));
   STC_LAUNCH_OK("tc_conv_bwd_dx_big_kernel");
   *handled = true;
   return STC_OK;

@@ -37,7 +37,22 @@ struct BigPlan {
   int x_vec;
   uint32_t stage_bytes;   // one weight chunk: [hi: Hout rows x 128 B | lo: Hout rows x 128 B]
   uint32_t off_b, off_pm, off_q, off_bias, off_bar, smem_bytes;
+  int land;               // depth of the per-thread cp.async landing ring for the row chunks (0: register double buffer)
+  uint32_t off_land;
 };
+
+__device__ __forceinline__ void bg_cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void bg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bg_cp_async_wait_depth(int pending) {   // wait until at most `pending` groups are in flight
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
 
 // img[(cb, ch)][hi | lo][o][kb]  <-  W[((k*Kc + cb)*L + l(kb))*Hout + o],  k = ch / nchk, kb = 32 (ch % nchk) + ...
 __global__ void tc_big_prep_kernel(const float* __restrict__ W, uint8_t* __restrict__ img, int Din, int h, int Ks, int Kc,
@@ -181,6 +196,68 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
   // =============================== producers + epilogue (16 warps) ===============================
   uint32_t g = 0;                                      // running chunk counter of this CTA
   uint32_t acc_phase = 0;
+  // ---- row chunks, asynchronous form: every thread owns one 32-byte slot per ring stage; its 8 K-values of a chunk
+  //      travel global -> shared with cp.async, `land - 1` chunks ahead and ACROSS block / tile boundaries (the register
+  //      double buffer restarts at every categorical block and exposes one round trip per chunk, 30 % of the kernel's
+  //      stall samples in profiles/r3o_config3_wide_ncu.txt).  Only the owner touches a slot: no barriers.
+  const int LD = p.land;
+  const uint32_t land0 = smem_u32(smem + p.off_land) + (uint32_t)tid * 32u;
+  int c_tile = blockIdx.x, c_cbi = 0, c_ch = 0;        // the chunk the next copy is for
+  uint32_t c_seq = 0;
+  auto issue_copy = [&]() {
+    if (c_tile < p.ntiles) {
+      const long long cg0 = (long long)c_tile * p.npt;
+      const int cnodes = (int)min((long long)p.npt, total_nodes - cg0);
+      const bool cvalid = erow < cnodes * C;
+      const long long cgr = cg0 * C + erow;
+      const uint32_t dst = land0 + (c_seq % (uint32_t)LD) * (uint32_t)(BG_THREADS * 32);
+      const int k = c_ch / p.nchk, j = c_ch - k * p.nchk;
+      const int kb0 = 32 * j + 8 * qtr;
+      bool z0 = true, z1 = true;
+      if (cvalid) {
+        if (kb0 < h) {
+          const float* hs = (k == 0 ? a.h0 : a.yh + (size_t)(k - 1) * R * h) + cgr * h + kb0;
+          bg_cp_async16(dst, hs);
+          bg_cp_async16(dst + 16u, hs + 4);
+          z0 = z1 = false;
+        } else {
+          const int xi = kb0 - h;
+          const float* xs;
+          if (k == 0) {
+            const long long gn = cg0 + enode;
+            const long long b = gn / a.N;
+            xs = a.x0 + b * a.x0_bs + ((gn - b * a.N) * C + ecat) * Din;
+          } else {
+            xs = a.yx + (size_t)(k - 1) * R * Din + cgr * Din;
+          }
+          if (xvec) {
+            if (xi < Din) { bg_cp_async16(dst, xs + xi); z0 = false; }
+            if (xi + 4 < Din) { bg_cp_async16(dst + 16u, xs + xi + 4); z1 = false; }
+          } else {   // unaligned x-part (layer-0 cells, Din = 1): plain loads, it is tiny
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = (xi + i < Din) ? xs[xi + i] : 0.f;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "f"(e[4]), "f"(e[5]), "f"(e[6]), "f"(e[7]) : "memory");
+            z0 = z1 = false;
+          }
+        }
+      }
+      if (z0) asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.f) : "memory");
+      if (z1) asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst + 16u), "f"(0.f) : "memory");
+      if (++c_ch == p.nch) {
+        c_ch = 0;
+        if (++c_cbi == 2) {
+          c_cbi = 0;
+          c_tile += gridDim.x;
+        }
+      }
+    }
+    ++c_seq;
+    bg_cp_async_commit();
+  };
+  if (LD > 0)
+    for (int i = 0; i < LD - 1; ++i) issue_copy();
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const long long g0 = (long long)tile * p.npt;
     const int nodes_valid = (int)min((long long)p.npt, total_nodes - g0);
@@ -223,9 +300,18 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
     for (int cbi = 0; cbi < 2; ++cbi) {                // categorical block c = 1, then c = 0
       const int cb = 1 - cbi;
       float4 cur[2], nxt[2];
-      load_chunk(0, cur);
+      nxt[0] = nxt[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (LD == 0) load_chunk(0, cur);
       for (int ch = 0; ch < p.nch; ++ch, ++g) {
-        if (ch + 1 < p.nch) load_chunk(ch + 1, nxt);   // next chunk's loads travel under this chunk's work (two chunks ahead measured slower)
+        if (LD > 0) {
+          issue_copy();                                  // chunk g + LD - 1 (a group is committed even past the end)
+          bg_cp_async_wait_depth(LD - 1);                // my piece of chunk g has landed
+          const uint32_t src = land0 + (g % (uint32_t)LD) * (uint32_t)(BG_THREADS * 32);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[0].x), "=f"(cur[0].y), "=f"(cur[0].z), "=f"(cur[0].w) : "r"(src) : "memory");
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[1].x), "=f"(cur[1].y), "=f"(cur[1].z), "=f"(cur[1].w) : "r"(src + 16u) : "memory");
+        } else if (ch + 1 < p.nch) {
+          load_chunk(ch + 1, nxt);   // register double buffer: next chunk's loads travel under this chunk's work
+        }
         const int buf = (int)(g & 1u);
         const uint32_t ua = g >> 1;
         if (ua >= 1u) {                                // the MMAs that read this A buffer two chunks ago are done
@@ -246,8 +332,10 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[buf]);       // one arrive per producer warp: the issuer takes it from here
-        cur[0] = nxt[0];
-        cur[1] = nxt[1];
+        if (LD == 0) {
+          cur[0] = nxt[0];
+          cur[1] = nxt[1];
+        }
       }
       // ---- epilogue of this categorical block ----
       mbar_wait(acc_full, acc_phase);
@@ -336,6 +424,7 @@ tc_conv_fwd_big_kernel(const ConvArgs a, const BigPlan p, const uint8_t* __restr
       bg_producer_sync();    // the P_1 tile is rewritten by the next block's epilogue
     }
   }
+  if (LD > 0) bg_cp_async_wait_depth(0);
   }   // producers
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512u);
@@ -388,6 +477,20 @@ int try_launch_conv_fwd_big(const ConvArgs& a, cudaStream_t st, bool* handled) {
   p.off_q = (uint32_t)o; o += round_up((size_t)a.C * a.C * sizeof(float), 16);
   p.off_bias = (uint32_t)o; o += round_up((size_t)a.Hout * sizeof(float), 16);
   p.off_bar = (uint32_t)o; o += 8 * (2 * BG_STAGES + 6) + 16;
+  o = round_up(o, 128);
+  {   // as many landing stages (16 KB each: 512 threads x 32 B) as fit, at most 4; fewer than 2: register double buffer
+    static int land_max = -1;
+    if (land_max < 0) {
+      const char* e = getenv("STC_BIG_LAND");
+      land_max = (e && e[0]) ? atoi(e) : 4;
+    }
+    int land = (int)(((size_t)226 * 1024 - o) / (BG_THREADS * 32));
+    if (land > land_max) land = land_max;
+    if (land < 2) land = 0;
+    p.land = land;
+    p.off_land = (uint32_t)o;
+    o += (size_t)land * BG_THREADS * 32;
+  }
   p.smem_bytes = (uint32_t)o;
   if (p.smem_bytes > 226 * 1024) return STC_OK;
   {

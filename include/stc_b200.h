@@ -181,6 +181,12 @@ int stc_halo_unpack(const float* recv, int32_t width, int32_t B, int32_t row0, i
  * 3xTF32 tcgen05 product with TMEM accumulation (the same code path as the gate contraction).  N <= 256. */
 int stc_tf32x3_gemm(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K, void* stream);
 
+/* Independent kernels of one stc_cell_fwd / stc_cell_bwd call (dW beside the adjoint hops, the dGs outer products, the
+ * Xt-side hops beside the H-side hops) may be forked onto internal side streams and are joined back with events
+ * before the call returns; by default only for problems too small to fill the device.  mode: -1 = by problem size
+ * (default; the STC_CONCURRENCY environment variable sets the initial value), 0 = always one stream, 1 = always fork. */
+int stc_concurrency_set(int32_t mode);
+
 /* Number of kernel launches the last stc_cell_fwd / stc_cell_bwd on this thread issued
  * (bench.py reports gpu_launches from these). */
 int stc_last_launch_count(void);

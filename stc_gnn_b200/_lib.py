@@ -21,7 +21,7 @@ EXPORTED = (
     "stc_timing_enable", "stc_timing_collect", "stc_kernel_kind_name", "stc_tf32x3_gemm",
     "stc_cell_saved_layout", "stc_cell_fwd_stage", "stc_debug_trace_set",
     "stc_cell_bwd_scratch_layout", "stc_cell_bwd_stage",
-    "stc_support_apply_rows", "stc_halo_pack", "stc_halo_unpack",
+    "stc_support_apply_rows", "stc_halo_pack", "stc_halo_unpack", "stc_concurrency_set",
 )
 STAGE_GATES, STAGE_CANDI = 0, 1
 SAVED_REGIONS = ("u", "r", "c", "Yr", "Yx", "Yh", "Q", "Pg", "Pc")
@@ -87,6 +87,8 @@ def load(build_if_missing: bool = True):
     lib.stc_halo_pack.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p]
     lib.stc_halo_unpack.restype = c_int
     lib.stc_halo_unpack.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]
+    lib.stc_concurrency_set.restype = c_int
+    lib.stc_concurrency_set.argtypes = [c_int32]
     lib.stc_tf32x3_gemm.restype = c_int
     lib.stc_tf32x3_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     lib.stc_timing_enable.restype = c_int
@@ -136,6 +138,11 @@ LAUNCHES = 0
 def note_launches() -> None:
     global LAUNCHES
     LAUNCHES += int(_lib.stc_last_launch_count())
+
+
+def set_concurrency(mode: int) -> None:
+    """-1: fork independent kernels of a cell call onto side streams only for small problems (default); 0: never; 1: always."""
+    check(load().stc_concurrency_set(int(mode)), "stc_concurrency_set")
 
 
 def timing_enable(on: bool) -> None:

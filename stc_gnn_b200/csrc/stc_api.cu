@@ -156,13 +156,15 @@ static SidePool* side_pool() {
   return p.ok ? &p : nullptr;
 }
 
-static int concurrency_mode() {   // -1 auto, 0 off, 1 on
-  static int cached = -2;
-  if (cached == -2) {
+static std::atomic<int> g_concurrency{-2};   // -2: not read yet; -1 auto, 0 off, 1 on
+static int concurrency_mode() {
+  int m = g_concurrency.load(std::memory_order_relaxed);
+  if (m == -2) {
     const char* e = getenv("STC_CONCURRENCY");
-    cached = (e && e[0]) ? (atoi(e) != 0 ? 1 : 0) : -1;
+    m = (e && e[0]) ? (atoi(e) != 0 ? 1 : 0) : -1;
+    g_concurrency.store(m, std::memory_order_relaxed);
   }
-  return cached;
+  return m;
 }
 
 // Fork / join helper of one cell call.  Inactive (every stream() is the caller's stream, fork / join are no-ops) when the
@@ -331,6 +333,15 @@ int stc_debug_trace_set(void* dev_buf, int64_t n_slots) {
   std::lock_guard<std::mutex> lk(g_tmu);
   g_trace_buf = (long long*)dev_buf;
   g_trace_tiles = dev_buf ? (int)(n_slots / (2 * TRACE_SLOTS)) : 0;
+  return STC_OK;
+}
+
+int stc_concurrency_set(int32_t mode) {
+  if (mode < -1 || mode > 1) {
+    set_error("stc_concurrency_set: mode %d (use -1 = by problem size, 0 = one stream, 1 = always fork)", mode);
+    return STC_ERR_BAD_ARG;
+  }
+  g_concurrency.store(mode, std::memory_order_relaxed);
   return STC_OK;
 }
 

@@ -441,3 +441,38 @@ def test_config4_knn65536_f64_forward_backward_exact_subgraph():
         outside = torch.ones(N, dtype=torch.bool)
         outside[Ut] = False
         assert float(gg[k][:, outside].abs().max()) == 0.0, f"config4 {k} must vanish outside the closure of S"
+
+
+def test_inplace_and_returned_leaf_gradients_agree_and_lanes_do_not_change_results(monkeypatch):
+    """Two execution options of the same arithmetic: (a) leaf gradients accumulated in place by the kernels vs returned
+    through autograd and summed by it, (b) independent kernels of a cell call forked onto side streams vs one stream.
+    A 2-layer x T = 3 stack (shared weights across steps, supports feeding every cell) exercises the accumulation."""
+    from stc_gnn_b200 import _lib, cell as cellmod
+    torch.manual_seed(5)
+    stack = S.RecurrentStack(20, 5, 2, 2, 1, 16, 2, 2).to(DEV)
+    params = list(stack.parameters())
+    g = torch.Generator().manual_seed(12)
+    Gs0 = (torch.rand(20, 20, generator=g) / 10).to(DEV)
+    Gc0 = (torch.rand(5, 5, generator=g) / 3).to(DEV)
+    X = torch.randn(3, 3, 20, 5, 1, generator=g).to(DEV)
+
+    def run(inplace, lanes):
+        monkeypatch.setattr(cellmod, "INPLACE_LEAF_GRADS", inplace)
+        _lib.set_concurrency(lanes)
+        Gs, Gc = Gs0.clone().requires_grad_(True), Gc0.clone().requires_grad_(True)
+        for p in params:
+            p.grad = None
+        out = stack(Gs, Gc, X)
+        out.square().mean().backward()
+        torch.cuda.synchronize()
+        return [out.detach().clone()] + [t.grad.detach().clone() for t in params + [Gs, Gc]]
+
+    try:
+        base = run(True, 0)
+        for inplace, lanes in ((False, 0), (True, 1), (False, 1)):
+            got = run(inplace, lanes)
+            assert torch.equal(got[0], base[0]), "forward must be bit-identical"
+            for i, (a, b) in enumerate(zip(got[1:], base[1:])):   # atomics: summation order differs, nothing else
+                O.assert_close(a.cpu(), b.double().cpu(), f"gradient {i} (inplace={inplace}, lanes={lanes})")
+    finally:
+        _lib.set_concurrency(-1)

@@ -43,23 +43,81 @@ def uninstall(stc_gnn_module=None):
     return stc_gnn_module
 
 
-def run_main(framework_dir: str, argv):
+class SlicedLoader:
+    """Iterates a reference ``IncDataset`` (``Data_Container.py:43-66``) in contiguous batches by slicing its tensors.
+
+    Same batches, in the same order, as the ``DataLoader(dataset, batch_size, shuffle=False)`` the reference builds
+    (``Data_Container.py:102``: no shuffling, last partial batch kept) -- without default-collating ``batch_size``
+    single-item device tensors per step."""
+
+    def __init__(self, dataset, batch_size: int):
+        self.dataset, self.batch_size = dataset, int(batch_size)
+        self.x, self.y = dataset.inputs["x_seq"], dataset.output
+        self.n = len(dataset)
+
+    def __len__(self):
+        return (self.n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for s in range(0, self.n, self.batch_size):
+            e = min(self.n, s + self.batch_size)
+            yield self.x[s:e], self.y[s:e]
+
+
+def _patch_loop_hygiene(data_container_module):
+    """Trainer-loop hygiene around the frozen files; returns an undo function.
+
+    * ``DataGenerator.get_data_loader`` keeps the reference's own windowing and split and only swaps each DataLoader
+      for a ``SlicedLoader`` over the same dataset;
+    * ``torch.cuda.empty_cache()`` -- called after EVERY step by ``Model_Trainer.py:87``, which hands every cached block
+      back to the driver and makes the next step cudaMalloc all of its buffers again -- becomes a no-op for the run."""
+    import torch
+    gen_cls = data_container_module.DataGenerator
+    orig_get, orig_empty = gen_cls.get_data_loader, torch.cuda.empty_cache
+
+    def get_data_loader(self, params, data):
+        loaders = orig_get(self, params, data)
+        return {mode: SlicedLoader(dl.dataset, dl.batch_size) for mode, dl in loaders.items()}
+
+    gen_cls.get_data_loader = get_data_loader
+    torch.cuda.empty_cache = lambda: None
+
+    def undo():
+        gen_cls.get_data_loader = orig_get
+        torch.cuda.empty_cache = orig_empty
+    return undo
+
+
+def run_main(framework_dir: str, argv, hygiene: bool = False, install_cell: bool = True):
     """Run the reference's Main.py unmodified with the B200 cell installed:
-    ``run_main('/path/to/STC-GNN/framework', ['-city', 'SF', '-device', 'cuda:0'])``."""
+    ``run_main('/path/to/STC-GNN/framework', ['-city', 'SF', '-device', 'cuda:0'])``.
+
+    ``hygiene``: additionally feed the trainer contiguous batch slices instead of per-item collation and neutralise its
+    per-step ``torch.cuda.empty_cache()`` (see ``_patch_loop_hygiene``); ``install_cell=False`` runs the stock cell (for
+    A/B timing of the same script)."""
     framework_dir = os.path.abspath(framework_dir)
     sys.dont_write_bytecode = True
     if framework_dir not in sys.path:
         sys.path.insert(0, framework_dir)
     old_cwd, old_argv = os.getcwd(), sys.argv
     os.chdir(framework_dir)
+    undo = None
     try:
-        install()
+        if install_cell:
+            install()
+        if hygiene:
+            import Data_Container  # noqa: N813  (the reference's module)
+            undo = _patch_loop_hygiene(Data_Container)
         sys.argv = [os.path.join(framework_dir, "Main.py")] + list(argv)
         runpy.run_path("Main.py", run_name="__main__")
     finally:
+        if undo is not None:
+            undo()
         sys.argv = old_argv
         os.chdir(old_cwd)
 
 
 if __name__ == "__main__":
-    run_main(sys.argv[1], sys.argv[2:])
+    _args = sys.argv[2:]
+    _hyg = "--hygiene" in _args
+    run_main(sys.argv[1], [x for x in _args if x != "--hygiene"], hygiene=_hyg)

@@ -128,3 +128,39 @@ def test_seeded_init_and_checkpoint_compat_with_live_reference():
     finally:
         from stc_gnn_b200.install import uninstall
         uninstall(ref)
+
+
+def test_sliced_loader_yields_the_reference_dataloaders_batches():
+    """the loop-hygiene loaders keep the reference's windowing / split and reproduce its DataLoader's
+    batches exactly (order, shapes, last partial batch) -- checked against the live reference's own data path."""
+    import io
+    from contextlib import redirect_stdout
+    from tests.helpers import find_reference
+    ref = find_reference()
+    if ref is None:
+        pytest.skip("needs the live reference")
+    import sys
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    sys.dont_write_bytecode = True
+    import Data_Container as dc
+    from stc_gnn_b200.install import SlicedLoader, _patch_loop_hygiene
+    with redirect_stdout(io.StringIO()):
+        data = dc.DataInput(os.path.join(os.path.dirname(ref), "data", "SF-incidents-4h.npz")).load_data()
+    data = dict(data, inc=data["inc"][:400])                       # a slice is enough: 388 windows, 6:1:1
+    gen = dc.DataGenerator(obs_len=9, pred_len=3, data_split_ratio=(6, 1, 1))
+    params = dict(H=10, W=10, C=5, device="cpu", batch_size=32)
+    stock = gen.get_data_loader(params=params, data=data)
+    undo = _patch_loop_hygiene(dc)
+    try:
+        fast = gen.get_data_loader(params=params, data=data)
+        assert all(isinstance(v, SlicedLoader) for v in fast.values())
+    finally:
+        undo()
+    assert dc.DataGenerator.get_data_loader(gen, params, data)["train"].__class__.__name__ == "DataLoader"   # undone
+    for mode in ("train", "validate", "test"):
+        a, b = list(stock[mode]), list(fast[mode])
+        assert len(a) == len(b) == len(fast[mode])
+        for (xa, ya), (xb, yb) in zip(a, b):
+            assert torch.equal(xa, xb) and torch.equal(ya, yb)
+    assert a[-1][0].shape[0] != 32 or len(stock["test"].dataset) % 32 == 0   # the partial batch is part of the comparison

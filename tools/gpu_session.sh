@@ -11,6 +11,7 @@
 #   launches[:B]     ncu launch list of one bench step     ncu[:REGEX[:SKIP[:COUNT]]]  one ncu --set full capture
 #   support|config3|config4|config5   tools/bench_configs.py side workloads
 #   full:N:CFG:B[:stock|adam]  reference STCGNN + installed cell, DP over N GPUs (CFG = sf | longc)
+#   mainpy[:EPOCHS]  the reference's Main.py for EPOCHS epochs: stock cell | installed | installed + loop hygiene
 #   halo:N[:train]   tools/bench_halo.py on N GPUs         trace      clock64 phase trace of the gate convolutions
 #   memcheck         compute-sanitizer over the smallest parity case of every kernel family
 #   probe            what the box has (GPU, host cores / memory, reference probe)
@@ -83,6 +84,7 @@ for stage in "$@"; do
       if [ "$N" = 1 ]; then timeout 900 python tools/bench_full_model.py $FLAGS 2>> gpurun_out/full_$T.err | tee -a gpurun_out/full_$T.jsonl
       else timeout 900 bash -c "$(declare -f RUN); RUN $N tools/bench_full_model.py $FLAGS" 2>> gpurun_out/full_$T.err | tee -a gpurun_out/full_$T.jsonl; fi
       tail -2 gpurun_out/full_$T.err ;;
+    mainpy) timeout 1200 python tools/bench_main.py --epochs ${A1:-2} 2> gpurun_out/mainpy_$T.err | tee gpurun_out/mainpy_$T.jsonl | cut -c1-400 ;;
     trace) timeout 200 python tools/trace_conv.py 2048 16 > gpurun_out/trace_$T.txt 2>&1; tail -5 gpurun_out/trace_$T.txt ;;
     memcheck)
       P=tests/test_cell_gpu.py

@@ -52,8 +52,8 @@ def main():
             code = CHILD.format(root=ROOT, ref=ref, epochs=epochs, out=out, data=data, hygiene=hygiene, install=install)
             res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1500)
         txt = res.stdout + res.stderr
-        times = [float(x) for x in re.findall(r"training time: ([0-9.eE+-]+) s/epoch", txt)]
-        infer = [float(x) for x in re.findall(r"inference time: ([0-9.eE+-]+) s", txt)]
+        times = [float(x) for x in re.findall(r"Epoch \d+: training time: ([0-9.eE+-]+) s/epoch", txt)]   # not the "Average ..." line
+        infer = [float(x) for x in re.findall(r"; inference time: ([0-9.eE+-]+) s", txt)]
         loss = re.findall(r"training loss: ([0-9.eE+-]+);", txt)
         wall = re.findall(r"WALL_S ([0-9.]+)", txt)
         rec = {"kind": "main_py_epoch", "variant": name, "epochs": int(epochs), "rc": res.returncode,

@@ -118,6 +118,6 @@ def run_main(framework_dir: str, argv, hygiene: bool = False, install_cell: bool
 
 
 if __name__ == "__main__":
-    _args = sys.argv[2:]
+    _args = sys.argv[2:]      # python -m stc_gnn_b200.install <framework dir> [--hygiene] <Main.py arguments ...>
     _hyg = "--hygiene" in _args
     run_main(sys.argv[1], [x for x in _args if x != "--hygiene"], hygiene=_hyg)

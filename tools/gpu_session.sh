@@ -93,6 +93,8 @@ for stage in "$@"; do
         "$P::test_cell_matches_oracle_dense[None-shape1]" "$P::test_cell_matches_oracle_dense[None-shape4]" "$P::test_cell_matches_oracle_dense[None-shape6]" \
         "$P::test_cell_matches_oracle_dense[None-shape8]" "$P::test_cell_matches_oracle_csr[shape0]" \
         "$P::test_support_apply_matches_oracle[dense]" "$P::test_support_apply_matches_oracle[csr]" \
+        "$P::test_inplace_and_returned_leaf_gradients_agree_and_lanes_do_not_change_results" \
+        "tests/test_halo_gpu.py::test_row_subset_apply_and_halo_pack_unpack_kernels" "tests/test_halo_gpu.py::test_staged_cell_single_rank" \
         > gpurun_out/memcheck_$T.log 2>&1; echo "memcheck exit $?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|rror:" gpurun_out/memcheck_$T.log | head -12 ;;
     *) echo "unknown stage $stage" ;;
   esac

@@ -560,6 +560,28 @@ def run_b200(args):
                 Xq, yq = Xq.to(dev), yq.to(dev)
                 return lambda: step(Xq, yq)
             eager = gpu_eager_baseline(dev, [32, 512, 4096], ours_at)
+            # the reference's own batch size replayed from a CUDA graph (an eager step of 48 C-ABI calls is host-bound there)
+            try:
+                Xq, yq, _, _ = synthetic_inputs(32, seed=0)
+                Xq, yq = Xq.to(dev), yq.to(dev)
+                gs32 = S.GraphedStep(lambda X, y: loss_fn(stack(Gs, Gc, X), y), [Xq, yq], leaves, warmup=3)
+                for _ in range(3):
+                    gs32.replay(Xq, yq)
+                torch.cuda.synchronize()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(20):
+                    gs32.replay(Xq, yq)
+                g1.record()
+                torch.cuda.synchronize()
+                ms32 = g0.elapsed_time(g1) / 20
+                eager["graph_replay_b32"] = {"batch": 32, "b200_samples_per_s": 32 / (ms32 / 1e3), "b200_ms_per_step": ms32,
+                                             "what": "stc_gnn_b200.GraphedStep replay of the same fwd+bwd step"}
+                del gs32
+            except Exception as exc:
+                eager["graph_replay_b32"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+            for p in leaves:
+                p.grad = None
         if not args.no_cpu_baseline:
             cpu_baseline = cpu_baseline_record(args.cpu_batch, 40, 1, budget_s=14.0)
 

@@ -130,6 +130,31 @@ int stc_cell_bwd(const StcDims* d, const StcSupport* gs, const float* gc,
                  int32_t accumulate_params, const void* saved, size_t saved_bytes,
                  void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- the Xt-side spatial terms hoisted out of the time loop ----
+ * In the encoder's first layer Xt does not depend on the recurrence (STC_GNN.py:107-118), so its spatial terms for ALL
+ * timesteps can be produced by one batched stc_support_apply and handed in:
+ *   yx_terms      [Ks-1][B][N][C][Din] contiguous = Y_1 .. Y_{Ks-1} of this step's Xt (NULL: computed inside, as
+ *                 stc_cell_fwd / stc_cell_bwd do); the forward then launches no Xt-side hop.
+ *   dyx_terms_out [Ks-1][B][N][C][Din]: stc_cell_bwd_x writes the adjoints of those terms there and does NOT fold them:
+ *                 no Xt-side adjoint hop and no Xt-side dGs contribution is launched; d_xt (if given) holds the term-0
+ *                 part only.  The caller folds all timesteps at once (dGs += sum_t X_t (x) dY_1,t via
+ *                 stc_support_outer, dXt += Gs dY_1 via stc_support_apply).  Both pointers go together. */
+int stc_cell_fwd_x(const StcDims* d, const StcSupport* gs, const float* gc,
+                   const float* xt, int64_t xt_batch_stride, const float* h_prev,
+                   const float* Wg, const float* bg, const float* Wc, const float* bc,
+                   float* h_out, void* saved, size_t saved_bytes, const float* yx_terms, void* stream);
+int stc_cell_bwd_x(const StcDims* d, const StcSupport* gs, const float* gc,
+                   const float* xt, int64_t xt_batch_stride, const float* h_prev,
+                   const float* Wg, const float* Wc, const float* d_h_out,
+                   float* d_xt, float* d_h_prev,
+                   float* dWg, float* dbg, float* dWc, float* dbc, float* dGs, float* dGc,
+                   int32_t accumulate_params, const void* saved, size_t saved_bytes,
+                   void* scratch, size_t scratch_bytes, const float* yx_terms, float* dyx_terms_out, void* stream);
+/* dGs[n][m] += coef * sum_{b,j} A[b][n][j] * Bm[b][m][j]  -- the gradient of the mode product Y = Gs^T X w.r.t. a dense
+ * Gs [N][N] with A = X ([B][N][width], batch stride in elements) and Bm = dL/dY ([B][N][width] contiguous). */
+int stc_support_outer(int32_t N, int32_t B, int32_t width, const float* a, int64_t a_batch_stride, const float* b,
+                      float coef, float* dGs, void* stream);
+
 /* ---- the backward split the same way (gradients through a row-partitioned graph) ----
  * Order: stage STC_STAGE_CANDI first, then STC_STAGE_GATES (the reverse of the forward).
  *   1. STC_STAGE_CANDI: clears the parameter and Gc gradients unless accumulate_params, runs the candidate-conv adjoint.  Leaves

@@ -22,6 +22,7 @@ EXPORTED = (
     "stc_cell_saved_layout", "stc_cell_fwd_stage", "stc_debug_trace_set",
     "stc_cell_bwd_scratch_layout", "stc_cell_bwd_stage",
     "stc_support_apply_rows", "stc_halo_pack", "stc_halo_unpack", "stc_concurrency_set",
+    "stc_cell_fwd_x", "stc_cell_bwd_x", "stc_support_outer",
 )
 STAGE_GATES, STAGE_CANDI = 0, 1
 SAVED_REGIONS = ("u", "r", "c", "Yr", "Yx", "Yh", "Q", "Pg", "Pc")
@@ -61,6 +62,10 @@ def load(build_if_missing: bool = True):
     lib.stc_cell_fwd.restype = c_int
     lib.stc_cell_fwd.argtypes = [POINTER(StcDims), POINTER(StcSupport), c_void_p, c_void_p, c_int64, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.stc_cell_fwd_x.restype = c_int
+    lib.stc_cell_fwd_x.argtypes = lib.stc_cell_fwd.argtypes[:-1] + [c_void_p, c_void_p]
+    lib.stc_support_outer.restype = c_int
+    lib.stc_support_outer.argtypes = [c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_float, c_void_p, c_void_p]
     lib.stc_cell_saved_layout.restype = c_int
     lib.stc_cell_saved_layout.argtypes = [POINTER(StcDims), POINTER(c_int64), c_int32]
     lib.stc_cell_fwd_stage.restype = c_int
@@ -71,6 +76,8 @@ def load(build_if_missing: bool = True):
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_void_p, c_size_t,
                                  c_void_p]
+    lib.stc_cell_bwd_x.restype = c_int
+    lib.stc_cell_bwd_x.argtypes = lib.stc_cell_bwd.argtypes[:-1] + [c_void_p, c_void_p, c_void_p]
     lib.stc_cell_bwd_scratch_layout.restype = c_int
     lib.stc_cell_bwd_scratch_layout.argtypes = [POINTER(StcDims), POINTER(c_int64), c_int32]
     lib.stc_cell_bwd_stage.restype = c_int

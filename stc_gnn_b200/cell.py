@@ -73,10 +73,12 @@ def _ptr(t):
 
 
 class _CellFunction(torch.autograd.Function):
-    """One cell step. Inputs that may need gradients: Gs (dense only), Gc, Xt, H, Wg, bg, Wc, bc."""
+    """One cell step. Inputs that may need gradients: Gs (dense only), Gc, Xt, H, Wg, bg, Wc, bc, and -- when the
+    caller hoisted the Xt-side spatial terms out of the time loop (stack.py) -- those terms `Yx` [Ks-1,B,N,C,Din], whose
+    gradient is returned un-folded."""
 
     @staticmethod
-    def forward(ctx, Gs, Gc, Xt, H, Wg, bg, Wc, bc, cfg):
+    def forward(ctx, Gs, Gc, Xt, H, Wg, bg, Wc, bc, Yx, cfg):
         lib = _lib.load()
         Ks, Kc, act = cfg
         B, N, C, Din = Xt.shape
@@ -117,11 +119,25 @@ class _CellFunction(torch.autograd.Function):
         saved = torch.empty(_buffer_floats(lib, dims, ctx.size_key)[0], dtype=torch.float32, device=Xt.device)
         Hn = torch.empty((B, N, C, h), dtype=torch.float32, device=Xt.device)
         stream = torch.cuda.current_stream().cuda_stream
-        status = 0 if B == 0 else lib.stc_cell_fwd(dims, gs_struct, Gc_c.data_ptr(), Xt_c.data_ptr(), xbs, H_c.data_ptr(),
-                                  Wg_c.data_ptr(), _ptr(bg_c), Wc_c.data_ptr(), _ptr(bc_c), Hn.data_ptr(),
-                                  saved.data_ptr(), saved.numel() * 4, stream)
+        Yx_c = None
+        if Yx is not None and Ks > 1:
+            if Yx.shape != (Ks - 1, B, N, C, Din) or not Yx.is_cuda or Yx.dtype != torch.float32:
+                raise RuntimeError(f"hoisted Xt-side terms must be a float32 CUDA tensor of shape {(Ks - 1, B, N, C, Din)}, "
+                                   f"got {tuple(Yx.shape)}")
+            Yx_c = Yx.contiguous()
+        if B == 0:
+            status = 0
+        elif Yx_c is not None:
+            status = lib.stc_cell_fwd_x(dims, gs_struct, Gc_c.data_ptr(), Xt_c.data_ptr(), xbs, H_c.data_ptr(),
+                                        Wg_c.data_ptr(), _ptr(bg_c), Wc_c.data_ptr(), _ptr(bc_c), Hn.data_ptr(),
+                                        saved.data_ptr(), saved.numel() * 4, Yx_c.data_ptr(), stream)
+        else:
+            status = lib.stc_cell_fwd(dims, gs_struct, Gc_c.data_ptr(), Xt_c.data_ptr(), xbs, H_c.data_ptr(),
+                                      Wg_c.data_ptr(), _ptr(bg_c), Wc_c.data_ptr(), _ptr(bc_c), Hn.data_ptr(),
+                                      saved.data_ptr(), saved.numel() * 4, stream)
         _lib.check(status, "stc_cell_fwd")
         _lib.note_launches()
+        ctx.hoisted = Yx_c is not None
         ctx.cfg, ctx.dims_tuple, ctx.xbs, ctx.csr = cfg, (B, N, C, Din, h), xbs, csr
         ctx.gs_obj = Gs if csr else None
         ctx.has_bias = bg is not None
@@ -131,7 +147,8 @@ class _CellFunction(torch.autograd.Function):
             for i, t in ((0, None if csr else Gs), (1, Gc), (4, Wg), (5, bg), (6, Wc), (7, bc)):
                 if t is not None and ctx.needs_input_grad[i] and t.is_leaf and t.is_contiguous():
                     ctx.sinks[i] = t
-        ctx.save_for_backward(*( [] if csr else [gs_keep] ), Gc_c, Xt_c, H_c, Wg_c, Wc_c, saved)
+        ctx.save_for_backward(*( [] if csr else [gs_keep] ), Gc_c, Xt_c, H_c, Wg_c, Wc_c, saved,
+                              *([Yx_c] if Yx_c is not None else []))
         return Hn
 
     @staticmethod
@@ -140,7 +157,8 @@ class _CellFunction(torch.autograd.Function):
         lib = _lib.load()
         Ks, Kc, act = ctx.cfg
         B, N, C, Din, h = ctx.dims_tuple
-        sv = ctx.saved_tensors
+        sv = list(ctx.saved_tensors)
+        Yx = sv.pop() if ctx.hoisted else None
         if ctx.csr:
             Gs = ctx.gs_obj
             Gc, Xt, H, Wg, Wc, saved = sv
@@ -148,15 +166,19 @@ class _CellFunction(torch.autograd.Function):
         else:
             Gs, Gc, Xt, H, Wg, Wc, saved = sv
             gs_struct = dense_struct(Gs)
-        need = ctx.needs_input_grad  # Gs, Gc, Xt, H, Wg, bg, Wc, bc, cfg
+        need = ctx.needs_input_grad  # Gs, Gc, Xt, H, Wg, bg, Wc, bc, Yx, cfg
         dev = dHn.device
         dHn = dHn.contiguous()
         L, P = Din + h, Ks * Kc
         dims = _dims(B, N, C, Din, h, Ks, Kc, act, ctx.has_bias)
         new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        if ctx.hoisted and need[2]:
+            raise RuntimeError("hoisted Xt-side terms: the gradient w.r.t. Xt is folded by the caller (stack.py hoists only "
+                               "when the input sequence needs no gradient)")
         dXt = new(B, N, C, Din) if need[2] else None
         dH = new(B, N, C, h)
-        returned = [None] * 9
+        dYx = torch.empty_like(Yx) if ctx.hoisted else None
+        returned = [None] * 10
 
         def target(i, shape, wanted=True):
             """Buffer the kernels ADD input i's gradient into: the leaf's own `.grad` (created zeroed on first use in a
@@ -177,18 +199,24 @@ class _CellFunction(torch.autograd.Function):
         dbg, dbc = target(5, (2 * h,), ctx.has_bias), target(7, (h,), ctx.has_bias)
         dGs = target(0, (N, N), need[0] and not ctx.csr)
         dGc = target(1, (C, C), need[1])
-        returned[2], returned[3] = dXt, dH
+        returned[2], returned[3], returned[8] = dXt, dH, dYx
         if B == 0:  # empty batch: every parameter gradient is zero (the targets are zeroed or untouched), nothing to launch
+            if dYx is not None:
+                dYx.zero_()
             return tuple(returned)
         scratch = torch.empty(_buffer_floats(lib, dims, ctx.size_key)[1], dtype=torch.float32, device=dev)
-        status = lib.stc_cell_bwd(dims, gs_struct, Gc.data_ptr(), Xt.data_ptr(), ctx.xbs, H.data_ptr(), Wg.data_ptr(),
-                                  Wc.data_ptr(), dHn.data_ptr(), _ptr(dXt), dH.data_ptr(), dWg.data_ptr(), _ptr(dbg),
-                                  dWc.data_ptr(), _ptr(dbc), _ptr(dGs), _ptr(dGc), 1, saved.data_ptr(),
-                                  saved.numel() * 4, scratch.data_ptr(), scratch.numel() * 4,
-                                  torch.cuda.current_stream().cuda_stream)
+        common = (dims, gs_struct, Gc.data_ptr(), Xt.data_ptr(), ctx.xbs, H.data_ptr(), Wg.data_ptr(),
+                  Wc.data_ptr(), dHn.data_ptr(), _ptr(dXt), dH.data_ptr(), dWg.data_ptr(), _ptr(dbg),
+                  dWc.data_ptr(), _ptr(dbc), _ptr(dGs), _ptr(dGc), 1, saved.data_ptr(),
+                  saved.numel() * 4, scratch.data_ptr(), scratch.numel() * 4)
+        stream = torch.cuda.current_stream().cuda_stream
+        if ctx.hoisted:
+            status = lib.stc_cell_bwd_x(*common, Yx.data_ptr(), dYx.data_ptr(), stream)
+        else:
+            status = lib.stc_cell_bwd(*common, stream)
         _lib.check(status, "stc_cell_bwd")
         _lib.note_launches()
-        for i in (0, 1, 4, 5, 6, 7):       # inputs that need no gradient get none, whatever was computed for them
+        for i in (0, 1, 4, 5, 6, 7, 8):    # inputs that need no gradient get none, whatever was computed for them
             if not need[i]:
                 returned[i] = None
         return tuple(returned)
@@ -196,7 +224,7 @@ class _CellFunction(torch.autograd.Function):
 
 def stc_cell_forward(Gs, Gc, Xt, Ht_1, Wg, bg, Wc, bc, Ks: int, Kc: int, activation=None) -> torch.Tensor:
     """Functional form of the cell: H' = STC_Cell(Gs, Gc, Xt, Ht_1) with explicit weights (differentiable)."""
-    return _CellFunction.apply(Gs, Gc, Xt, Ht_1, Wg, bg, Wc, bc, (int(Ks), int(Kc), _activation_code(activation)))
+    return _CellFunction.apply(Gs, Gc, Xt, Ht_1, Wg, bg, Wc, bc, None, (int(Ks), int(Kc), _activation_code(activation)))
 
 
 class STC_Cell(nn.Module):
@@ -223,7 +251,9 @@ class STC_Cell(nn.Module):
         weight = next(self.parameters()).data
         return weight.new_zeros(batch_size, self.num_nodes, self.num_categories, self.hidden_dim)
 
-    def forward(self, Gs, Gc: torch.Tensor, Xt: torch.Tensor, Ht_1: torch.Tensor):
+    def forward(self, Gs, Gc: torch.Tensor, Xt: torch.Tensor, Ht_1: torch.Tensor, _Yx: torch.Tensor = None):
+        """`_Yx` (not part of the reference's signature): the spatial terms of Xt, [Ks-1,B,N,C,Din], when the caller
+        produced them for a whole sequence at once (stack.py); their gradient comes back un-folded."""
         assert len(Xt.shape) == len(Ht_1.shape) == 4, 'STC-cell must take in 4D tensor as input [Xt, Ht-1]'
         if isinstance(Gs, torch.Tensor) and Gs.layout != torch.strided:
             Gs = _csr_cache(Gs)
@@ -235,7 +265,7 @@ class STC_Cell(nn.Module):
                                             getattr(self.candi, "b", None), self.Ks, self.Kc, _ACT_NAMES[self._act],
                                             reduce_params=getattr(Gs, "reduce_per_cell", True))
         return _CellFunction.apply(Gs, Gc, Xt, Ht_1, self.gates.W, getattr(self.gates, "b", None), self.candi.W,
-                                   getattr(self.candi, "b", None), (self.Ks, self.Kc, self._act))
+                                   getattr(self.candi, "b", None), _Yx, (self.Ks, self.Kc, self._act))
 
 
 _CSR_CACHE = {}

@@ -433,6 +433,7 @@ struct FwdCtx {
   float* ws;
   cudaStream_t st;
   Lanes* lanes = nullptr;   // set by stc_cell_fwd: the Xt-side terms and the Gc terms may run beside the H-side terms
+  const float* yx_pre = nullptr;   // caller-supplied spatial terms of Xt ([Ks-1][B][N][C][Din]): skip the Xt-side hops
 };
 
 // spatial Chebyshev terms of Xt and H:  Y_1 = Gs^T Y_0,  Y_k = 2 Gs^T Y_{k-1} - Y_{k-2}
@@ -445,11 +446,11 @@ static int fwd_terms_xh(const FwdCtx& f) {
   const long long nbs_h = (long long)d.N * CH;
   // the two recurrences are independent of each other: Xt's on side stream 0 (when lanes are active), H's on the caller's
   cudaStream_t sx = f.st;
-  if (f.lanes && f.lanes->active() && d.Ks > 1) {
+  if (f.lanes && f.lanes->active() && d.Ks > 1 && !f.yx_pre) {
     STC_TRY(f.lanes->fork(0));
     sx = f.lanes->stream(0);
   }
-  for (int k = 1; k < d.Ks; ++k) {
+  for (int k = 1; k < d.Ks && !f.yx_pre; ++k) {
     const float alpha = k == 1 ? 1.f : 2.f, beta = k == 1 ? 0.f : -1.f;
     const float* xin = k == 1 ? f.xt : ws + w.Yx + (size_t)(k - 2) * Rx;
     const int64_t xin_bs = k == 1 ? f.xt_bs : (int64_t)d.N * CD;
@@ -476,6 +477,7 @@ static int fwd_gates(const FwdCtx& f, const float* Wg, const float* bg) {
   float* ws = f.ws;
   if (d.Kc > 1) STC_TRY(launch_cheby_small(f.gc, d.C, d.Kc, ws + w.Q, f.st));
   ConvArgs a = base_args(d, f.xt, f.xt_bs, Wg, ws + w.Q, ws, w, 0);
+  if (f.yx_pre) a.yx = f.yx_pre;
   a.h0 = f.h_prev;
   a.yh = ws + w.Yh;
   a.bias = d.has_bias ? bg : nullptr;
@@ -513,6 +515,7 @@ static int fwd_candi(const FwdCtx& f, const float* Wc, const float* bc, float* h
   float* ws = f.ws;
   const size_t Rh = w.R * d.h;
   ConvArgs a = base_args(d, f.xt, f.xt_bs, Wc, ws + w.Q, ws, w, 1);
+  if (f.yx_pre) a.yx = f.yx_pre;
   a.h0 = ws + w.Yr;
   a.yh = ws + w.Yr + Rh;
   a.bias = d.has_bias ? bc : nullptr;
@@ -545,13 +548,14 @@ static int check_fwd_args(const StcDims* dp, const float* gc, const float* xt, c
   return STC_OK;
 }
 
-int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
-                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* bg, const float* Wc,
-                 const float* bc, float* h_out, void* wsv, size_t ws_bytes, void* stream) {  // wsv = `saved`
+static int cell_fwd_impl(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                         int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* bg, const float* Wc,
+                         const float* bc, float* h_out, void* wsv, size_t ws_bytes, const float* yx_terms, void* stream,
+                         const char* who) {
   reset_launch_count();
-  STC_TRY(check_fwd_args(dp, gc, xt, h_prev, Wg, bg, Wc, bc, h_out, wsv, ws_bytes, "stc_cell_fwd"));
+  STC_TRY(check_fwd_args(dp, gc, xt, h_prev, Wg, bg, Wc, bc, h_out, wsv, ws_bytes, who));
   if (!gs) {
-    set_error("stc_cell_fwd: NULL support");
+    set_error("%s: NULL support", who);
     return STC_ERR_BAD_ARG;
   }
   const StcDims& d = *dp;
@@ -561,11 +565,26 @@ int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
   Lanes lanes((cudaStream_t)stream, d);
   FwdCtx f{d, w, gs, gc, xt, xt_batch_stride, h_prev, (float*)wsv, (cudaStream_t)stream};
   f.lanes = &lanes;
+  f.yx_pre = d.Ks > 1 ? yx_terms : nullptr;
   STC_TRY(fwd_terms_xh(f));
   STC_TRY(fwd_gates(f, Wg, bg));
   STC_TRY(fwd_terms_rh(f));
   STC_TRY(fwd_candi(f, Wc, bc, h_out));
   return STC_OK;
+}
+
+int stc_cell_fwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* bg, const float* Wc,
+                 const float* bc, float* h_out, void* wsv, size_t ws_bytes, void* stream) {  // wsv = `saved`
+  return cell_fwd_impl(dp, gs, gc, xt, xt_batch_stride, h_prev, Wg, bg, Wc, bc, h_out, wsv, ws_bytes, nullptr, stream,
+                       "stc_cell_fwd");
+}
+
+int stc_cell_fwd_x(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                   int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* bg, const float* Wc,
+                   const float* bc, float* h_out, void* wsv, size_t ws_bytes, const float* yx_terms, void* stream) {
+  return cell_fwd_impl(dp, gs, gc, xt, xt_batch_stride, h_prev, Wg, bg, Wc, bc, h_out, wsv, ws_bytes, yx_terms, stream,
+                       "stc_cell_fwd_x");
 }
 
 int stc_cell_saved_layout(const StcDims* dp, int64_t* offsets, int32_t n_offsets) {
@@ -645,6 +664,8 @@ struct BwdCtx {
   float* sc;          // scratch
   cudaStream_t st;
   Lanes* lanes = nullptr;   // set by stc_cell_bwd: dW runs beside the adjoint hops on side stream 0
+  const float* yx_pre = nullptr;   // caller-supplied spatial terms of Xt (as in forward)
+  float* dyx_out = nullptr;        // caller's buffer for the x-part adjoints of terms k >= 1 (the caller folds them)
   bool want_dGc() const { return dGc != nullptr && d.Kc > 1; }
   float* dYx0() const { return d_xt ? d_xt : sc + w.dYx0; }
 };
@@ -705,6 +726,7 @@ static int bwd_candi(const BwdCtx& b, const float* Wc, float* dWc, float* dbc) {
   const WsLayout& w = b.w;
   const size_t Rh = w.R * d.h;
   ConvArgs a = base_args(d, b.xt, b.xt_bs, Wc, b.sv + w.Q, b.sv, w, 1);
+  if (b.yx_pre) a.yx = b.yx_pre;
   a.h0 = b.sv + w.Yr;
   a.yh = b.sv + w.Yr + Rh;
   a.Hprev = b.h_prev;
@@ -714,7 +736,7 @@ static int bwd_candi(const BwdCtx& b, const float* Wc, float* dWc, float* dbc) {
   a.dpre = b.sc + w.dpre;
   a.dbias = d.has_bias ? dbc : nullptr;
   a.dYx0 = b.dYx0();
-  a.dYx = b.sc + w.dYx;
+  a.dYx = b.dyx_out ? b.dyx_out : b.sc + w.dYx;
   a.accum_x = 0;
   a.dYh0 = b.sc + w.dYr;
   a.dYh = b.sc + w.dYr + Rh;
@@ -731,6 +753,7 @@ static int bwd_gates(const BwdCtx& b, const float* Wg, float* dWg, float* dbg) {
   const StcDims& d = b.d;
   const WsLayout& w = b.w;
   ConvArgs a = base_args(d, b.xt, b.xt_bs, Wg, b.sv + w.Q, b.sv, w, 0);
+  if (b.yx_pre) a.yx = b.yx_pre;
   a.h0 = b.h_prev;
   a.yh = b.sv + w.Yh;
   a.Hprev = b.h_prev;
@@ -742,7 +765,7 @@ static int bwd_gates(const BwdCtx& b, const float* Wg, float* dWg, float* dbg) {
   a.dpre = b.sc + w.dpre;
   a.dbias = d.has_bias ? dbg : nullptr;
   a.dYx0 = b.dYx0();
-  a.dYx = b.sc + w.dYx;
+  a.dYx = b.dyx_out ? b.dyx_out : b.sc + w.dYx;
   a.accum_x = 1;
   a.dYh0 = b.d_h_prev;
   a.dYh = b.sc + w.dYh;
@@ -757,21 +780,26 @@ static int bwd_gates(const BwdCtx& b, const float* Wg, float* dWg, float* dbg) {
   return STC_OK;
 }
 
-int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
-                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* Wc,
-                 const float* d_h_out, float* d_xt, float* d_h_prev, float* dWg, float* dbg, float* dWc, float* dbc,
-                 float* dGs, float* dGc, int32_t accumulate_params, const void* savedv, size_t saved_bytes,
-                 void* scratchv, size_t scratch_bytes, void* stream) {
+static int cell_bwd_impl(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                         int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* Wc,
+                         const float* d_h_out, float* d_xt, float* d_h_prev, float* dWg, float* dbg, float* dWc, float* dbc,
+                         float* dGs, float* dGc, int32_t accumulate_params, const void* savedv, size_t saved_bytes,
+                         void* scratchv, size_t scratch_bytes, const float* yx_terms, float* dyx_terms_out, void* stream,
+                         const char* who) {
   reset_launch_count();
   STC_TRY(check_bwd_args(dp, gc, xt, h_prev, Wg, Wc, d_h_out, d_h_prev, dWg, dbg, dWc, dbc, savedv, saved_bytes, scratchv,
-                         scratch_bytes, "stc_cell_bwd"));
+                         scratch_bytes, who));
   const StcDims& d = *dp;
   if (!gs) {
-    set_error("stc_cell_bwd: NULL argument");
+    set_error("%s: NULL argument", who);
     return STC_ERR_BAD_ARG;
   }
   if (dGs && gs->kind != STC_SUPPORT_DENSE) {
-    set_error("stc_cell_bwd: dGs is only defined for a dense support");
+    set_error("%s: dGs is only defined for a dense support", who);
+    return STC_ERR_BAD_ARG;
+  }
+  if (d.Ks > 1 && ((yx_terms != nullptr) != (dyx_terms_out != nullptr))) {
+    set_error("%s: yx_terms and dyx_terms_out go together (the caller that supplied the Xt-side terms folds their adjoints)", who);
     return STC_ERR_BAD_ARG;
   }
   const WsLayout w = make_layout(d);
@@ -781,6 +809,11 @@ int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
   BwdCtx b{d, w, gc, xt, xt_batch_stride, h_prev, d_h_out, d_xt, d_h_prev, dGc,
            const_cast<float*>((const float*)savedv), (float*)scratchv, st};
   b.lanes = &lanes;
+  const bool hoisted = d.Ks > 1 && yx_terms != nullptr;
+  if (hoisted) {
+    b.yx_pre = yx_terms;
+    b.dyx_out = dyx_terms_out;
+  }
   STC_TRY(bwd_begin(b, dWg, dbg, dWc, dbc, dGs, accumulate_params));
   if (d.B == 0) return STC_OK;
   const size_t Rh = w.R * d.h;
@@ -796,14 +829,47 @@ int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const
   STC_TRY(adjoint_chain(d, *gs, CH, b.sv + w.Yr, (int64_t)d.N * CH, b.sv + w.Yr + Rh, b.sc + w.dYr, b.sc + w.dYr + Rh,
                         dGs, st, &lanes, 1));
   STC_TRY(bwd_gates(b, Wg, dWg, dbg));
-  cudaStream_t sx = st;
-  if (lanes.active() && d.Ks > 1) {
-    STC_TRY(lanes.fork(2));
-    sx = lanes.stream(2);
+  if (!hoisted) {   // (hoisted: the x-part adjoints of terms k >= 1 sit in the caller's buffer; d_xt holds term 0 only)
+    cudaStream_t sx = st;
+    if (lanes.active() && d.Ks > 1) {
+      STC_TRY(lanes.fork(2));
+      sx = lanes.stream(2);
+    }
+    STC_TRY(adjoint_chain(d, *gs, CD, xt, xt_batch_stride, b.sv + w.Yx, b.dYx0(), b.sc + w.dYx, dGs, sx, &lanes, 1));
   }
-  STC_TRY(adjoint_chain(d, *gs, CD, xt, xt_batch_stride, b.sv + w.Yx, b.dYx0(), b.sc + w.dYx, dGs, sx, &lanes, 1));
   STC_TRY(adjoint_chain(d, *gs, CH, h_prev, (int64_t)d.N * CH, b.sv + w.Yh, d_h_prev, b.sc + w.dYh, dGs, st, &lanes, 1));
   return lanes.join_all();
+}
+
+int stc_cell_bwd(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                 int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* Wc,
+                 const float* d_h_out, float* d_xt, float* d_h_prev, float* dWg, float* dbg, float* dWc, float* dbc,
+                 float* dGs, float* dGc, int32_t accumulate_params, const void* savedv, size_t saved_bytes,
+                 void* scratchv, size_t scratch_bytes, void* stream) {
+  return cell_bwd_impl(dp, gs, gc, xt, xt_batch_stride, h_prev, Wg, Wc, d_h_out, d_xt, d_h_prev, dWg, dbg, dWc, dbc, dGs, dGc,
+                       accumulate_params, savedv, saved_bytes, scratchv, scratch_bytes, nullptr, nullptr, stream,
+                       "stc_cell_bwd");
+}
+
+int stc_cell_bwd_x(const StcDims* dp, const StcSupport* gs, const float* gc, const float* xt,
+                   int64_t xt_batch_stride, const float* h_prev, const float* Wg, const float* Wc,
+                   const float* d_h_out, float* d_xt, float* d_h_prev, float* dWg, float* dbg, float* dWc, float* dbc,
+                   float* dGs, float* dGc, int32_t accumulate_params, const void* savedv, size_t saved_bytes,
+                   void* scratchv, size_t scratch_bytes, const float* yx_terms, float* dyx_terms_out, void* stream) {
+  return cell_bwd_impl(dp, gs, gc, xt, xt_batch_stride, h_prev, Wg, Wc, d_h_out, d_xt, d_h_prev, dWg, dbg, dWc, dbc, dGs, dGc,
+                       accumulate_params, savedv, saved_bytes, scratchv, scratch_bytes, yx_terms, dyx_terms_out, stream,
+                       "stc_cell_bwd_x");
+}
+
+int stc_support_outer(int32_t N, int32_t B, int32_t width, const float* a, int64_t a_batch_stride, const float* b,
+                      float coef, float* dGs, void* stream) {
+  reset_launch_count();
+  if (!a || !b || !dGs) {
+    set_error("stc_support_outer: NULL argument");
+    return STC_ERR_BAD_ARG;
+  }
+  STC_TRY(check_arch());
+  return launch_support_outer(N, B, width, a, a_batch_stride, b, coef, dGs, (cudaStream_t)stream);
 }
 
 int stc_cell_bwd_scratch_layout(const StcDims* dp, int64_t* offsets, int32_t n_offsets) {

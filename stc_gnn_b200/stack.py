@@ -9,7 +9,66 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from . import _lib
 from .cell import STC_Cell
+from .support import dense_struct, support_apply
+
+
+class _XSideTerms(torch.autograd.Function):
+    """Spatial terms of the WHOLE input sequence in one launch (Ks = 2, dense Gs).
+
+    In the encoder's first layer Xt does not depend on the recurrence (`framework/STC_GNN.py:107-118`), and with the
+    shipped input width (Din = 1, C = 5) a per-step product is 5 floats wide: it runs on the general FFMA kernels at
+    0.05 of HBM bandwidth, 18 + 9 launches per step.  Here the sequence is regrouped as [B, N, T*C*Din] (padded to a
+    multiple of 4 columns) so that ONE tensor-core `stc_support_apply` produces Y_1 = Gs^T X for all T, and the backward
+    folds all T adjoints into dGs with ONE `stc_support_outer`.  Outputs: T tensors [1, B, N, C, Din] (= [Ks-1, ...]),
+    handed to the cells as `_Yx`.  The input sequence itself gets no gradient through this path (callers hoist only
+    when it needs none)."""
+
+    @staticmethod
+    def forward(ctx, Gs, X_seq):
+        B, T, N, C, Din = X_seq.shape
+        W = T * C * Din
+        Wp = (W + 3) & ~3
+        Xp = X_seq.new_zeros(B, N, Wp) if Wp != W else X_seq.new_empty(B, N, Wp)
+        Xp[:, :, :W] = X_seq.permute(0, 2, 1, 3, 4).reshape(B, N, W)
+        Gs_c = Gs.detach().contiguous()
+        Y1p = support_apply(Gs_c, Xp, transpose=True)
+        outs = tuple(Y1p[:, :, t * C * Din:(t + 1) * C * Din].reshape(1, B, N, C, Din).contiguous() for t in range(T))
+        ctx.save_for_backward(Gs_c, Xp)
+        ctx.shape = (B, T, N, C, Din, W, Wp)
+        return outs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *dY):
+        Gs, Xp = ctx.saved_tensors
+        B, T, N, C, Din, W, Wp = ctx.shape
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        dYp = Xp.new_zeros(B, N, Wp) if Wp != W else Xp.new_empty(B, N, Wp)
+        for t, g in enumerate(dY):
+            piece = dYp[:, :, t * C * Din:(t + 1) * C * Din]
+            if g is None:
+                piece.zero_()
+            else:
+                piece.copy_(g.reshape(B, N, C * Din))
+        dGs = torch.zeros(N, N, dtype=torch.float32, device=Xp.device)
+        lib = _lib.load()
+        _lib.check(lib.stc_support_outer(N, B, Wp, Xp.data_ptr(), N * Wp, dYp.data_ptr(), 1.0, dGs.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "stc_support_outer")
+        _lib.note_launches()
+        return dGs, None
+
+
+def _hoistable(Gs, X_seq: torch.Tensor, cell: STC_Cell) -> bool:
+    """One batched launch pays when the per-step product is narrow (the shipped Din = 1) and nothing needs dX_seq."""
+    if not isinstance(Gs, torch.Tensor) or Gs.layout != torch.strided or not Gs.is_cuda or Gs.dtype != torch.float32:
+        return False
+    B, T, N, C, Din = X_seq.shape
+    narrow = (C * Din) % 4 != 0 or C * Din < 32
+    return (cell.Ks == 2 and narrow and T >= 2 and B > 0 and N <= 128 and not X_seq.requires_grad and X_seq.is_cuda
+            and X_seq.dtype == torch.float32)
 
 
 class RecurrentStack(nn.Module):
@@ -35,11 +94,13 @@ class RecurrentStack(nn.Module):
         # add per timestep (select_backward) -- same values, none of that traffic.
         seq = [X_seq[:, t] for t in range(T)]
         last = []
-        for cell in self.encoder:
+        for li, cell in enumerate(self.encoder):
             Ht = cell.init_hidden(B)
             outs = []
+            # layer 0: the Xt-side spatial terms of all T steps from one batched launch (row f1)
+            yx = _XSideTerms.apply(Gs, X_seq) if (li == 0 and _hoistable(Gs, X_seq, cell)) else None
             for t in range(T):
-                Ht = cell(Gs=Gs, Gc=Gc, Xt=seq[t], Ht_1=Ht)
+                Ht = cell(Gs=Gs, Gc=Gc, Xt=seq[t], Ht_1=Ht, _Yx=None if yx is None else yx[t])
                 outs.append(Ht)
             seq = outs
             last.append(Ht)

@@ -476,3 +476,47 @@ def test_inplace_and_returned_leaf_gradients_agree_and_lanes_do_not_change_resul
                 O.assert_close(a.cpu(), b.double().cpu(), f"gradient {i} (inplace={inplace}, lanes={lanes})")
     finally:
         _lib.set_concurrency(-1)
+
+
+def test_stack_with_hoisted_x_side_terms_matches_reference_golden():
+    """when the input sequence needs no gradient, RecurrentStack produces the layer-0 Xt-side spatial
+    terms of all T steps with one batched launch and folds their adjoints into dGs with one outer product.  Same golden
+    as test_stack_matches_reference_golden (outputs, dGs, dGc, every parameter gradient); the launch count proves the path."""
+    from stc_gnn_b200 import _lib
+    cfg, t = load_stack()
+    stack = S.RecurrentStack(cfg["N"], cfg["C"], cfg["Ks"], cfg["Kc"], cfg["Din"], cfg["h"], cfg["layers"],
+                             cfg["horizon"]).to(DEV)
+    with torch.no_grad():
+        for tag, mods in (("enc", stack.encoder), ("dec", stack.decoder)):
+            for i, cell in enumerate(mods):
+                for conv in ("gates", "candi"):
+                    for pn in ("W", "b"):
+                        getattr(getattr(cell, conv), pn).copy_(t[f"{tag}{i}_{conv}_{pn}"])
+
+    def run(x_needs_grad):
+        Gs = t["Gs"].to(DEV).requires_grad_(True)
+        Gc = t["Gc"].to(DEV).requires_grad_(True)
+        X = t["X_seq"].to(DEV).requires_grad_(x_needs_grad)
+        stack.zero_grad(set_to_none=True)
+        l0 = _lib.LAUNCHES
+        out = stack(Gs, Gc, X)
+        out.backward(t["dOut"].to(DEV))
+        torch.cuda.synchronize()
+        return out.detach(), Gs.grad, Gc.grad, [p.grad.clone() for p in stack.parameters()], _lib.LAUNCHES - l0
+
+    out_h, dGs_h, dGc_h, dP_h, launches_h = run(False)     # hoisted
+    out_p, dGs_p, dGc_p, dP_p, launches_p = run(True)      # per-cell Xt-side hops
+    T = cfg["T"]
+    assert launches_h <= launches_p - 3 * T + 2, (launches_h, launches_p)   # T hops + T outer products + T adjoint hops -> 1 + 1
+    O.assert_close(out_h.cpu(), t["out"], "stack out (hoisted)")
+    bad = []
+    def chk(got, ref, name):
+        n, w = O.violations(got, ref, atol_scale=5e-5)       # the stack-level floor of test_stack_matches_reference_golden
+        if n:
+            bad.append(f"{name}: {n}/{ref.numel()} worst {w:.2e} x mean|ref|")
+    chk(dGs_h.cpu(), t["dGs"], "dGs")
+    chk(dGc_h.cpu(), t["dGc"], "dGc")
+    names = [f"{tag}{i}_{conv}_{pn}" for tag in ("enc", "dec") for i in range(cfg["layers"]) for conv in ("gates", "candi") for pn in ("W", "b")]
+    for nm, g_ in zip(names, dP_h):
+        chk(g_.cpu(), t["d_" + nm], nm)
+    assert not bad, "; ".join(bad)

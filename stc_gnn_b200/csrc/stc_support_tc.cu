@@ -102,9 +102,9 @@ tc_support_kernel(const float* __restrict__ G, const float* __restrict__ X, long
     if (elect_one_sync()) {
       const uint32_t idesc = make_idesc_tf32_atmem_bmn(128, TS_NT);
       // the hi and lo images of an X stage are adjacent with one column-block pitch, and so are the main and the
-      // cross-term accumulator: G_hi x [X_hi | X_lo] is ONE N = 2 TS_NT MMA.  The kernel is bound by MMA issue (13
-      // K-steps x 3 MMAs of N = 64 ~ 3.5 K cycles per tile against 2.3 K cycles of HBM time at the SM's fair share),
-      // so 2 MMAs per K-step instead of 3 is a direct gain.
+      // cross-term accumulator: G_hi x [X_hi | X_lo] is ONE N = 2 TS_NT MMA, i.e. 2 MMAs per K-step instead of 3.
+      // (Measured neutral, profiles/r3l_outer_support_ncu.txt: this kernel is bound neither by MMA issue nor by its
+      //  load structure -- the tensor work is the same three products either way.)
       const uint32_t idesc2 = make_idesc_tf32_atmem_bmn(128, 2 * TS_NT);
       int it = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {

@@ -1,6 +1,6 @@
 """Error margins of the wide-state parity cases: worst |got - ref| / mean|ref| per tensor and the number of elements
 outside the test tolerance (rtol 1e-4 + 1e-5 x mean|ref|), for the config 3 shapes (N = 4096, C = 16, F = 64, CSR).
-Run on a B200:  python tools/margins.py [repeats]"""
+Run on a B200:  python tests/margins_config3.py [repeats]"""
 import json
 import os
 import sys

@@ -325,7 +325,7 @@ int stc_timing_collect(double* ms, int64_t* launches, double* bytes, int32_t n_k
 const char* stc_kernel_kind_name(int32_t kind) {
   static const char* names[KK_COUNT] = {"support_dense", "support_csr", "support_outer", "cheby_small",
                                         "conv_fwd",      "conv_bwd_dx", "conv_bwd_dw", "tc_conv_fwd", "tc_conv_bwd_dx", "tc_conv_bwd_dw",
-                                        "tc_support", "tc_gemm_test", "tc_outer", "tc_cell_fwd"};
+                                        "tc_support", "tc_gemm_test", "tc_outer", "tc_support_big"};
   return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "?";
 }
 

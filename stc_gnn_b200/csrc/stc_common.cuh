@@ -42,7 +42,7 @@ void reset_launch_count();
 // ---- optional per-kernel timing (stc_timing_* in the ABI) ---------------------------------------
 enum KernelKind {
   KK_SUPPORT_DENSE = 0, KK_SUPPORT_CSR, KK_SUPPORT_OUTER, KK_CHEBY_SMALL, KK_CONV_FWD, KK_CONV_BWD_DX,
-  KK_CONV_BWD_DW, KK_TC_CONV_FWD, KK_TC_CONV_BWD_DX, KK_TC_CONV_BWD_DW, KK_TC_SUPPORT, KK_TC_GEMM_TEST, KK_TC_OUTER, KK_TC_CELL_FWD, KK_COUNT
+  KK_CONV_BWD_DW, KK_TC_CONV_FWD, KK_TC_CONV_BWD_DX, KK_TC_CONV_BWD_DW, KK_TC_SUPPORT, KK_TC_GEMM_TEST, KK_TC_OUTER, KK_TC_SUPPORT_BIG, KK_COUNT
 };
 struct ScopedKernelTimer {  // declare right before a launch; the destructor records the stop event
   ScopedKernelTimer(int kind, cudaStream_t st, double alg_bytes);
@@ -104,6 +104,10 @@ int launch_halo_rows(bool pack, float* x_ext, long long x_bs, int W, int B, cons
 int try_launch_support_tc(const float* G, int N, int B, int width, bool transpose, const float* x, int64_t x_bs,
                           const float* z, int64_t z_bs, float* y, float alpha, float beta, cudaStream_t st,
                           bool* handled);
+// dense N > 128 (stc_support_tc_big.cu)
+int try_launch_support_tc_big(const float* G, int N, int B, int width, bool transpose, const float* x, int64_t x_bs,
+                              const float* z, int64_t z_bs, float* y, float alpha, float beta, cudaStream_t st,
+                              bool* handled);
 int try_launch_outer_tc(int N, int B, int width, const float* a, int64_t a_bs, const float* bmat, float coef, float* dG,
                         cudaStream_t st, bool* handled);
 

@@ -202,6 +202,8 @@ int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool tra
       bool handled = false;
       STC_TRY(try_launch_support_tc(gs.vals, N, B, width, transpose, x, x_bs, z, z_bs, y, alpha, beta, st, &handled));
       if (handled) return STC_OK;
+      STC_TRY(try_launch_support_tc_big(gs.vals, N, B, width, transpose, x, x_bs, z, z_bs, y, alpha, beta, st, &handled));
+      if (handled) return STC_OK;
     }
     long long total_q = (long long)B * width;
     dim3 grid(ceil_div(total_q, SD_BQ), ceil_div(N, SD_BM));

@@ -190,6 +190,33 @@ def test_support_apply_matches_oracle(kind):
     O.assert_close(Y2, 2 * O.support_apply(G.double(), X.double()) - X.double(), "2 G X - X")
 
 
+@pytest.mark.parametrize("N,B,shape", [(130, 3, (3, 4)), (200, 2, (5, 4)), (256, 5, (4, 16)), (333, 1, (2, 6)),
+                                       (520, 2, (4, 8)), (1100, 1, (1, 36))])
+def test_dense_support_wider_than_one_tile(N, B, shape):
+    """Dense learned support with N > 128 (what MGP_Gen produces on a large graph, STC_GNN.py:231-243): the tiled
+    tensor-core kernel against the fp64 oracle -- both orientations, the Chebyshev form 2 G X - Z, accumulation in place,
+    node counts that are not multiples of the 128 / 64 tiles (and not of 4), column counts below one tile."""
+    from stc_gnn_b200 import _lib
+    g = torch.Generator().manual_seed(N)
+    G = torch.softmax(torch.randn(N, N, generator=g) * 2.0, dim=1).float()   # rows sum to one, all positive
+    X = torch.randn(B, N, *shape, generator=g).float()
+    Z = torch.randn(B, N, *shape, generator=g).float()
+    Gd, Xd, Zd = G.to(DEV), X.to(DEV), Z.to(DEV)
+    _lib.timing_enable(True)
+    _lib.timing_collect()
+    Y = S.support_apply(Gd, Xd, transpose=True)
+    Y2 = S.support_apply(Gd, Xd, transpose=False, alpha=2.0, beta=-1.0, Z=Zd)
+    acc = Zd.clone()
+    S.support_apply(Gd, Xd, transpose=False, alpha=1.0, beta=1.0, Z=acc, out=acc)
+    torch.cuda.synchronize()
+    _lib.timing_enable(False)
+    kinds = _lib.timing_collect()
+    assert kinds.get("tc_support_big", (0, 0, 0))[1] == 3, kinds   # the tensor-core kernel took every launch
+    O.assert_close(Y.cpu(), O.support_T_apply(G.double(), X.double()), "G^T X")
+    O.assert_close(Y2.cpu(), 2 * O.support_apply(G.double(), X.double()) - Z.double(), "2 G X - Z")
+    O.assert_close(acc.cpu(), O.support_apply(G.double(), X.double()) + Z.double(), "Z += G X")
+
+
 # ---- size-independent properties at the benchmark's full size (SF shape, B = 1024) -----------------
 def test_full_size_properties():
     dev = torch.device(DEV)

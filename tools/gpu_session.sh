@@ -14,6 +14,7 @@
 #   mainpy[:EPOCHS]  the reference's Main.py for EPOCHS epochs: stock cell | installed | installed + loop hygiene
 #   halo:N[:train]   tools/bench_halo.py on N GPUs         trace      clock64 phase trace of the gate convolutions
 #   memcheck         compute-sanitizer over the smallest parity case of every kernel family
+#   dense            tools/bench_dense_support.py: dense support with N > 128 (tcgen05 vs FFMA vs cuBLAS fp32)
 #   probe            what the box has (GPU, host cores / memory, reference probe)
 mkdir -p gpurun_out
 T=${1:?tag}; shift
@@ -36,6 +37,7 @@ for stage in "$@"; do
       timeout 900 python -m pytest tests/test_dropin_gpu.py -m gpu -q -s -rs > gpurun_out/dropin_$T.log 2>&1
       tail -4 gpurun_out/dropin_$T.log; grep -E "^E  |FAILED|^ERROR" gpurun_out/dropin_$T.log | head -20 ;;
     smoke) timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1 ;;
+    dense) timeout 240 python tools/bench_dense_support.py 2> gpurun_out/dense_$T.err | tee gpurun_out/dense_$T.jsonl; tail -3 gpurun_out/dense_$T.err ;;
     bench)
       N=${A1:-1}; O=gpurun_out/bench_${N}gpu_$T
       if [ "$N" = 1 ]; then timeout 900 python bench.py 2> $O.err > $O.json

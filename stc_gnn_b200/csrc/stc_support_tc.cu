@@ -325,6 +325,7 @@ constexpr int TO_THREADS = CV_THREADS + 32;   // 8 producer / drain warps + 1 MM
 
 struct TcOuterPlan {
   int N, Npad, W, B, atoms_per_sample;
+  int nblk;       // 128-node blocks per side (1 when the support fits one tile); blockIdx.y = block row * nblk + block column
   int tmem_cols;
   int drain;      // atoms per chain set
   uint32_t imgA, imgB, off_lo, off_bar, smem_bytes;
@@ -375,6 +376,9 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
   fence_after_sync();
   const int warp_u = uniform_warp_index();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  // N > 128: this CTA owns the 128 x 128 block (n0.., m0..) of dGs; rows past the edge of an operand block stay zero
+  const int n0 = ((int)blockIdx.y / p.nblk) * 128, m0 = ((int)blockIdx.y % p.nblk) * 128;
+  const int rowsA = min(128, N - n0), rowsB = min(128, N - m0);
   const int nsamples = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const long long natoms = (long long)nsamples * p.atoms_per_sample;
 
@@ -427,16 +431,14 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
         const long long b = blockIdx.x + cs * (long long)gridDim.x;
         const int j = cat * ATOM_K + q * 4;
         if (j < W) {                       // W % 4 == 0; chunks past W are never read (the MMAs stop at ceil(kleft / 8))
-          const float* pa = A + b * a_bs + j;
-          const float* pb = Bm + b * (long long)N * W + j;
+          const float* pa = A + b * a_bs + (long long)n0 * W + j;
+          const float* pb = Bm + (b * (long long)N + m0) * W + j;
           const uint32_t base = smem_u32(Hring + (size_t)(seq % TO_SH) * hsz);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = r0 + 32 * i;
-            if (r < N) {
-              cp_async16(base + soff[i], pa + (long long)r * W);
-              cp_async16(base + p.imgA + soff[i], pb + (long long)r * W);
-            }
+            if (r < rowsA) cp_async16(base + soff[i], pa + (long long)r * W);
+            if (r < rowsB) cp_async16(base + p.imgA + soff[i], pb + (long long)r * W);
           }
         }
         if (++cat == p.atoms_per_sample) {
@@ -497,12 +499,9 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
         uint8_t* lbp = Lring + (size_t)(seq % TO_SL) * hsz;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (r0 + 32 * i < N) {
-            const float4 va = *reinterpret_cast<const float4*>(hb + soff[i]);
-            const float4 vb = *reinterpret_cast<const float4*>(hb + p.imgA + soff[i]);
-            store_split4(hb, lbp, soff[i], va);
-            store_split4(hb + p.imgA, lbp + p.imgA, soff[i], vb);
-          }
+          if (r0 + 32 * i < rowsA) store_split4(hb, lbp, soff[i], *reinterpret_cast<const float4*>(hb + soff[i]));
+          if (r0 + 32 * i < rowsB)
+            store_split4(hb + p.imgA, lbp + p.imgA, soff[i], *reinterpret_cast<const float4*>(hb + p.imgA + soff[i]));
         }
       }
       fence_async_smem();
@@ -513,7 +512,7 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
     }
     cp_async_wait<0>();
 
-    if (nrow < N) {
+    if (nrow < rowsA) {
       const bool v4 = (N & 3) == 0 && (col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(dG) & 15) == 0;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
@@ -521,13 +520,13 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
 #pragma unroll
           for (int i = 0; i < 8; i += 4) {
             const int m = col0 + ch * 8 + i;
-            float* dst = &dG[(size_t)nrow * N + m];
-            if (v4 && m + 3 < N) {
+            float* dst = &dG[(size_t)(n0 + nrow) * N + m0 + m];
+            if (v4 && m + 3 < rowsB) {
               red_add_v4(dst, coef * acc[ch][i], coef * acc[ch][i + 1], coef * acc[ch][i + 2], coef * acc[ch][i + 3]);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (m + e < N) atomicAdd(dst + e, coef * acc[ch][i + e]);
+                if (m + e < rowsB) atomicAdd(dst + e, coef * acc[ch][i + e]);
             }
           }
         }
@@ -543,10 +542,20 @@ int try_launch_outer_tc(int N, int B, int width, const float* a, int64_t a_bs, c
                         cudaStream_t st, bool* handled) {
   *handled = false;
   if (tc_support_disabled()) return STC_OK;
-  if (width % 4 != 0 || a_bs % 4 != 0 || !aligned16s(a) || !aligned16s(bmat) || N < 8 || N > 128) return STC_OK;
+  if (width % 4 != 0 || a_bs % 4 != 0 || !aligned16s(a) || !aligned16s(bmat) || N < 8) return STC_OK;
   TcOuterPlan p;
   p.N = N;
-  p.Npad = (N + 15) & ~15;
+  p.nblk = (N + 127) / 128;
+  if ((long long)p.nblk * p.nblk > 65535) return STC_OK;
+  if (N > 128) {   // A/B switch for tools/bench_dense_support.py (shared with the N > 128 support kernel)
+    static int big_off = -1;
+    if (big_off < 0) {
+      const char* e = getenv("STC_DISABLE_TC_SUPPORT_BIG");
+      big_off = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    if (big_off == 1) return STC_OK;
+  }
+  p.Npad = N > 128 ? 128 : (N + 15) & ~15;
   p.W = width;
   p.B = B;
   p.atoms_per_sample = (width + ATOM_K - 1) / ATOM_K;
@@ -568,10 +577,14 @@ int try_launch_outer_tc(int N, int B, int width, const float* a, int64_t a_bs, c
   p.smem_bytes = p.off_bar + 8 * (2 * TO_SH + 1) + 16;
   if (p.smem_bytes > 227 * 1024) return STC_OK;
   STC_TRY(set_smem(tc_outer_kernel, p.smem_bytes));
+  // one tile: the CTAs split the samples.  N > 128: one CTA per 128 x 128 block of dGs and sample slice -- as few slices
+  // as still fill the device twice over (long K runs per CTA, one pass of vector reductions per CTA at the end)
+  const int nblocks = p.nblk * p.nblk;
   int grid = device_sm_count();
+  if (nblocks > 1) grid = (2 * grid + nblocks - 1) / nblocks;
   if (grid > B) grid = B;
   ScopedKernelTimer _t(KK_TC_OUTER, st, 4.0 * B * N * width * 2 + 4.0 * N * N);
-  tc_outer_kernel<<<grid, TO_THREADS, p.smem_bytes, st>>>(a, a_bs, bmat, coef, dG, p);
+  tc_outer_kernel<<<dim3(grid, nblocks), TO_THREADS, p.smem_bytes, st>>>(a, a_bs, bmat, coef, dG, p);
   STC_LAUNCH_OK("tc_outer_kernel");
   *handled = true;
   return STC_OK;

@@ -71,6 +71,8 @@ SHAPES = [
     (1, 10, 64, 64, 64, 2, 2),    # LongC-like: C = 64 categories, F = 64 (two nodes per 128-row tile)
     (2, 9, 2, 3, 4, 1, 3),
     (4, 1, 1, 1, 1, 2, 2),        # degenerate sizes
+    (2, 200, 4, 16, 16, 2, 2),    # dense support wider than one tile: tiled tcgen05 support + 2 x 2 blocks of dGs
+    (1, 300, 5, 4, 16, 3, 2),     # ... three Chebyshev terms, 3 x 3 blocks with a 44-node edge
 ]
 
 
@@ -215,6 +217,23 @@ def test_dense_support_wider_than_one_tile(N, B, shape):
     O.assert_close(Y.cpu(), O.support_T_apply(G.double(), X.double()), "G^T X")
     O.assert_close(Y2.cpu(), 2 * O.support_apply(G.double(), X.double()) - Z.double(), "2 G X - Z")
     O.assert_close(acc.cpu(), O.support_apply(G.double(), X.double()) + Z.double(), "Z += G X")
+
+
+def test_dense_wide_support_cell_runs_on_the_tensor_core_kernels():
+    """A cell step on a dense N = 200 support (forward hops, adjoint hops, dGs) launches no FFMA support kernel."""
+    from stc_gnn_b200 import _lib
+    shape = (2, 200, 4, 16, 16, 2, 2)
+    B, N, C, Din, h, Ks, Kc = shape
+    cfg = dict(B=B, N=N, C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, activation=None)
+    t = random_case(B, N, C, Din, h, Ks, Kc, seed=sum(shape))
+    _lib.timing_enable(True)
+    _lib.timing_collect()
+    run_cuda_cell(t, cfg)
+    torch.cuda.synchronize()
+    _lib.timing_enable(False)
+    kinds = _lib.timing_collect()
+    assert "support_dense" not in kinds and "support_outer" not in kinds, kinds
+    assert kinds["tc_support_big"][1] >= 4 and kinds["tc_outer"][1] >= 2, kinds
 
 
 # ---- size-independent properties at the benchmark's full size (SF shape, B = 1024) -----------------

@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import stc_gnn_b200 as S  # noqa: E402
+from stc_gnn_b200 import _lib  # noqa: E402
 
 CASES = [(1024, 16, 16 * 64), (4096, 8, 16 * 64), (4096, 8, 16 * 128)]   # (N, B, W = C * F)
 
@@ -48,6 +49,23 @@ def main():
             err_ref = (torch.einsum("bnw,nm->bmw", X, G).double() - ref).abs().max().item() / ref.abs().mean().item()
             row.update({"cublas_fp32_einsum_ms": round(ms_ref, 3), "max_err_over_mean_ref": float(f"{err:.2e}"),
                         "cublas_fp32_max_err_over_mean_ref": float(f"{err_ref:.2e}")})
+        print(json.dumps(row), flush=True)
+        # gradient of the same product w.r.t. the support: dGs[n][m] += sum_{b,j} X[b][n][j] * D[b][m][j]
+        D = torch.randn(B, N, W, device=dev, generator=g)
+        dG = torch.zeros(N, N, device=dev)
+        lib = _lib.load()
+        stream = torch.cuda.current_stream().cuda_stream
+        ms = time_ms(lambda: _lib.check(lib.stc_support_outer(N, B, W, X.data_ptr(), N * W, D.data_ptr(), 1.0, dG.data_ptr(),
+                                                              stream), "stc_support_outer"), iters)
+        row = {"case": f"dGs outer N={N} B={B} W={W}", "kernel": "support_outer (FFMA)" if child else "tc_outer, 128x128 blocks",
+               "ms": round(ms, 3), "useful_TFLOPs": round(flop / ms * 1e-9, 1)}
+        if not child:
+            ms_ref = time_ms(lambda: torch.einsum("bnw,bmw->nm", X, D), iters)
+            dG.zero_()
+            _lib.check(lib.stc_support_outer(N, B, W, X.data_ptr(), N * W, D.data_ptr(), 1.0, dG.data_ptr(), stream), "outer")
+            ref = torch.einsum("bnw,bmw->nm", X.double(), D.double())
+            err = (dG.double() - ref).abs().max().item() / ref.abs().mean().item()
+            row.update({"cublas_fp32_einsum_ms": round(ms_ref, 3), "max_err_over_mean_ref": float(f"{err:.2e}")})
         print(json.dumps(row), flush=True)
     if not child:
         env = dict(os.environ, STC_DISABLE_TC_SUPPORT_BIG="1")

@@ -9,6 +9,8 @@
 //                        adjoint (STC_GNN.py:24-29 applied to Gc).
 #include "stc_common.cuh"
 
+#include <algorithm>
+
 namespace stc {
 
 // ------------------------------------------------------------------------------------------------
@@ -98,6 +100,19 @@ support_dense_kernel(const float* __restrict__ G, int N, const float* __restrict
       Y[yi] = v;
       if (axpy_out) axpy_out[yi] = fmaf(axpy_coef, X[b * x_bs + (long long)m * W + col], axpy_out[yi]);
     }
+  }
+}
+
+// out[b][i] += coef * x[b * x_bs + i]  (16 bytes per thread and step; the Chebyshev adjoint's  ybar[k-2] -= ybar[k])
+__global__ void __launch_bounds__(256)
+axpy_rows_kernel(float* __restrict__ out, const float* __restrict__ x, long long x_bs, float coef, long long per_b4,
+                 long long total4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / per_b4, r = i - b * per_b4;
+    const float4 xv = *reinterpret_cast<const float4*>(x + b * x_bs + 4 * r);
+    float4 o = reinterpret_cast<float4*>(out)[i];
+    o.x = fmaf(coef, xv.x, o.x); o.y = fmaf(coef, xv.y, o.y); o.z = fmaf(coef, xv.z, o.z); o.w = fmaf(coef, xv.w, o.w);
+    reinterpret_cast<float4*>(out)[i] = o;
   }
 }
 
@@ -198,12 +213,25 @@ int launch_support_apply(const StcSupport& gs, int N, int B, int width, bool tra
       set_error("dense support without vals");
       return STC_ERR_BAD_ARG;
     }
-    if (axpy_out == nullptr) {
+    // the tensor-core kernels do not carry the fused "axpy_out += axpy_coef * x" of the Chebyshev adjoint (terms k >= 2):
+    // that update is elementwise and reads x before anything overwrites it, so it runs first as its own pass
+    const bool axpy_split = axpy_out != nullptr && width % 4 == 0 && x_bs % 4 == 0 && axpy_out != y && x != y &&
+                            (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(axpy_out) & 15) == 0;
+    if (axpy_out == nullptr || axpy_split) {
       bool handled = false;
+      if (axpy_split) {
+        const long long per_b4 = (long long)N * width / 4, total4 = per_b4 * B;
+        const int blocks = (int)std::min<long long>((total4 + 255) / 256, (long long)device_sm_count() * 16);
+        axpy_rows_kernel<<<blocks, 256, 0, st>>>(axpy_out, x, x_bs, axpy_coef, per_b4, total4);
+        STC_LAUNCH_OK("axpy_rows_kernel");
+      }
       STC_TRY(try_launch_support_tc(gs.vals, N, B, width, transpose, x, x_bs, z, z_bs, y, alpha, beta, st, &handled));
       if (handled) return STC_OK;
       STC_TRY(try_launch_support_tc_big(gs.vals, N, B, width, transpose, x, x_bs, z, z_bs, y, alpha, beta, st, &handled));
       if (handled) return STC_OK;
+      if (axpy_split) {   // neither tensor-core kernel took the product: the FFMA kernel runs it without its fused update
+        axpy_out = nullptr;
+      }
     }
     long long total_q = (long long)B * width;
     dim3 grid(ceil_div(total_q, SD_BQ), ceil_div(N, SD_BM));

@@ -220,20 +220,25 @@ def test_dense_support_wider_than_one_tile(N, B, shape):
 
 
 def test_dense_wide_support_cell_runs_on_the_tensor_core_kernels():
-    """A cell step on a dense N = 200 support (forward hops, adjoint hops, dGs) launches no FFMA support kernel."""
+    """A cell step with three Chebyshev terms on a dense N = 200 support (forward hops, adjoint hops including the
+    ybar[k-2] -= ybar[k] update, dGs) launches no FFMA support kernel and matches the oracle."""
     from stc_gnn_b200 import _lib
-    shape = (2, 200, 4, 16, 16, 2, 2)
+    shape = (2, 200, 4, 16, 16, 3, 2)
     B, N, C, Din, h, Ks, Kc = shape
     cfg = dict(B=B, N=N, C=C, Din=Din, h=h, Ks=Ks, Kc=Kc, activation=None)
     t = random_case(B, N, C, Din, h, Ks, Kc, seed=sum(shape))
+    Hn_o, g_o = oracle_cell_with_grads(t, cfg)
     _lib.timing_enable(True)
     _lib.timing_collect()
-    run_cuda_cell(t, cfg)
+    Hn, g = run_cuda_cell(t, cfg)
     torch.cuda.synchronize()
     _lib.timing_enable(False)
     kinds = _lib.timing_collect()
     assert "support_dense" not in kinds and "support_outer" not in kinds, kinds
-    assert kinds["tc_support_big"][1] >= 4 and kinds["tc_outer"][1] >= 2, kinds
+    assert kinds["tc_support_big"][1] >= 8 and kinds["tc_outer"][1] >= 4, kinds
+    O.assert_close(Hn, Hn_o, "Hn")
+    for k, v in g.items():
+        O.assert_close(v, g_o[k], k)
 
 
 # ---- size-independent properties at the benchmark's full size (SF shape, B = 1024) -----------------

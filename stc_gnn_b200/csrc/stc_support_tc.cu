@@ -499,9 +499,14 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
         uint8_t* lbp = Lring + (size_t)(seq % TO_SL) * hsz;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (r0 + 32 * i < rowsA) store_split4(hb, lbp, soff[i], *reinterpret_cast<const float4*>(hb + soff[i]));
-          if (r0 + 32 * i < rowsB)
-            store_split4(hb + p.imgA, lbp + p.imgA, soff[i], *reinterpret_cast<const float4*>(hb + p.imgA + soff[i]));
+          // both raw chunks are read before either is rewritten: the in-place stores would otherwise order the second
+          // load behind them (measured: 5.6 -> 6.6 ms per step when the two operands were converted one after the other)
+          const bool okA = r0 + 32 * i < rowsA, okB = r0 + 32 * i < rowsB;
+          float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+          if (okA) va = *reinterpret_cast<const float4*>(hb + soff[i]);
+          if (okB) vb = *reinterpret_cast<const float4*>(hb + p.imgA + soff[i]);
+          if (okA) store_split4(hb, lbp, soff[i], va);
+          if (okB) store_split4(hb + p.imgA, lbp + p.imgA, soff[i], vb);
         }
       }
       fence_async_smem();

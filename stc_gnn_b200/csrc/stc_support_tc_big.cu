@@ -51,25 +51,6 @@ struct TcSupBigPlan {
   uint32_t off_x, off_o, off_bar, smem_bytes, imgX;
 };
 
-// waiting with back-off: the epilogue warps wait for whole accumulation chains; a bare try_wait loop keeps issuing in
-// the schedulers they share with the producer and stager warps
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P1;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) break;
-    __nanosleep(128);
-  }
-}
-
 __global__ void __launch_bounds__(TB_THREADS, 1)
 tc_support_big_kernel(const float* __restrict__ G, const float* __restrict__ X, long long x_bs, const float* Z,
                       long long z_bs, float* Y, float alpha, float beta, const TcSupBigPlan p) {
@@ -286,7 +267,7 @@ tc_support_big_kernel(const float* __restrict__ G, const float* __restrict__ X, 
       for (int g = 0; g < ngroups; ++g, ++gi) {
 #pragma unroll 1
         for (int half = 0; half < TB_HALVES; ++half) {
-          mbar_wait_sleep(&accfull[half], (uint32_t)gi & 1u);
+          mbar_wait_backoff(&accfull[half], (uint32_t)gi & 1u, 128u);   // whole chains: always with back-off (stc_tc.cuh)
           fence_after_sync();
 #pragma unroll
           for (int hh = 0; hh < TB_NT / 16; ++hh) {

@@ -299,5 +299,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Waiting with back-off for warps that are AHEAD of the pipeline (producers waiting for a free stage, epilogue warps
+// waiting for a whole accumulation chain): a bare try_wait loop issues an instruction every ~3 cycles (measured on
+// tc_support_big, profiles/r4k_tc_support_big_ncu.txt: the four waiting epilogue warps executed as many instructions as
+// the eight working warps) in a scheduler it shares with working warps.  ns == 0 spins like mbar_wait.
+// (A/B on the one-tile kernels tc_support / tc_outer, whose waits are short: neutral at 0 / 32 / 128 ns --
+//  profiles/r4o_wait_backoff_ab.txt -- so they keep mbar_wait.)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns) __nanosleep(ns);
+  }
+}
+
 }  // namespace tc
 }  // namespace stc

@@ -13,7 +13,7 @@
 #   full:N:CFG:B[:stock|adam]  reference STCGNN + installed cell, DP over N GPUs (CFG = sf | longc)
 #   mainpy[:EPOCHS]  the reference's Main.py for EPOCHS epochs: stock cell | installed | installed + loop hygiene
 #   halo:N[:train]   tools/bench_halo.py on N GPUs         trace      clock64 phase trace of the gate convolutions
-#   memcheck         compute-sanitizer over the smallest parity case of every kernel family
+#   memcheck         compute-sanitizer over the smallest parity case of every kernel family (memcheck2: the dense N > 128 kernels)
 #   dense            tools/bench_dense_support.py: dense support with N > 128 (tcgen05 vs FFMA vs cuBLAS fp32)
 #   probe            what the box has (GPU, host cores / memory, reference probe)
 mkdir -p gpurun_out
@@ -98,6 +98,12 @@ for stage in "$@"; do
         "$P::test_inplace_and_returned_leaf_gradients_agree_and_lanes_do_not_change_results" \
         "tests/test_halo_gpu.py::test_row_subset_apply_and_halo_pack_unpack_kernels" "tests/test_halo_gpu.py::test_staged_cell_single_rank" \
         > gpurun_out/memcheck_$T.log 2>&1; echo "memcheck exit $?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|rror:" gpurun_out/memcheck_$T.log | head -12 ;;
+    memcheck2)   # the dense N > 128 kernels (tc_support_big, block-wise tc_outer, split axpy)
+      P=tests/test_cell_gpu.py
+      timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest -x -q \
+        "$P::test_dense_support_wider_than_one_tile[130-3-shape0]" "$P::test_dense_support_wider_than_one_tile[333-1-shape3]" \
+        "$P::test_cell_matches_oracle_dense[None-shape11]" "$P::test_dense_wide_support_cell_runs_on_the_tensor_core_kernels" \
+        > gpurun_out/memcheck2_$T.log 2>&1; echo "memcheck exit $?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|rror:" gpurun_out/memcheck2_$T.log | head -12 ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

@@ -345,6 +345,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // requested in place (raw -> hi in the landing zone, lo into a second, shorter ring), so no block-wide barrier is needed
 // between the copy and the conversion; warp 8 only issues MMAs, paced by full / done mbarriers.  TMEM: two slots of
 // [main | cross] used round-robin, drained into fp32 registers every `drain` atoms (bounded chains).
+// BLOCKS = false: the support fits one tile (n0 = m0 = 0, every row bound is N -- exactly the one-tile code);
+// BLOCKS = true: gridDim.y walks the 128 x 128 blocks of a larger support.
+template <bool BLOCKS>
 __global__ void __launch_bounds__(TO_THREADS, 1)
 tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __restrict__ Bm, float coef, float* dG,
                 const TcOuterPlan p) {
@@ -377,8 +380,9 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
   const int warp_u = uniform_warp_index();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
   // N > 128: this CTA owns the 128 x 128 block (n0.., m0..) of dGs; rows past the edge of an operand block stay zero
-  const int n0 = ((int)blockIdx.y / p.nblk) * 128, m0 = ((int)blockIdx.y % p.nblk) * 128;
-  const int rowsA = min(128, N - n0), rowsB = min(128, N - m0);
+  const int n0 = BLOCKS ? ((int)blockIdx.y / p.nblk) * 128 : 0, m0 = BLOCKS ? ((int)blockIdx.y % p.nblk) * 128 : 0;
+  const int rowsA = BLOCKS ? min(128, N - n0) : N, rowsB = BLOCKS ? min(128, N - m0) : N;
+  const int rows_both = BLOCKS ? min(rowsA, rowsB) : N;
   const int nsamples = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const long long natoms = (long long)nsamples * p.atoms_per_sample;
 
@@ -437,8 +441,13 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = r0 + 32 * i;
-            if (r < rowsA) cp_async16(base + soff[i], pa + (long long)r * W);
-            if (r < rowsB) cp_async16(base + p.imgA + soff[i], pb + (long long)r * W);
+            if (r < rows_both) {   // the common case (always, when the support fits one tile): one branch for both operands
+              cp_async16(base + soff[i], pa + (long long)r * W);
+              cp_async16(base + p.imgA + soff[i], pb + (long long)r * W);
+            } else {               // edge blocks of a large support: the operands have different row counts
+              if (r < rowsA) cp_async16(base + soff[i], pa + (long long)r * W);
+              if (r < rowsB) cp_async16(base + p.imgA + soff[i], pb + (long long)r * W);
+            }
           }
         }
         if (++cat == p.atoms_per_sample) {
@@ -501,12 +510,16 @@ tc_outer_kernel(const float* __restrict__ A, long long a_bs, const float* __rest
         for (int i = 0; i < 4; ++i) {
           // both raw chunks are read before either is rewritten: the in-place stores would otherwise order the second
           // load behind them (measured: 5.6 -> 6.6 ms per step when the two operands were converted one after the other)
-          const bool okA = r0 + 32 * i < rowsA, okB = r0 + 32 * i < rowsB;
-          float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-          if (okA) va = *reinterpret_cast<const float4*>(hb + soff[i]);
-          if (okB) vb = *reinterpret_cast<const float4*>(hb + p.imgA + soff[i]);
-          if (okA) store_split4(hb, lbp, soff[i], va);
-          if (okB) store_split4(hb + p.imgA, lbp + p.imgA, soff[i], vb);
+          if (r0 + 32 * i < rows_both) {
+            const float4 va = *reinterpret_cast<const float4*>(hb + soff[i]);
+            const float4 vb = *reinterpret_cast<const float4*>(hb + p.imgA + soff[i]);
+            store_split4(hb, lbp, soff[i], va);
+            store_split4(hb + p.imgA, lbp + p.imgA, soff[i], vb);
+          } else if (r0 + 32 * i < rowsA) {
+            store_split4(hb, lbp, soff[i], *reinterpret_cast<const float4*>(hb + soff[i]));
+          } else if (r0 + 32 * i < rowsB) {
+            store_split4(hb + p.imgA, lbp + p.imgA, soff[i], *reinterpret_cast<const float4*>(hb + p.imgA + soff[i]));
+          }
         }
       }
       fence_async_smem();
@@ -581,7 +594,8 @@ int try_launch_outer_tc(int N, int B, int width, const float* a, int64_t a_bs, c
   p.off_bar = (TO_SH + TO_SL) * hsz;
   p.smem_bytes = p.off_bar + 8 * (2 * TO_SH + 1) + 16;
   if (p.smem_bytes > 227 * 1024) return STC_OK;
-  STC_TRY(set_smem(tc_outer_kernel, p.smem_bytes));
+  auto kern = p.nblk > 1 ? tc_outer_kernel<true> : tc_outer_kernel<false>;
+  STC_TRY(set_smem(kern, p.smem_bytes));
   // one tile: the CTAs split the samples.  N > 128: one CTA per 128 x 128 block of dGs and sample slice -- as few slices
   // as still fill the device twice over (long K runs per CTA, one pass of vector reductions per CTA at the end)
   const int nblocks = p.nblk * p.nblk;
@@ -589,7 +603,7 @@ int try_launch_outer_tc(int N, int B, int width, const float* a, int64_t a_bs, c
   if (nblocks > 1) grid = (2 * grid + nblocks - 1) / nblocks;
   if (grid > B) grid = B;
   ScopedKernelTimer _t(KK_TC_OUTER, st, 4.0 * B * N * width * 2 + 4.0 * N * N);
-  tc_outer_kernel<<<dim3(grid, nblocks), TO_THREADS, p.smem_bytes, st>>>(a, a_bs, bmat, coef, dG, p);
+  kern<<<dim3(grid, nblocks), TO_THREADS, p.smem_bytes, st>>>(a, a_bs, bmat, coef, dG, p);
   STC_LAUNCH_OK("tc_outer_kernel");
   *handled = true;
   return STC_OK;

@@ -150,16 +150,35 @@ tc_support_big_kernel(const float* __restrict__ G, const float* __restrict__ X, 
         }
       }
     };
+    // the column (sample, feature) of this thread's chunk only changes with the tile: its two source pointers (one per
+    // half) are recomputed there, not per item (two 64-bit divisions per fetch were a third of this role's instructions)
+    long long src_tile = -1;
+    const float* src_h[TB_HALVES] = {nullptr, nullptr};
     auto fetch = [&](long long tile, int seg, int half, float4 (&r)[TB_SLOTS]) {
-      const long long cg = (tile / p.nmt) * TB_TW + half * TB_NT + c0;
-      const bool ok = tile < p.ntiles && cg < p.total_cols;     // W % 4 == 0: a chunk never straddles samples
-      const long long b = ok ? cg / W : 0;
-      const float* src = X + b * x_bs + (cg - b * W);
-      const int n0 = seg * TB_KS + r0;
+      if (tile != src_tile) {
+        src_tile = tile;
+        const long long cg0 = (tile / p.nmt) * TB_TW + c0;
 #pragma unroll
-      for (int i = 0; i < TB_SLOTS; ++i) {
-        const int n = n0 + 8 * i;
-        r[i] = (ok && n < N) ? __ldg(reinterpret_cast<const float4*>(src + (long long)n * W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int hf = 0; hf < TB_HALVES; ++hf) {
+          const long long cg = cg0 + hf * TB_NT;
+          const bool ok = tile < p.ntiles && cg < p.total_cols;   // W % 4 == 0: a chunk never straddles samples
+          const long long b = ok ? cg / W : 0;
+          src_h[hf] = ok ? X + b * x_bs + (cg - b * W) : nullptr;
+        }
+      }
+      const float* src = half == 0 ? src_h[0] : src_h[1];
+      const int n0 = seg * TB_KS + r0;
+      if (src != nullptr && n0 + 8 * (TB_SLOTS - 1) < N) {        // every row of the item in range: no per-row predicates
+        const float* s0 = src + (long long)n0 * W;
+#pragma unroll
+        for (int i = 0; i < TB_SLOTS; ++i) r[i] = __ldg(reinterpret_cast<const float4*>(s0 + (long long)(8 * i) * W));
+      } else {
+#pragma unroll
+        for (int i = 0; i < TB_SLOTS; ++i) {
+          const int n = n0 + 8 * i;
+          r[i] = (src != nullptr && n < N) ? __ldg(reinterpret_cast<const float4*>(src + (long long)n * W))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
     auto stage = [&](int xi, const float4 (&r)[TB_SLOTS]) {
@@ -195,8 +214,14 @@ tc_support_big_kernel(const float* __restrict__ G, const float* __restrict__ X, 
     const int ml = q * 32 + lane;                    // output node within the node tile
     const uint32_t tl = tmem_base + (uint32_t)TB_ACC_COLS + ((uint32_t)(q * 32) << 16);
     float ga[TB_KS];
+    long long m_tile = -1;
+    int m_cached = 0;
     auto fetch_a = [&](long long tile, int seg) {
-      const int m = (int)(tile % p.nmt) * 128 + ml;
+      if (tile != m_tile) {     // the 64-bit modulo only when the tile changes
+        m_tile = tile;
+        m_cached = (int)(tile % p.nmt) * 128 + ml;
+      }
+      const int m = m_cached;
       const int k0 = seg * TB_KS;
       const bool ok = m < N;
       if (ok && k0 + TB_KS <= N) {   // whole segment in range (every segment but the last): no per-element predicates
